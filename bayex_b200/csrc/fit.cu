@@ -1,0 +1,429 @@
+// GP fit path on the device: Gram build, Cholesky, T = L^-1, alpha, NLML, analytic gradient, clip + AdamW.
+// Replaces gp.py:41-57 (fit half of gaussian_process), gp.py:78-87 (neg_log_likelihood), gp.py:90-110 (posterior_fit).
+#include "internal.h"
+
+namespace bx {
+
+constexpr float kPriorNoise = -8.0f, kPriorAmp = 1.0f, kPriorLs = 1.0f;  // gp.py:83
+constexpr float kLog2Pi = 1.8378770664093453f;
+
+// raw hypers -> hyp[amp, noise, ymean(untouched), log2 amp], scale[k] = sqrt(log2 e)/softplus(ls_raw[k])   (gp.py:41,45)
+__global__ void hyp_prepare_kernel(const float* __restrict__ raw, int d, int d4, float* hyp, float* scale) {
+  const int t = threadIdx.x;
+  if (t == 0) {
+    const float amp = softplus_f(raw[1]);
+    hyp[HYP_NOISE] = softplus_f(raw[0]);
+    hyp[HYP_AMP] = amp;
+    hyp[HYP_LOG2AMP] = log2f(amp);
+  }
+  for (int k = t; k < d4; k += blockDim.x) scale[k] = (k < d) ? kSqrtLog2e / softplus_f(raw[2 + k]) : 0.f;
+}
+
+// U[i][k] = X[i][k] * scale[k] for i < n, zero padding elsewhere.
+__global__ void scale_obs_kernel(const float* __restrict__ X, int n, int d, int np, int d4, const float* __restrict__ scale,
+                                 float* U) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= np * d4) return;
+  const int i = e / d4, k = e % d4;
+  U[e] = (i < n && k < d) ? X[(size_t)i * d + k] * scale[k] : 0.f;
+}
+
+// ymean = mean(y[:n]) (gp.py:43), yc = y - ymean (gp.py:44), zero padded.  Single block, fixed reduction order.
+__global__ void __launch_bounds__(1024) center_y_kernel(const float* __restrict__ y, int n, int np, float* yc, float* hyp) {
+  __shared__ float red[32];
+  __shared__ float mean_s;
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) acc += y[i];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.f;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) { mean_s = v / (float)n; hyp[HYP_YMEAN] = mean_s; }
+  }
+  __syncthreads();
+  const float m = mean_s;
+  for (int i = threadIdx.x; i < np; i += blockDim.x) yc[i] = (i < n) ? y[i] - m : 0.f;
+}
+
+// K = amp * exp(-|u_i - u_j|^2) + (noise + 1e-6) I  on the valid block, identity on the padding (gp.py:46).
+// 32x32 output tile per block; observation rows staged in shared memory; coalesced row stores.
+__global__ void __launch_bounds__(256) gram_kernel(const float* __restrict__ U, int n, int np, int d4,
+                                                   const float* __restrict__ hyp, float* K, int ld) {
+  extern __shared__ float sm[];
+  float* Ui = sm;                  // [32][d4+1]
+  float* Uj = sm + 32 * (d4 + 1);  // [32][d4+1]
+  const int i0 = blockIdx.y * 32, j0 = blockIdx.x * 32, tid = threadIdx.x;
+  for (int e = tid; e < 32 * d4; e += 256) {
+    const int r = e / d4, k = e % d4;
+    Ui[r * (d4 + 1) + k] = U[(size_t)(i0 + r) * d4 + k];
+    Uj[r * (d4 + 1) + k] = U[(size_t)(j0 + r) * d4 + k];
+  }
+  __syncthreads();
+  const float amp = hyp[HYP_AMP], diag = hyp[HYP_NOISE] + kJitter;
+  const int c = tid & 31;
+  for (int r = tid >> 5; r < 32; r += 8) {
+    const int i = i0 + r, j = j0 + c;
+    float s = 0.f;
+    for (int k = 0; k < d4; ++k) {
+      const float df = Ui[r * (d4 + 1) + k] - Uj[c * (d4 + 1) + k];
+      s = fmaf(df, df, s);
+    }
+    float v;
+    if (i < n && j < n) v = amp * exp2f(-s) + (i == j ? diag : 0.f);
+    else v = (i == j) ? 1.f : 0.f;
+    K[(size_t)i * ld + j] = v;
+  }
+}
+
+// quad = |v|^2 (v = T yc), logdet = sum of per-block parts, NLML (gp.py:52-57 on the compacted rows).
+__global__ void __launch_bounds__(256) nlml_kernel(const float* __restrict__ v, int np, const float* __restrict__ logdet_part,
+                                                   int nb, int n, float* hyp, const int* status) {
+  __shared__ float red[8];
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < np; i += 256) acc = fmaf(v[i], v[i], acc);
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float quad = 0.f;
+    for (int w = 0; w < 8; ++w) quad += red[w];
+    float logdet = 0.f;
+    for (int b = 0; b < nb; ++b) logdet += logdet_part[b];
+    const float amp = hyp[HYP_AMP], la = logf(amp);
+    float nl = 0.5f * quad + logdet;            // gp.py:52-53  (masked rows are compacted away: :54 vanishes)
+    nl += ((float)n * 0.5f) * kLog2Pi;          // gp.py:55
+    nl += -0.5f * kLog2Pi - la - la * la;       // gp.py:56
+    hyp[HYP_QUAD] = quad; hyp[HYP_LOGDET] = logdet; hyp[HYP_NLML] = nl;
+    hyp[HYP_STATUS] = (float)status[0];
+  }
+}
+
+// Padded diagonal of T <- 0 (so padded observations contribute nothing to V), optional TF32 head/tail split.
+__global__ void finalize_T_kernel(float* T, int n, int np, float* Thi, float* Tlo) {
+  const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (size_t)np * np) return;
+  const int i = (int)(e / np), j = (int)(e % np);
+  float t = T[e];
+  if (i >= n || j >= n) { t = 0.f; T[e] = 0.f; }
+  if (Thi) {
+    const float hi = __uint_as_float(__float_as_uint(t) & 0xFFFFE000u);  // 10-bit mantissa: exact in TF32
+    Thi[e] = hi;
+    Tlo[e] = t - hi;
+  }
+}
+
+// Gradient contraction over the lower triangle of W = K^-1 - alpha alpha^T  (SURVEY 8.A3):
+//   part[blk] = { tr(W), sum W_ij C_ij, sum W_ij C_ij (u_ik - u_jk)^2  (k < d) }   (off-diagonal pairs counted twice)
+__global__ void __launch_bounds__(256) grad_contract_kernel(const float* __restrict__ Kinv, int ld, const float* __restrict__ alpha,
+                                                            const float* __restrict__ U, int n, int d, int d4, float* part) {
+  extern __shared__ float sm[];
+  float* Ui = sm;
+  float* Uj = sm + 32 * (d4 + 1);
+  __shared__ float red[8];
+  // linear lower-triangular tile index -> (bi, bj), bj <= bi
+  const int t = blockIdx.x;
+  int bi = (int)((sqrtf(8.f * (float)t + 1.f) - 1.f) * 0.5f);
+  while ((bi + 1) * (bi + 2) / 2 <= t) ++bi;
+  while (bi * (bi + 1) / 2 > t) --bi;
+  const int bj = t - bi * (bi + 1) / 2;
+  const int i0 = bi * 32, j0 = bj * 32, tid = threadIdx.x;
+  for (int e = tid; e < 32 * d4; e += 256) {
+    const int r = e / d4, k = e % d4;
+    Ui[r * (d4 + 1) + k] = U[(size_t)(i0 + r) * d4 + k];
+    Uj[r * (d4 + 1) + k] = U[(size_t)(j0 + r) * d4 + k];
+  }
+  __syncthreads();
+  const int c = tid & 31, r0 = tid >> 5;
+  float wc[4], tr = 0.f, samp = 0.f;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int r = r0 + q * 8, i = i0 + r, j = j0 + c;
+    wc[q] = 0.f;
+    if (i < n && j < n && j <= i) {
+      const float w = Kinv[(size_t)i * ld + j] - alpha[i] * alpha[j];
+      float s = 0.f;
+      for (int k = 0; k < d4; ++k) {
+        const float df = Ui[r * (d4 + 1) + k] - Uj[c * (d4 + 1) + k];
+        s = fmaf(df, df, s);
+      }
+      if (i == j) tr += w;
+      wc[q] = w * exp2f(-s) * (i == j ? 1.f : 2.f);
+      samp += wc[q];
+    }
+  }
+  float* out = part + (size_t)blockIdx.x * (d + 2);
+  for (int slot = 0; slot < d + 2; ++slot) {
+    float v;
+    if (slot == 0) v = tr;
+    else if (slot == 1) v = samp;
+    else {
+      const int k = slot - 2;
+      v = 0.f;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int r = r0 + q * 8;
+        const float df = Ui[r * (d4 + 1) + k] - Uj[c * (d4 + 1) + k];
+        v = fmaf(wc[q], df * df, v);
+      }
+    }
+    v = warp_sum(v);
+    __syncthreads();
+    if ((tid & 31) == 0) red[tid >> 5] = v;
+    __syncthreads();
+    if (tid == 0) {
+      float tot = 0.f;
+      for (int w = 0; w < 8; ++w) tot += red[w];
+      out[slot] = tot;
+    }
+  }
+}
+
+// Sum the per-tile partials (fixed order), apply the chain rule; gbuf = [nlml, loss, dloss/draw (d+2), dnlml/draw (d+2)].
+__global__ void __launch_bounds__(256) grad_finalize_kernel(const float* __restrict__ part, int ntiles, int d,
+                                                            const float* __restrict__ raw, const float* __restrict__ hyp,
+                                                            float* gbuf) {
+  __shared__ float red[8];
+  __shared__ float sums[BX_MAX_D + 2];
+  for (int slot = 0; slot < d + 2; ++slot) {
+    float acc = 0.f;
+    for (int t = threadIdx.x; t < ntiles; t += 256) acc += part[(size_t)t * (d + 2) + slot];
+    acc = warp_sum(acc);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float tot = 0.f;
+      for (int w = 0; w < 8; ++w) tot += red[w];
+      sums[slot] = tot;
+    }
+  }
+  __syncthreads();
+  const float amp = hyp[HYP_AMP];
+  float prior = 0.f;
+  for (int p = threadIdx.x; p < d + 2; p += 256) {
+    float g;  // d NLML / d raw_p
+    if (p == 0) g = 0.5f * sums[0] * sigmoid_f(raw[0]);
+    else if (p == 1) {
+      const float la = logf(amp);
+      g = (0.5f * sums[1] - 1.f / amp - 2.f * la / amp) * sigmoid_f(raw[1]);
+    } else {
+      const float ls = softplus_f(raw[p]);
+      // d/dls exp(-(dx/ls)^2) = exp(.) 2 (dx/ls)^2 / ls ;  (u_i-u_j)^2 = log2e (dx/ls)^2
+      g = 0.5f * amp * sums[p] * (2.f / (kLog2e * ls)) * sigmoid_f(raw[p]);
+    }
+    const float pr = (p == 0) ? kPriorNoise : (p == 1 ? kPriorAmp : kPriorLs);
+    gbuf[2 + (d + 2) + p] = g;
+    gbuf[2 + p] = -g + (raw[p] - pr);  // gp.py:78-87: loss = -(NLML - 1/2 sum (raw - prior)^2)
+  }
+  if (threadIdx.x == 0) {
+    for (int p = 0; p < d + 2; ++p) {
+      const float pr = (p == 0) ? kPriorNoise : (p == 1 ? kPriorAmp : kPriorLs);
+      prior += (raw[p] - pr) * (raw[p] - pr);
+    }
+    gbuf[0] = hyp[HYP_NLML];
+    gbuf[1] = -(hyp[HYP_NLML] - 0.5f * prior);
+  }
+}
+
+// clip_by_global_norm(10) + adamw(lr) on the d+2 raw hypers (gp.py:99,105-106).  adam = [m | v | t].
+__global__ void adamw_kernel(float* raw, const float* __restrict__ gbuf, int d, float lr, float* adam, float* trace,
+                             int step) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const int P = d + 2;
+  float* m = adam;
+  float* v = adam + P;
+  float* tcount = adam + 2 * P;
+  if (trace)
+    for (int p = 0; p < P; ++p) trace[(size_t)step * P + p] = raw[p];
+  float gn = 0.f;
+  for (int p = 0; p < P; ++p) gn = fmaf(gbuf[2 + p], gbuf[2 + p], gn);
+  gn = sqrtf(gn);
+  const float t = tcount[0] + 1.f;
+  tcount[0] = t;
+  const float c1 = 1.f - powf(0.9f, t), c2 = 1.f - powf(0.999f, t);
+  for (int p = 0; p < P; ++p) {
+    float g = gbuf[2 + p];
+    if (!(gn < 10.f)) g = g / gn * 10.f;
+    m[p] = 0.9f * m[p] + 0.1f * g;
+    v[p] = 0.999f * v[p] + 0.001f * g * g;
+    const float u = (m[p] / c1) / (sqrtf(v[p] / c2) + 1e-8f) + 1e-4f * raw[p];
+    raw[p] = raw[p] - lr * u;
+  }
+}
+
+FitWs carve_fit_ws(void* base, int n, int d) {
+  FitWs w{};
+  w.np = round_up(n, BX_TILE);
+  w.d4 = round_up(d, 4);
+  w.nb = w.np / NB;
+  const int t32 = w.np / 32;
+  w.ntiles = t32 * (t32 + 1) / 2;
+  size_t off = 0;
+  auto take = [&](size_t nfloat) {
+    float* p = base ? reinterpret_cast<float*>(reinterpret_cast<char*>(base) + off) : nullptr;
+    off += (nfloat * sizeof(float) + 255) / 256 * 256;
+    return p;
+  };
+  w.A = take((size_t)w.np * w.np);
+  w.TMP = take((size_t)w.np * w.np);
+  w.Dinv = take((size_t)w.nb * NB * NB);
+  w.logdet_part = take(w.nb);
+  w.yc = take(w.np);
+  w.v = take(w.np);
+  w.alpha = take(w.np);
+  w.U = take((size_t)w.np * w.d4);
+  w.scale = take(w.d4);
+  w.hyp = take(8);
+  w.part = take((size_t)w.ntiles * (d + 2));
+  w.gbuf = take(2 + 2 * (d + 2));
+  w.adam = take(2 * (d + 2) + 1);
+  w.status = reinterpret_cast<int*>(take(1));
+  w.bytes = off;
+  return w;
+}
+
+int32_t launch_factor(cudaStream_t s, const float* d_X, const float* d_y, int n, int d, const float* d_raw, FitWs& w,
+                      float* T_out, float* U_out, float* alpha_out, float* scale_out, float* hyp_out) {
+  float* T = T_out ? T_out : w.A;
+  float* U = U_out ? U_out : w.U;
+  float* alpha = alpha_out ? alpha_out : w.alpha;
+  float* scale = scale_out ? scale_out : w.scale;
+  float* hyp = hyp_out ? hyp_out : w.hyp;
+  const int np = w.np, d4 = w.d4;
+  BX_CUDA(cudaMemsetAsync(w.status, 0, sizeof(int), s));
+  hyp_prepare_kernel<<<1, 64, 0, s>>>(d_raw, d, d4, hyp, scale);
+  BX_LAUNCH_CHECK();
+  scale_obs_kernel<<<(np * d4 + 255) / 256, 256, 0, s>>>(d_X, n, d, np, d4, scale, U);
+  BX_LAUNCH_CHECK();
+  center_y_kernel<<<1, 1024, 0, s>>>(d_y, n, np, w.yc, hyp);
+  BX_LAUNCH_CHECK();
+  const size_t gsm = 2 * 32 * (d4 + 1) * sizeof(float);
+  gram_kernel<<<dim3(np / 32, np / 32), 256, gsm, s>>>(U, n, np, d4, hyp, T, np);
+  BX_LAUNCH_CHECK();
+  int32_t rc = cholesky_inplace(s, T, np, np, w.Dinv, w.logdet_part, w.status);
+  if (rc) return rc;
+  rc = tri_inverse_inplace(s, T, np, np, w.Dinv, w.TMP);
+  if (rc) return rc;
+  rc = trmv_lower(s, T, np, np, w.yc, w.v);
+  if (rc) return rc;
+  rc = trmv_lower_t(s, T, np, np, w.v, alpha);
+  if (rc) return rc;
+  nlml_kernel<<<1, 256, 0, s>>>(w.v, np, w.logdet_part, w.nb, n, hyp, w.status);
+  BX_LAUNCH_CHECK();
+  return 0;
+}
+
+// One NLML + gradient evaluation at d_raw; leaves gbuf filled.  Uses ws.A for T and ws.TMP for K^-1.
+static int32_t launch_grad(cudaStream_t s, const float* d_X, const float* d_y, int n, int d, const float* d_raw, FitWs& w) {
+  int32_t rc = launch_factor(s, d_X, d_y, n, d, d_raw, w, nullptr, nullptr, nullptr, nullptr, nullptr);
+  if (rc) return rc;
+  GemmArgs g{};  // K^-1 = T^T T on the lower 64x64 tiles
+  g.A = w.A; g.lda = w.np; g.B = w.A; g.ldb = w.np; g.C = w.TMP; g.ldc = w.np;
+  g.M = g.N = g.K = w.np; g.alpha = 1.f; g.beta = 0.f; g.kmode = KM_TN_BOTH; g.lower_only = 1;
+  rc = gemm(s, true, false, g);
+  if (rc) return rc;
+  const size_t gsm = 2 * 32 * (w.d4 + 1) * sizeof(float);
+  grad_contract_kernel<<<w.ntiles, 256, gsm, s>>>(w.TMP, w.np, w.alpha, w.U, n, d, w.d4, w.part);
+  BX_LAUNCH_CHECK();
+  grad_finalize_kernel<<<1, 256, 0, s>>>(w.part, w.ntiles, d, d_raw, w.hyp, w.gbuf);
+  BX_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace bx
+
+using namespace bx;
+
+extern "C" size_t bx_fit_workspace_bytes(int32_t n, int32_t d) {
+  if (n <= 0 || d <= 0 || d > BX_MAX_D) return 0;
+  return carve_fit_ws(nullptr, n, d).bytes;
+}
+
+static int32_t check_fit_args(const void* X, const void* y, int32_t n, int32_t d, const void* raw, void* ws, size_t ws_bytes) {
+  BX_CHECK_ARG(X && y && raw && ws, BX_E_ARG, "null pointer argument");
+  BX_CHECK_ARG(n > 0 && d > 0, BX_E_ARG, "n and d must be positive (n=%d d=%d)", n, d);
+  BX_CHECK_ARG(d <= BX_MAX_D, BX_E_RANGE, "d=%d exceeds BX_MAX_D=%d", d, BX_MAX_D);
+  BX_CHECK_ARG(ws_bytes >= bx_fit_workspace_bytes(n, d), BX_E_WORKSPACE, "workspace too small: %zu < %zu", ws_bytes,
+               bx_fit_workspace_bytes(n, d));
+  return 0;
+}
+
+extern "C" int32_t bx_nlml_grad(const float* d_X, const float* d_y, int32_t n, int32_t d, const float* d_raw, float* d_out,
+                                void* d_ws, size_t ws_bytes, void* stream) {
+  int32_t rc = check_fit_args(d_X, d_y, n, d, d_raw, d_ws, ws_bytes);
+  if (rc) return rc;
+  BX_CHECK_ARG(d_out, BX_E_ARG, "null output");
+  cudaStream_t s = (cudaStream_t)stream;
+  FitWs w = carve_fit_ws(d_ws, n, d);
+  rc = launch_grad(s, d_X, d_y, n, d, d_raw, w);
+  if (rc) return rc;
+  BX_CUDA(cudaMemcpyAsync(d_out, w.gbuf, sizeof(float) * (2 + 2 * (d + 2)), cudaMemcpyDeviceToDevice, s));
+  return 0;
+}
+
+extern "C" int32_t bx_fit_adamw(const float* d_X, const float* d_y, int32_t n, int32_t d, float* d_raw, float lr,
+                                int32_t steps, float* d_trace, void* d_ws, size_t ws_bytes, int32_t use_graph,
+                                void* stream) {
+  int32_t rc = check_fit_args(d_X, d_y, n, d, d_raw, d_ws, ws_bytes);
+  if (rc) return rc;
+  BX_CHECK_ARG(steps >= 0, BX_E_ARG, "steps must be >= 0");
+  cudaStream_t s = (cudaStream_t)stream;
+  FitWs w = carve_fit_ws(d_ws, n, d);
+  BX_CUDA(cudaMemsetAsync(w.adam, 0, sizeof(float) * (2 * (d + 2) + 1), s));  // fresh moments per call (gp.py:100)
+  if (steps == 0) return 0;
+  if (use_graph && !d_trace) {
+    // One step is captured once and replayed `steps` times: the loop never returns to the host.
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    BX_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+    rc = launch_grad(s, d_X, d_y, n, d, d_raw, w);
+    if (rc == 0) {
+      adamw_kernel<<<1, 32, 0, s>>>(d_raw, w.gbuf, d, lr, w.adam, nullptr, 0);
+      cudaError_t le = cudaGetLastError();
+      if (le != cudaSuccess) { set_error("adamw launch failed: %s", cudaGetErrorString(le)); rc = (int32_t)le; }
+    }
+    cudaError_t ce = cudaStreamEndCapture(s, &graph);
+    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+    BX_CUDA(ce);
+    BX_CUDA(cudaGraphInstantiate(&exec, graph, 0));
+    for (int i = 0; i < steps; ++i) {
+      cudaError_t e = cudaGraphLaunch(exec, s);
+      if (e != cudaSuccess) {
+        set_error("cudaGraphLaunch failed: %s", cudaGetErrorString(e));
+        cudaGraphExecDestroy(exec); cudaGraphDestroy(graph);
+        return (int32_t)e;
+      }
+    }
+    // The exec object must outlive its queued launches.
+    BX_CUDA(cudaStreamSynchronize(s));
+    cudaGraphExecDestroy(exec);
+    cudaGraphDestroy(graph);
+    return 0;
+  }
+  for (int i = 0; i < steps; ++i) {
+    rc = launch_grad(s, d_X, d_y, n, d, d_raw, w);
+    if (rc) return rc;
+    adamw_kernel<<<1, 32, 0, s>>>(d_raw, w.gbuf, d, lr, w.adam, d_trace, i);
+    BX_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+extern "C" int32_t bx_factor_build(const float* d_X, const float* d_y, int32_t n, int32_t d, const float* d_raw,
+                                   float* d_U, float* d_T, float* d_Thi, float* d_Tlo, float* d_alpha, float* d_scale,
+                                   float* d_hyp, void* d_ws, size_t ws_bytes, void* stream) {
+  int32_t rc = check_fit_args(d_X, d_y, n, d, d_raw, d_ws, ws_bytes);
+  if (rc) return rc;
+  BX_CHECK_ARG(d_U && d_T && d_alpha && d_scale && d_hyp, BX_E_ARG, "null factor output");
+  BX_CHECK_ARG((d_Thi == nullptr) == (d_Tlo == nullptr), BX_E_ARG, "Thi and Tlo must be given together");
+  cudaStream_t s = (cudaStream_t)stream;
+  FitWs w = carve_fit_ws(d_ws, n, d);
+  rc = launch_factor(s, d_X, d_y, n, d, d_raw, w, d_T, d_U, d_alpha, d_scale, d_hyp);
+  if (rc) return rc;
+  const size_t tot = (size_t)w.np * w.np;
+  finalize_T_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(d_T, n, w.np, d_Thi, d_Tlo);
+  BX_LAUNCH_CHECK();
+  return 0;
+}

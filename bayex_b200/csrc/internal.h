@@ -1,0 +1,71 @@
+// Internal (non-ABI) declarations shared between the .cu translation units.
+#pragma once
+#include "common.cuh"
+
+namespace bx {
+
+constexpr int NB = 64;  // linear-algebra block size (Cholesky panel, GEMM tile)
+
+// K-range restriction of one 64x64 output tile at (i0, j0); exploits triangular operands.
+enum KMode {
+  KM_FULL = 0,
+  KM_A_LOWER = 1,   // A lower triangular (NN): k < i0 + 64
+  KM_B_LOWER = 2,   // B lower triangular (NN): k >= j0
+  KM_TN_BOTH = 3,   // A^T B with both lower triangular: k >= max(i0, j0)
+  KM_TN_A = 4,      // A^T B with A lower triangular: k >= i0
+};
+
+struct GemmArgs {
+  const float* A;
+  const float* B;
+  float* C;
+  int lda, ldb, ldc;
+  int M, N, K;  // multiples of 64
+  float alpha, beta;
+  int kmode;
+  int lower_only;  // compute only tiles with i0 >= j0
+  // tree-batched mode for the recursive triangular inverse (tree_nb > 0): blockIdx.z = node of `tree_level`
+  int tree_nb, tree_level, tree_pass;
+};
+
+// C = alpha * op(A) * op(B) + beta * C on the SIMT fp32 pipes (row-major, 64x64x16 tiles).
+int32_t gemm(cudaStream_t s, bool ta, bool tb, const GemmArgs& g, int grid_z = 1);
+
+// In-place lower Cholesky of the np x np matrix A (row-major, lda); also the inverses of the 64x64 diagonal blocks
+// (Dinv [np/64][64][64]) and per-block sum(log diag) (logdet_part [np/64]).  status[0] |= 1 on a bad pivot.
+int32_t cholesky_inplace(cudaStream_t s, float* A, int np, int lda, float* Dinv, float* logdet_part, int* status);
+// In place L -> T = L^-1 (upper triangle zeroed), using Dinv from cholesky_inplace and a np x np scratch matrix.
+int32_t tri_inverse_inplace(cudaStream_t s, float* A, int np, int lda, const float* Dinv, float* TMP);
+// out = T * x (lower) and out = T^T * x
+int32_t trmv_lower(cudaStream_t s, const float* T, int np, int ld, const float* x, float* out);
+int32_t trmv_lower_t(cudaStream_t s, const float* T, int np, int ld, const float* x, float* out);
+
+// Workspace carve-up for the fit path.
+struct FitWs {
+  float *A, *TMP, *Dinv, *logdet_part, *yc, *v, *alpha, *U, *scale, *hyp, *part, *gbuf, *adam;
+  int* status;
+  int np, d4, nb, ntiles;
+  size_t bytes;
+};
+FitWs carve_fit_ws(void* base, int n, int d);
+
+// One evaluation of the posterior factor from raw hypers: fills A(=T), alpha, U, scale, hyp.  If T_out != nullptr the
+// factor is built directly in T_out instead of ws.A.
+int32_t launch_factor(cudaStream_t s, const float* d_X, const float* d_y, int n, int d, const float* d_raw, FitWs& w,
+                      float* T_out, float* U_out, float* alpha_out, float* scale_out, float* hyp_out);
+
+// Arguments of the scoring kernels (both engines).
+struct ScoreArgs {
+  bx_factor_t f;
+  const float* cand;  // explicit candidates [M x d] (GEN == false)
+  uint64_t m_begin, m_count;
+  int acq_id;
+  float acq_param, ystar;
+  float* mu;
+  float* sigma;
+  float* acq;
+  unsigned long long* best;
+  uint64_t index_base;
+};
+
+}  // namespace bx

@@ -1,0 +1,286 @@
+// Dense fp32 linear algebra for the fit path (gp.py:46-49 and its gradient): SIMT GEMM, blocked Cholesky, recursive
+// triangular inverse, triangular mat-vecs.  Tensor cores are deliberately not used here (north star: only the
+// candidate contraction may use them).
+#include <stdarg.h>
+
+#include "internal.h"
+
+namespace bx {
+
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+const char* last_error() { return g_err; }
+
+// ------------------------------------------------------------------------------------------------------------------
+// 64x64x16 SIMT GEMM.  256 threads, 4x4 register tile per thread.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int GT = 64, GK = 16, GP = GT + 4;
+
+__device__ __forceinline__ void tree_node(int nb, int level, int z, int& lo, int& mid, int& hi) {
+  lo = 0;
+  hi = nb;
+  for (int b = level - 1; b >= 0; --b) {
+    int m = (lo + hi) >> 1;
+    if ((z >> b) & 1) lo = m; else hi = m;
+  }
+  mid = (lo + hi) >> 1;
+}
+
+template <bool TA, bool TB>
+__global__ void __launch_bounds__(256) gemm64_kernel(GemmArgs g) {
+  __shared__ __align__(16) float As[GK][GP];
+  __shared__ __align__(16) float Bs[GK][GP];
+  const float* A = g.A;
+  const float* B = g.B;
+  float* C = g.C;
+  int M = g.M, N = g.N, K = g.K, kmode = g.kmode;
+  float alpha = g.alpha;
+  if (g.tree_nb > 0) {
+    int lo, mid, hi;
+    tree_node(g.tree_nb, g.tree_level, blockIdx.z, lo, mid, hi);
+    if (hi - lo < 2) return;
+    if (g.tree_pass == 1) {  // TMP[mid:hi, lo:mid] = L[mid:hi, lo:mid] * T[lo:mid, lo:mid]
+      A += (size_t)mid * NB * g.lda + (size_t)lo * NB;
+      B += (size_t)lo * NB * g.ldb + (size_t)lo * NB;
+      C += (size_t)mid * NB * g.ldc + (size_t)lo * NB;
+      M = (hi - mid) * NB; N = K = (mid - lo) * NB; kmode = KM_B_LOWER; alpha = 1.f;
+    } else {                 // T[mid:hi, lo:mid] = -T[mid:hi, mid:hi] * TMP[mid:hi, lo:mid]
+      A += (size_t)mid * NB * g.lda + (size_t)mid * NB;
+      B += (size_t)mid * NB * g.ldb + (size_t)lo * NB;
+      C += (size_t)mid * NB * g.ldc + (size_t)lo * NB;
+      M = K = (hi - mid) * NB; N = (mid - lo) * NB; kmode = KM_A_LOWER; alpha = -1.f;
+    }
+  }
+  const int i0 = blockIdx.y * GT, j0 = blockIdx.x * GT;
+  if (i0 >= M || j0 >= N) return;
+  if (g.lower_only && j0 > i0) return;
+  int k_lo = 0, k_hi = K;
+  if (kmode == KM_A_LOWER) k_hi = min(K, i0 + GT);
+  else if (kmode == KM_B_LOWER) k_lo = j0;
+  else if (kmode == KM_TN_BOTH) k_lo = max(i0, j0);
+  else if (kmode == KM_TN_A) k_lo = i0;
+
+  const int tid = threadIdx.x, rg = tid & 15, cg = tid >> 4;
+  float acc[4][4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
+
+  for (int k0 = k_lo; k0 < k_hi; k0 += GK) {
+    if (!TA) {  // A is [M x K]
+      const int r = tid >> 2, kk = (tid & 3) * 4;
+      const float4 v = *reinterpret_cast<const float4*>(A + (size_t)(i0 + r) * g.lda + k0 + kk);
+      As[kk + 0][r] = v.x; As[kk + 1][r] = v.y; As[kk + 2][r] = v.z; As[kk + 3][r] = v.w;
+    } else {    // A is [K x M]
+      const int kk = tid >> 4, m = (tid & 15) * 4;
+      *reinterpret_cast<float4*>(&As[kk][m]) = *reinterpret_cast<const float4*>(A + (size_t)(k0 + kk) * g.lda + i0 + m);
+    }
+    if (!TB) {  // B is [K x N]
+      const int kk = tid >> 4, n = (tid & 15) * 4;
+      *reinterpret_cast<float4*>(&Bs[kk][n]) = *reinterpret_cast<const float4*>(B + (size_t)(k0 + kk) * g.ldb + j0 + n);
+    } else {    // B is [N x K]
+      const int r = tid >> 2, kk = (tid & 3) * 4;
+      const float4 v = *reinterpret_cast<const float4*>(B + (size_t)(j0 + r) * g.ldb + k0 + kk);
+      Bs[kk + 0][r] = v.x; Bs[kk + 1][r] = v.y; Bs[kk + 2][r] = v.z; Bs[kk + 3][r] = v.w;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < GK; ++kk) {
+      const float4 a = *reinterpret_cast<const float4*>(&As[kk][rg * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&Bs[kk][cg * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[r][c] = fmaf(av[r], bv[c], acc[r][c]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    float* cp = C + (size_t)(i0 + rg * 4 + r) * g.ldc + j0 + cg * 4;
+    float4 o = make_float4(alpha * acc[r][0], alpha * acc[r][1], alpha * acc[r][2], alpha * acc[r][3]);
+    if (g.beta != 0.f) {
+      const float4 c = *reinterpret_cast<const float4*>(cp);
+      o.x = fmaf(g.beta, c.x, o.x); o.y = fmaf(g.beta, c.y, o.y); o.z = fmaf(g.beta, c.z, o.z); o.w = fmaf(g.beta, c.w, o.w);
+    }
+    *reinterpret_cast<float4*>(cp) = o;
+  }
+}
+
+int32_t gemm(cudaStream_t s, bool ta, bool tb, const GemmArgs& g, int grid_z) {
+  dim3 grid(g.N / GT, g.M / GT, grid_z);
+  if (grid.x == 0 || grid.y == 0) return 0;
+  if (!ta && !tb) gemm64_kernel<false, false><<<grid, 256, 0, s>>>(g);
+  else if (ta && !tb) gemm64_kernel<true, false><<<grid, 256, 0, s>>>(g);
+  else if (!ta && tb) gemm64_kernel<false, true><<<grid, 256, 0, s>>>(g);
+  else gemm64_kernel<true, true><<<grid, 256, 0, s>>>(g);
+  BX_LAUNCH_CHECK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Diagonal-block factorisation: L_kk = chol(A_kk) in shared memory, plus L_kk^-1 and sum(log diag).
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) potrf_diag_kernel(float* A, int lda, int kb, float* Dinv, float* logdet_part,
+                                                         int* status) {
+  __shared__ float S[NB][NB + 1];
+  __shared__ float X[NB][NB + 1];
+  const int tid = threadIdx.x;
+  float* blk = A + (size_t)kb * NB * lda + (size_t)kb * NB;
+  for (int e = tid; e < NB * NB; e += 256) {
+    const int r = e >> 6, c = e & 63;
+    S[r][c] = (c <= r) ? blk[(size_t)r * lda + c] : 0.f;
+    X[r][c] = 0.f;
+  }
+  __syncthreads();
+  for (int j = 0; j < NB; ++j) {
+    if (tid == 0) {
+      const float dj = S[j][j];
+      if (!(dj > 0.f) || !(dj < CUDART_INF_F)) atomicOr(status, 1);
+      S[j][j] = sqrtf(dj);
+    }
+    __syncthreads();
+    const float inv = 1.f / S[j][j];
+    if (tid > j && tid < NB) S[tid][j] *= inv;
+    __syncthreads();
+    const int rem = NB - 1 - j;  // trailing square (j+1..63)^2, lower part only
+    for (int e = tid; e < rem * rem; e += 256) {
+      const int r = j + 1 + e / rem, c = j + 1 + e % rem;
+      if (c <= r) S[r][c] = fmaf(-S[r][j], S[c][j], S[r][c]);
+    }
+    __syncthreads();
+  }
+  // inverse by forward substitution, one column per thread
+  if (tid < NB) {
+    const int c = tid;
+    X[c][c] = 1.f / S[c][c];
+    for (int i = c + 1; i < NB; ++i) {
+      float acc = 0.f;
+      for (int j = c; j < i; ++j) acc = fmaf(S[i][j], X[j][c], acc);
+      X[i][c] = -acc / S[i][i];
+    }
+  }
+  __syncthreads();
+  float* dinv = Dinv + (size_t)kb * NB * NB;
+  for (int e = tid; e < NB * NB; e += 256) {
+    const int r = e >> 6, c = e & 63;
+    if (c <= r) blk[(size_t)r * lda + c] = S[r][c];
+    dinv[e] = X[r][c];
+  }
+  if (tid < 32) {
+    float l = logf(S[tid][tid]) + logf(S[tid + 32][tid + 32]);
+    l = warp_sum(l);
+    if (tid == 0) logdet_part[kb] = l;
+  }
+}
+
+int32_t cholesky_inplace(cudaStream_t s, float* A, int np, int lda, float* Dinv, float* logdet_part, int* status) {
+  const int nb = np / NB;
+  for (int k = 0; k < nb; ++k) {
+    potrf_diag_kernel<<<1, 256, 0, s>>>(A, lda, k, Dinv, logdet_part, status);
+    BX_LAUNCH_CHECK();
+    const int rem = nb - k - 1;
+    if (rem == 0) break;
+    float* panel = A + (size_t)(k + 1) * NB * lda + (size_t)k * NB;
+    GemmArgs p{};  // panel <- panel * Dinv_k^T   (in place: each CTA owns its 64 rows x 64 cols)
+    p.A = panel; p.lda = lda; p.B = Dinv + (size_t)k * NB * NB; p.ldb = NB; p.C = panel; p.ldc = lda;
+    p.M = rem * NB; p.N = NB; p.K = NB; p.alpha = 1.f; p.beta = 0.f; p.kmode = KM_FULL;
+    int32_t rc = gemm(s, false, true, p);
+    if (rc) return rc;
+    GemmArgs u{};  // trailing(lower tiles) -= panel * panel^T
+    u.A = panel; u.lda = lda; u.B = panel; u.ldb = lda; u.C = A + (size_t)(k + 1) * NB * lda + (size_t)(k + 1) * NB; u.ldc = lda;
+    u.M = rem * NB; u.N = rem * NB; u.K = NB; u.alpha = -1.f; u.beta = 1.f; u.kmode = KM_FULL; u.lower_only = 1;
+    rc = gemm(s, false, true, u);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+// Diagonal blocks <- Dinv, everything above the block diagonal <- 0.
+__global__ void tri_prep_kernel(float* A, int np, int lda, const float* Dinv) {
+  const int bi = blockIdx.y, bj = blockIdx.x;
+  if (bj < bi) return;
+  float* blk = A + (size_t)bi * NB * lda + (size_t)bj * NB;
+  for (int e = threadIdx.x; e < NB * NB; e += blockDim.x) {
+    const int r = e >> 6, c = e & 63;
+    blk[(size_t)r * lda + c] = (bi == bj) ? Dinv[(size_t)bi * NB * NB + e] : 0.f;
+  }
+}
+
+int32_t tri_inverse_inplace(cudaStream_t s, float* A, int np, int lda, const float* Dinv, float* TMP) {
+  const int nb = np / NB;
+  tri_prep_kernel<<<dim3(nb, nb), 256, 0, s>>>(A, np, lda, Dinv);
+  BX_LAUNCH_CHECK();
+  int levels = 0;
+  while ((1 << levels) < nb) ++levels;
+  for (int level = levels - 1; level >= 0; --level) {
+    const int nodes = 1 << level;
+    const int sz = (nb + nodes - 1) / nodes;  // largest node at this level (blocks)
+    const int half = (sz + 1) / 2;
+    for (int pass = 1; pass <= 2; ++pass) {
+      GemmArgs g{};
+      g.tree_nb = nb; g.tree_level = level; g.tree_pass = pass;
+      g.lda = lda; g.ldb = (pass == 1) ? lda : np; g.ldc = (pass == 1) ? np : lda;
+      g.A = A; g.B = (pass == 1) ? A : TMP; g.C = (pass == 1) ? TMP : A;
+      g.M = half * NB; g.N = half * NB; g.K = 0; g.beta = 0.f;  // real extents are set per node in the kernel
+      int32_t rc = gemm(s, false, false, g, nodes);
+      if (rc) return rc;
+    }
+  }
+  return 0;
+}
+
+// out[i] = sum_{j<=i} T[i][j] x[j] : one warp per row.
+__global__ void trmv_lower_kernel(const float* __restrict__ T, int np, int ld, const float* __restrict__ x, float* out) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= np) return;
+  float acc = 0.f;
+  for (int j = lane; j <= row; j += 32) acc = fmaf(T[(size_t)row * ld + j], x[j], acc);
+  acc = warp_sum(acc);
+  if (lane == 0) out[row] = acc;
+}
+// out[j] = sum_{i>=j} T[i][j] x[i] : 32 columns x 8 row strips per block.
+__global__ void __launch_bounds__(256) trmv_lower_t_kernel(const float* __restrict__ T, int np, int ld,
+                                                           const float* __restrict__ x, float* out) {
+  __shared__ float red[8][33];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int j = blockIdx.x * 32 + cx;
+  float acc = 0.f;
+  for (int i = blockIdx.x * 32 + ry; i < np; i += 8)
+    if (i >= j) acc = fmaf(T[(size_t)i * ld + j], x[i], acc);
+  red[ry][cx] = acc;
+  __syncthreads();
+  if (ry == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) t += red[r][cx];
+    out[j] = t;
+  }
+}
+int32_t trmv_lower(cudaStream_t s, const float* T, int np, int ld, const float* x, float* out) {
+  trmv_lower_kernel<<<(np + 7) / 8, 256, 0, s>>>(T, np, ld, x, out);
+  BX_LAUNCH_CHECK();
+  return 0;
+}
+int32_t trmv_lower_t(cudaStream_t s, const float* T, int np, int ld, const float* x, float* out) {
+  trmv_lower_t_kernel<<<np / 32, 256, 0, s>>>(T, np, ld, x, out);
+  BX_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace bx
+
+extern "C" const char* bx_last_error(void) { return bx::last_error(); }
+extern "C" int32_t bx_version(void) { return BX_VERSION; }
+extern "C" uint64_t bx_pack(float value, uint32_t index) { return bx::pack_best(value, index); }
+extern "C" void bx_unpack(uint64_t key, float* value, uint32_t* index) {
+  if (value) *value = bx::from_orderable_u32((uint32_t)(key >> 32));
+  if (index) *index = 0xFFFFFFFFu - (uint32_t)(key & 0xFFFFFFFFu);
+}

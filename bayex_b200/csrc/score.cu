@@ -1,0 +1,307 @@
+// Candidate generation and the SIMT (fp32 FFMA) scoring engine.
+//
+// score_simt_kernel fuses, per tile of 64 candidates:  Threefry generation or load (domain.py:74,130,159-161) ->
+// cross-Gram tile K* (gp.py:60-64) -> mean K*^T alpha (gp.py:66-67) -> V = T K* with T = L^-1 (gp.py:68, as a
+// triangular GEMM instead of a solve) -> column sums of V^2 (diag of gp.py:69, quirk Q8) -> std (gp.py:70) ->
+// EI/PI/UCB/LCB (acq.py) -> packed arg-max (optimizer.py:205).  K* and V live only in shared memory / registers.
+// This engine backs bx_score_points (explicit candidates: gp.predict, acq.*, refinement scoring) and is the
+// reference implementation the tcgen05 engine (score_tc.cu) is validated against on the GPU.
+#include "internal.h"
+
+namespace bx {
+
+int32_t make_sampler(const uint32_t key[2], const bx_dim_t* dims, int32_t d, SamplerPack* out, bool split_keys) {
+  BX_CHECK_ARG(key && dims && out, BX_E_ARG, "null pointer argument");
+  BX_CHECK_ARG(d > 0 && d <= BX_MAX_D, BX_E_RANGE, "d=%d outside [1, %d]", d, BX_MAX_D);
+  out->d = d;
+  for (int j = 0; j < d; ++j) {
+    DimSampler& s = out->dim[j];
+    uint32_t k0, k1;
+    if (split_keys) threefry2x32(key[0], key[1], 0u, (uint32_t)j, k0, k1);  // split(key, d)[j]  (domain.py:160)
+    else { k0 = key[0]; k1 = key[1]; }                                      // Domain.sample(key): the key itself
+    s.kind = dims[j].kind;
+    if (dims[j].kind == 0) {
+      BX_CHECK_ARG(dims[j].lo < dims[j].hi, BX_E_ARG, "Lower bound must be less than upper bound (dim %d)", j);
+      s.k0 = k0; s.k1 = k1; s.k2 = s.k3 = 0;
+      s.lo = dims[j].lo; s.hi = dims[j].hi; s.scale = dims[j].hi - dims[j].lo;
+      s.ilo = 0; s.span = 1; s.mult = 0;
+    } else {
+      BX_CHECK_ARG(dims[j].ilo < dims[j].ihi, BX_E_ARG, "Lower bound must be less than upper bound (dim %d)", j);
+      threefry2x32(k0, k1, 0u, 0u, s.k0, s.k1);  // randint: k1, k2 = split(key)  (domain.py:130)
+      threefry2x32(k0, k1, 0u, 1u, s.k2, s.k3);
+      s.ilo = dims[j].ilo;
+      s.span = (uint32_t)((int64_t)dims[j].ihi + 1 - (int64_t)dims[j].ilo);
+      uint32_t m = 65536u % s.span;
+      s.mult = (uint32_t)(((uint64_t)m * m) % s.span);
+      s.lo = (float)dims[j].ilo; s.hi = (float)dims[j].ihi; s.scale = 0.f;
+    }
+  }
+  return 0;
+}
+
+__global__ void threefry_fill_kernel(const __grid_constant__ SamplerPack sp, uint64_t m_begin, uint64_t m_count, float* out) {
+  const uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= m_count * (uint64_t)sp.d) return;
+  const uint64_t i = e / sp.d;
+  const int k = (int)(e % sp.d);
+  out[e] = sample_coord(sp.dim[k], m_begin + i);
+}
+__global__ void threefry_gather_kernel(const __grid_constant__ SamplerPack sp, const uint32_t* __restrict__ idx, int k,
+                                       float* out) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= k * sp.d) return;
+  out[e] = sample_coord(sp.dim[e % sp.d], (uint64_t)idx[e / sp.d]);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int CT = 64;   // candidates per block
+constexpr int RB = 64;   // T rows per accumulator tile
+constexpr int KS = 16;   // observations per k-step
+constexpr int SP = CT + 4;
+
+
+template <bool GEN>
+__global__ void __launch_bounds__(256) score_simt_kernel(const __grid_constant__ ScoreArgs a, const __grid_constant__ SamplerPack sp) {
+  extern __shared__ __align__(16) float sm[];
+  const int d = a.f.d, d4 = a.f.d4, np = a.f.np, cs_ld = d4 + 1;
+  float* cs = sm;                         // [CT][d4+1] scaled candidate coordinates
+  float* us = cs + CT * cs_ld;            // [KS][d4]   scaled observation rows of the current k-step
+  float* Ts = us + KS * d4;               // [KS][SP]   T tile, k-major
+  float* Ks = Ts + KS * SP;               // [KS][SP]   K* tile, k-major
+  float* red = Ks + KS * SP;              // [4][CT]    mean partials, then sum v^2
+  const int tid = threadIdx.x;
+  const uint64_t c_base = (uint64_t)blockIdx.x * CT;
+
+  for (int e = tid; e < CT * d4; e += 256) {
+    const int c = e / d4, k = e % d4;
+    float v = 0.f;
+    if (k < d && c_base + c < a.m_count) {
+      const float raw = GEN ? sample_coord(sp.dim[k], a.m_begin + c_base + c) : a.cand[(c_base + c) * d + k];
+      v = raw * a.f.d_scale[k];
+    }
+    cs[c * cs_ld + k] = v;
+  }
+  const float amp = a.f.d_hyp[HYP_AMP];
+  __syncthreads();
+
+  const int rg = tid & 15, cg = tid >> 4;    // accumulator mapping: rows 4rg.., candidates 4cg..
+  const int gc = tid & 63, gk = tid >> 6;    // generation mapping: candidate gc, observations gk + 4q
+  float ss[4] = {0.f, 0.f, 0.f, 0.f};
+  float mpart = 0.f;
+  const int nI = np / RB;
+  for (int I = 0; I < nI; ++I) {
+    const bool last = (I == nI - 1);
+    float acc[4][4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
+    const int ksteps = (I + 1) * (RB / KS);
+    for (int ks = 0; ks < ksteps; ++ks) {
+      const int k0 = ks * KS;
+      {  // T tile: rows I*64.., cols k0..k0+15 -> Ts[k][row]
+        const int r = tid >> 2, kk = (tid & 3) * 4;
+        const float4 v = *reinterpret_cast<const float4*>(a.f.d_T + (size_t)(I * RB + r) * np + k0 + kk);
+        Ts[(kk + 0) * SP + r] = v.x; Ts[(kk + 1) * SP + r] = v.y; Ts[(kk + 2) * SP + r] = v.z; Ts[(kk + 3) * SP + r] = v.w;
+      }
+      for (int e = tid; e < KS * d4; e += 256) us[e] = a.f.d_U[(size_t)k0 * d4 + e];
+      __syncthreads();
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {  // K* tile (gp.py:64): amp * exp(-|u_j - c|^2), never leaves shared memory
+        const int kk = gk + 4 * q;
+        float s = 0.f;
+        for (int k = 0; k < d4; ++k) {
+          const float df = us[kk * d4 + k] - cs[gc * cs_ld + k];
+          s = fmaf(df, df, s);
+        }
+        const float kv = amp * ex2_approx(-s);
+        Ks[kk * SP + gc] = kv;
+        if (last) mpart = fmaf(a.f.d_alpha[k0 + kk], kv, mpart);  // gp.py:66-67
+      }
+      __syncthreads();
+#pragma unroll
+      for (int kk = 0; kk < KS; ++kk) {
+        const float4 tv = *reinterpret_cast<const float4*>(&Ts[kk * SP + rg * 4]);
+        const float4 kv = *reinterpret_cast<const float4*>(&Ks[kk * SP + cg * 4]);
+        const float av[4] = {tv.x, tv.y, tv.z, tv.w}, bv[4] = {kv.x, kv.y, kv.z, kv.w};
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) acc[r][c] = fmaf(av[r], bv[c], acc[r][c]);
+      }
+      __syncthreads();
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {  // column sums of V^2 over this row block, reduced across the 16 row groups
+      float v = 0.f;
+#pragma unroll
+      for (int r = 0; r < 4; ++r) v = fmaf(acc[r][c], acc[r][c], v);
+      v += __shfl_xor_sync(0xffffffffu, v, 1);
+      v += __shfl_xor_sync(0xffffffffu, v, 2);
+      v += __shfl_xor_sync(0xffffffffu, v, 4);
+      v += __shfl_xor_sync(0xffffffffu, v, 8);
+      ss[c] += v;
+    }
+  }
+  red[gk * CT + gc] = mpart;
+  __syncthreads();
+  float mu = 0.f;
+  if (tid < CT) mu = red[tid] + red[CT + tid] + red[2 * CT + tid] + red[3 * CT + tid] + a.f.d_hyp[HYP_YMEAN];
+  __syncthreads();
+  if (rg == 0) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) red[cg * 4 + c] = ss[c];
+  }
+  __syncthreads();
+  unsigned long long key = 0ull;
+  if (tid < CT && c_base + tid < a.m_count) {
+    const float var = amp - red[tid];                 // diag(amp*cov(xt,xt) - v^T v)   gp.py:69
+    const float sd = sqrtf(fmaxf(var, 1e-10f));       // gp.py:70
+    const float av = acquisition(a.acq_id, mu, sd, a.ystar, a.acq_param);
+    const uint64_t row = c_base + tid;
+    if (a.mu) a.mu[row] = mu;
+    if (a.sigma) a.sigma[row] = sd;
+    if (a.acq) a.acq[row] = av;
+    key = pack_best(av, (uint32_t)(a.index_base + row));
+  }
+  if (a.best && tid < CT) {
+    key = warp_max_u64(key);
+    if ((tid & 31) == 0 && key) atomicMax(a.best, key);
+  }
+}
+
+static size_t score_simt_smem(int d4) { return sizeof(float) * (CT * (d4 + 1) + KS * d4 + 2 * KS * SP + 4 * CT); }
+
+int32_t check_factor(const bx_factor_t* f) {
+  BX_CHECK_ARG(f, BX_E_ARG, "null factor");
+  BX_CHECK_ARG(f->d_U && f->d_T && f->d_alpha && f->d_scale && f->d_hyp, BX_E_ARG, "factor has null device pointers");
+  BX_CHECK_ARG(f->n > 0 && f->d > 0 && f->d <= BX_MAX_D, BX_E_RANGE, "factor n=%d d=%d out of range", f->n, f->d);
+  BX_CHECK_ARG(f->np == round_up(f->n, BX_TILE) && f->d4 == round_up(f->d, 4), BX_E_ARG, "factor np/d4 inconsistent");
+  return 0;
+}
+
+int32_t launch_score_simt(cudaStream_t s, const ScoreArgs& a, const SamplerPack* sp, bool gen) {
+  static SamplerPack empty{};
+  const size_t smem = score_simt_smem(a.f.d4);
+  const unsigned grid = (unsigned)((a.m_count + CT - 1) / CT);
+  if (gen) {
+    BX_CUDA(cudaFuncSetAttribute(score_simt_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    score_simt_kernel<true><<<grid, 256, smem, s>>>(a, *sp);
+  } else {
+    BX_CUDA(cudaFuncSetAttribute(score_simt_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    score_simt_kernel<false><<<grid, 256, smem, s>>>(a, empty);
+  }
+  BX_LAUNCH_CHECK();
+  return 0;
+}
+
+// implemented in score_tc.cu
+int32_t launch_score_tc(cudaStream_t s, const ScoreArgs& a, const SamplerPack& sp);
+bool score_tc_supported(const bx_factor_t& f);
+
+}  // namespace bx
+
+using namespace bx;
+
+extern "C" int32_t bx_threefry_fill(const uint32_t key[2], const bx_dim_t* dims, int32_t d, uint64_t m_begin,
+                                    uint64_t m_count, float* d_out, void* stream) {
+  SamplerPack sp;
+  int32_t rc = make_sampler(key, dims, d, &sp);
+  if (rc) return rc;
+  BX_CHECK_ARG(d_out, BX_E_ARG, "null output");
+  BX_CHECK_ARG(m_begin + m_count <= 0x100000000ull, BX_E_RANGE, "candidate indices must stay below 2^32");
+  if (m_count == 0) return 0;
+  const uint64_t tot = m_count * (uint64_t)d;
+  threefry_fill_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(sp, m_begin, m_count, d_out);
+  BX_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int32_t bx_domain_sample(const uint32_t key[2], const bx_dim_t* dim, uint64_t m_begin, uint64_t m_count,
+                                    float* d_out, void* stream) {
+  SamplerPack sp;
+  int32_t rc = make_sampler(key, dim, 1, &sp, false);
+  if (rc) return rc;
+  BX_CHECK_ARG(d_out, BX_E_ARG, "null output");
+  BX_CHECK_ARG(m_begin + m_count <= 0x100000000ull, BX_E_RANGE, "candidate indices must stay below 2^32");
+  if (m_count == 0) return 0;
+  threefry_fill_kernel<<<(unsigned)((m_count + 255) / 256), 256, 0, (cudaStream_t)stream>>>(sp, m_begin, m_count, d_out);
+  BX_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int32_t bx_threefry_gather(const uint32_t key[2], const bx_dim_t* dims, int32_t d, const uint32_t* d_idx,
+                                      int32_t k, float* d_out, void* stream) {
+  SamplerPack sp;
+  int32_t rc = make_sampler(key, dims, d, &sp);
+  if (rc) return rc;
+  BX_CHECK_ARG(d_idx && d_out, BX_E_ARG, "null pointer argument");
+  if (k <= 0) return 0;
+  threefry_gather_kernel<<<(k * d + 255) / 256, 256, 0, (cudaStream_t)stream>>>(sp, d_idx, k, d_out);
+  BX_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int32_t bx_score_points(const bx_factor_t* f, const float* d_cand, uint64_t M, int32_t acq_id, float acq_param,
+                                   float ystar, float* d_mu, float* d_sigma, float* d_acq, uint64_t* d_best,
+                                   uint64_t index_base, void* stream) {
+  int32_t rc = check_factor(f);
+  if (rc) return rc;
+  BX_CHECK_ARG(d_cand, BX_E_ARG, "null candidates");
+  BX_CHECK_ARG(acq_id >= 0 && acq_id <= 3, BX_E_ARG, "unknown acquisition id %d", acq_id);
+  BX_CHECK_ARG(index_base + M <= 0x100000000ull, BX_E_RANGE, "candidate indices must stay below 2^32");
+  if (M == 0) return 0;
+  ScoreArgs a{};
+  a.f = *f; a.cand = d_cand; a.m_begin = 0; a.m_count = M; a.acq_id = acq_id; a.acq_param = acq_param; a.ystar = ystar;
+  a.mu = d_mu; a.sigma = d_sigma; a.acq = d_acq; a.best = reinterpret_cast<unsigned long long*>(d_best); a.index_base = index_base;
+  return launch_score_simt((cudaStream_t)stream, a, nullptr, false);
+}
+
+extern "C" int32_t bx_score_generated(const bx_factor_t* f, const uint32_t key[2], const bx_dim_t* dims, uint64_t m_begin,
+                                      uint64_t m_count, int32_t acq_id, float acq_param, float ystar, float* d_acq,
+                                      uint64_t* d_best, int32_t engine, void* stream) {
+  int32_t rc = check_factor(f);
+  if (rc) return rc;
+  BX_CHECK_ARG(acq_id >= 0 && acq_id <= 3, BX_E_ARG, "unknown acquisition id %d", acq_id);
+  BX_CHECK_ARG(m_begin + m_count <= 0x100000000ull, BX_E_RANGE, "candidate indices must stay below 2^32");
+  SamplerPack sp;
+  rc = make_sampler(key, dims, f->d, &sp);
+  if (rc) return rc;
+  if (m_count == 0) return 0;
+  ScoreArgs a{};
+  a.f = *f; a.cand = nullptr; a.m_begin = m_begin; a.m_count = m_count; a.acq_id = acq_id; a.acq_param = acq_param;
+  a.ystar = ystar; a.acq = d_acq; a.best = reinterpret_cast<unsigned long long*>(d_best); a.index_base = m_begin;
+  if (engine == BX_ENGINE_AUTO) engine = score_tc_supported(*f) ? BX_ENGINE_TCGEN05 : BX_ENGINE_SIMT;
+  if (engine == BX_ENGINE_TCGEN05) {
+    BX_CHECK_ARG(score_tc_supported(*f), BX_E_UNSUPPORTED, "tcgen05 engine needs the Thi/Tlo split of the factor");
+    return launch_score_tc((cudaStream_t)stream, a, sp);
+  }
+  BX_CHECK_ARG(engine == BX_ENGINE_SIMT, BX_E_ARG, "unknown engine %d", engine);
+  return launch_score_simt((cudaStream_t)stream, a, &sp, true);
+}
+
+// Masked pairwise kernel matrix - replaces: gp.py:20-23 cov (x1 [n1 x d], x2 [n2 x d] already divided by the length scale).
+namespace bx {
+__global__ void cov_kernel(const float* __restrict__ x1, int n1, const float* __restrict__ x2, int n2, int d,
+                           const float* __restrict__ m1, const float* __restrict__ m2, float* out) {
+  const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (size_t)n1 * n2) return;
+  const int i = (int)(e / n2), j = (int)(e % n2);
+  float s = 0.f;
+  for (int k = 0; k < d; ++k) {
+    const float df = x1[(size_t)i * d + k] - x2[(size_t)j * d + k];
+    s = fmaf(df, df, s);
+  }
+  out[e] = expf(-s) * (m1[i] * m2[j]);  // gp.py:15-17 exp_quadratic * outer(mask1, mask2)
+}
+}  // namespace bx
+
+extern "C" int32_t bx_cov(const float* d_x1, int32_t n1, const float* d_x2, int32_t n2, int32_t d, const float* d_m1,
+                          const float* d_m2, float* d_out, void* stream) {
+  BX_CHECK_ARG(d_x1 && d_x2 && d_m1 && d_m2 && d_out, BX_E_ARG, "null pointer argument");
+  BX_CHECK_ARG(n1 > 0 && n2 > 0 && d > 0, BX_E_ARG, "sizes must be positive");
+  const size_t tot = (size_t)n1 * n2;
+  bx::cov_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_x1, n1, d_x2, n2, d, d_m1, d_m2, d_out);
+  BX_LAUNCH_CHECK();
+  return 0;
+}

@@ -1,0 +1,271 @@
+"""Device-side plumbing between the bayex-shaped Python API and the C ABI.
+
+torch is used for device memory, streams and (optionally) ``torch.distributed``; all arithmetic happens in
+``libbayex_b200.so``.  ``Posterior`` owns the cached factor that the reference recomputes on every
+``predict`` call (gp.py:41-49).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import lib, check
+
+_STREAMS = {}
+_WORKSPACES = {}
+
+
+def device(index=None) -> torch.device:
+    if not torch.cuda.is_available():
+        raise RuntimeError("bayex_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device() if index is None else index)
+
+
+def stream(dev: torch.device) -> torch.cuda.Stream:
+    """One private non-default stream per device (CUDA-graph capture is illegal on the legacy stream)."""
+    s = _STREAMS.get(dev.index)
+    if s is None:
+        s = _STREAMS[dev.index] = torch.cuda.Stream(device=dev)
+    return s
+
+
+def _ptr(t):
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _workspace(dev, nbytes) -> torch.Tensor:
+    ws = _WORKSPACES.get(dev.index)
+    if ws is None or ws.numel() < nbytes:
+        ws = None
+        _WORKSPACES.pop(dev.index, None)
+        ws = _WORKSPACES[dev.index] = torch.empty(int(nbytes), dtype=torch.uint8, device=dev)
+    return ws
+
+
+def dims_array(domain: dict):
+    """bayex.domain objects (dict order = column order, domain.py:175) -> bx_dim_t[d]."""
+    arr = (_lib.DimT * len(domain))()
+    for j, dom in enumerate(domain.values()):
+        if getattr(dom, "is_integer", False):
+            arr[j] = _lib.DimT(1, float(dom.lower), float(dom.upper), int(dom.lower), int(dom.upper))
+        else:
+            arr[j] = _lib.DimT(0, float(np.float32(dom.lower)), float(np.float32(dom.upper)), 0, 0)
+    return arr
+
+
+def raw_vector(params, d) -> np.ndarray:
+    """GPParams (python floats or (1,1)/(1,d) arrays: gp.py:41 broadcasting, quirk Q2) -> float32[d+2]."""
+    nr = np.asarray(params.noise, dtype=np.float32).reshape(-1)[0]
+    ar = np.asarray(params.amplitude, dtype=np.float32).reshape(-1)[0]
+    ls = np.asarray(params.lengthscale, dtype=np.float32).reshape(-1)
+    if ls.size == 1 and d != 1:
+        ls = np.full((d,), ls[0], dtype=np.float32)
+    if ls.size != d:
+        raise ValueError(f"lengthscale has {ls.size} entries for {d} input dimensions")
+    return np.concatenate([[nr], [ar], ls]).astype(np.float32)
+
+
+def compact(x, y, mask):
+    """Apply the reference's mask on the host side: keep valid rows only (see include/bayex_b200.h)."""
+    x = np.asarray(x, dtype=np.float32)
+    if x.ndim == 1:
+        x = x[:, None]  # tests/test_gp.py:20-31: 1-D inputs mean d = 1
+    y = np.asarray(y, dtype=np.float32).reshape(-1)
+    m = np.asarray(mask).astype(bool).reshape(-1)
+    if not m.any():
+        raise ValueError("no valid observation (mask is all False)")
+    return np.ascontiguousarray(x[m]), np.ascontiguousarray(y[m])
+
+
+class Posterior:
+    """The fitted GP on one GPU: compacted observations, raw hypers and (after ``build``) the factor."""
+
+    def __init__(self, x, y, raw, dev=None, want_tc=True):
+        self.dev = device() if dev is None else dev
+        self.stream = stream(self.dev)
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        self.n, self.d = x.shape
+        if self.d > _lib.MAX_D:
+            raise ValueError(f"at most {_lib.MAX_D} dimensions are supported, got {self.d}")
+        self.np_ = (self.n + _lib.TILE - 1) // _lib.TILE * _lib.TILE
+        self.d4 = (self.d + 3) // 4 * 4
+        self.want_tc = want_tc
+        with torch.cuda.stream(self.stream):
+            self.X = torch.from_numpy(x).to(self.dev, non_blocking=False)
+            self.y = torch.from_numpy(np.ascontiguousarray(y, dtype=np.float32)).to(self.dev)
+            self.raw = torch.from_numpy(np.ascontiguousarray(raw, dtype=np.float32)).to(self.dev)
+        self.factor = None
+        self._bufs = None
+
+    # -- fit path ---------------------------------------------------------------------------------------------
+    def _ws(self):
+        nbytes = lib.bx_fit_workspace_bytes(self.n, self.d)
+        return _workspace(self.dev, nbytes), nbytes
+
+    def fit_hypers(self, lr=1e-3, steps=100, trace=False, use_graph=True):
+        """gp.py:90-110 on the device; updates ``self.raw`` in place."""
+        ws, nbytes = self._ws()
+        tr = torch.empty((steps, self.d + 2), dtype=torch.float32, device=self.dev) if trace else None
+        with torch.cuda.stream(self.stream):
+            check(lib.bx_fit_adamw(_ptr(self.X), _ptr(self.y), self.n, self.d, _ptr(self.raw), lr, steps, _ptr(tr),
+                                   _ptr(ws), nbytes, 1 if use_graph else 0, C.c_void_p(self.stream.cuda_stream)),
+                  "bx_fit_adamw")
+        self.factor = None
+        return tr
+
+    def nlml_grad(self):
+        """(nlml, loss, dloss/draw, dnlml/draw) at the current raw hypers (gp.py:74-87)."""
+        ws, nbytes = self._ws()
+        out = torch.empty(2 + 2 * (self.d + 2), dtype=torch.float32, device=self.dev)
+        with torch.cuda.stream(self.stream):
+            check(lib.bx_nlml_grad(_ptr(self.X), _ptr(self.y), self.n, self.d, _ptr(self.raw), _ptr(out), _ptr(ws),
+                                   nbytes, C.c_void_p(self.stream.cuda_stream)), "bx_nlml_grad")
+            o = out.cpu().numpy()
+        P = self.d + 2
+        return float(o[0]), float(o[1]), o[2:2 + P].copy(), o[2 + P:2 + 2 * P].copy()
+
+    def build(self):
+        """gp.py:41-49 once: factor arrays for every later scoring call."""
+        ws, nbytes = self._ws()
+        np_, d4 = self.np_, self.d4
+        with torch.cuda.stream(self.stream):
+            if self._bufs is None:
+                e = lambda *s: torch.empty(s, dtype=torch.float32, device=self.dev)
+                self._bufs = dict(U=e(np_, d4), T=e(np_, np_), alpha=e(np_), scale=e(d4), hyp=e(8),
+                                  Thi=e(np_, np_) if self.want_tc else None, Tlo=e(np_, np_) if self.want_tc else None)
+            b = self._bufs
+            check(lib.bx_factor_build(_ptr(self.X), _ptr(self.y), self.n, self.d, _ptr(self.raw), _ptr(b["U"]),
+                                      _ptr(b["T"]), _ptr(b["Thi"]), _ptr(b["Tlo"]), _ptr(b["alpha"]), _ptr(b["scale"]),
+                                      _ptr(b["hyp"]), _ptr(ws), nbytes, C.c_void_p(self.stream.cuda_stream)),
+                  "bx_factor_build")
+        self._set_factor()
+        return self
+
+    def _set_factor(self):
+        b = self._bufs
+        self.factor = _lib.FactorT(self.n, self.np_, self.d, self.d4, b["U"].data_ptr(), b["T"].data_ptr(),
+                                   0 if b["Thi"] is None else b["Thi"].data_ptr(),
+                                   0 if b["Tlo"] is None else b["Tlo"].data_ptr(), b["alpha"].data_ptr(),
+                                   b["scale"].data_ptr(), b["hyp"].data_ptr())
+
+    def hyp(self) -> np.ndarray:
+        self._need_factor()
+        with torch.cuda.stream(self.stream):
+            return self._bufs["hyp"].cpu().numpy()
+
+    def raw_host(self) -> np.ndarray:
+        with torch.cuda.stream(self.stream):
+            return self.raw.cpu().numpy()
+
+    def _need_factor(self):
+        if self.factor is None:
+            self.build()
+
+    # -- multi-GPU: the factor is built on one rank and broadcast (NCCL over NVLink) --------------------------
+    def broadcast(self, src=0, group=None):
+        import torch.distributed as dist
+        if self._bufs is None:
+            e = lambda *s: torch.empty(s, dtype=torch.float32, device=self.dev)
+            self._bufs = dict(U=e(self.np_, self.d4), T=e(self.np_, self.np_), alpha=e(self.np_), scale=e(self.d4),
+                              hyp=e(8), Thi=e(self.np_, self.np_) if self.want_tc else None,
+                              Tlo=e(self.np_, self.np_) if self.want_tc else None)
+        self.stream.synchronize()
+        names = ["U", "alpha", "scale", "hyp", "T"] + (["Thi", "Tlo"] if self.want_tc else [])
+        for name in names:
+            dist.broadcast(self._bufs[name], src=src, group=group)
+        dist.broadcast(self.raw, src=src, group=group)
+        torch.cuda.current_stream(self.dev).synchronize()
+        self._set_factor()
+        return self
+
+    # -- scoring ----------------------------------------------------------------------------------------------
+    def score_points(self, cand, acq="UCB", param=0.0, ystar=0.0, want=("mu", "sigma", "acq"), best=False):
+        """Posterior moments / acquisition at explicit points (gp.py:59-71, acq.py).  Returns device tensors."""
+        self._need_factor()
+        with torch.cuda.stream(self.stream):
+            if not isinstance(cand, torch.Tensor):
+                cand = torch.from_numpy(np.ascontiguousarray(cand, dtype=np.float32)).to(self.dev)
+            cand = cand.contiguous()
+            M = cand.shape[0]
+            out = {k: (torch.empty(M, dtype=torch.float32, device=self.dev) if k in want else None)
+                   for k in ("mu", "sigma", "acq")}
+            bst = torch.zeros(1, dtype=torch.int64, device=self.dev) if best else None
+            check(lib.bx_score_points(C.byref(self.factor), _ptr(cand), M, _lib.ACQ_IDS[acq], float(param), float(ystar),
+                                      _ptr(out["mu"]), _ptr(out["sigma"]), _ptr(out["acq"]), _ptr(bst), 0,
+                                      C.c_void_p(self.stream.cuda_stream)), "bx_score_points")
+        out["best"] = bst
+        return out
+
+    def score_generated(self, key, dims, m_begin, m_count, acq, param, ystar, keep_acq=True, engine=_lib.ENGINE_AUTO,
+                        best=None):
+        """Fused Threefry -> posterior -> acquisition -> arg-max over a slice of the candidate draw."""
+        self._need_factor()
+        with torch.cuda.stream(self.stream):
+            vals = torch.empty(m_count, dtype=torch.float32, device=self.dev) if keep_acq else None
+            if best is None:
+                best = torch.zeros(1, dtype=torch.int64, device=self.dev)
+            check(lib.bx_score_generated(C.byref(self.factor), _lib.key_words(key), dims, int(m_begin), int(m_count),
+                                         _lib.ACQ_IDS[acq], float(param), float(ystar), _ptr(vals), _ptr(best),
+                                         int(engine), C.c_void_p(self.stream.cuda_stream)), "bx_score_generated")
+        return vals, best
+
+    def topk(self, vals: torch.Tensor, k: int, index_base=0):
+        with torch.cuda.stream(self.stream):
+            M = vals.numel()
+            nbytes = lib.bx_topk_workspace_bytes(M, k)
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=self.dev)
+            ov = torch.empty(k, dtype=torch.float32, device=self.dev)
+            oi = torch.empty(k, dtype=torch.int32, device=self.dev)
+            check(lib.bx_topk(_ptr(vals), M, k, int(index_base), _ptr(ov), _ptr(oi), _ptr(ws), nbytes,
+                              C.c_void_p(self.stream.cuda_stream)), "bx_topk")
+        return ov, oi
+
+    def gather(self, key, dims, idx: torch.Tensor):
+        with torch.cuda.stream(self.stream):
+            k = idx.numel()
+            out = torch.empty((k, self.d), dtype=torch.float32, device=self.dev)
+            check(lib.bx_threefry_gather(_lib.key_words(key), dims, self.d, _ptr(idx), k, _ptr(out),
+                                         C.c_void_p(self.stream.cuda_stream)), "bx_threefry_gather")
+        return out
+
+    def refine(self, starts: torch.Tensor, rounds, acq, param, ystar):
+        self._need_factor()
+        with torch.cuda.stream(self.stream):
+            x = starts.clone().contiguous()
+            S = x.shape[0]
+            nbytes = lib.bx_refine_workspace_bytes(C.byref(self.factor), S)
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=self.dev)
+            val = torch.empty(S, dtype=torch.float32, device=self.dev)
+            check(lib.bx_refine(C.byref(self.factor), _ptr(x), S, int(rounds), _lib.ACQ_IDS[acq], float(param),
+                                float(ystar), _ptr(val), _ptr(ws), nbytes, C.c_void_p(self.stream.cuda_stream)),
+                  "bx_refine")
+        return x, val
+
+
+def threefry_fill(key, dims, d, m_begin, m_count, dev=None) -> torch.Tensor:
+    """Candidates [m_begin, m_begin+m_count) of ``sample_params(key, (M,))`` as a device tensor [m_count, d]."""
+    dev = device() if dev is None else dev
+    st = stream(dev)
+    with torch.cuda.stream(st):
+        out = torch.empty((m_count, d), dtype=torch.float32, device=dev)
+        check(lib.bx_threefry_fill(_lib.key_words(key), dims, d, int(m_begin), int(m_count), _ptr(out),
+                                   C.c_void_p(st.cuda_stream)), "bx_threefry_fill")
+    return out
+
+
+def domain_sample(key, dims, count, dev=None) -> torch.Tensor:
+    """``Domain.sample(key, (count,))``: one domain, the key used as is (domain.py:74,130)."""
+    dev = device() if dev is None else dev
+    st = stream(dev)
+    with torch.cuda.stream(st):
+        out = torch.empty((count,), dtype=torch.float32, device=dev)
+        check(lib.bx_domain_sample(_lib.key_words(key), dims, 0, int(count), _ptr(out), C.c_void_p(st.cuda_stream)),
+              "bx_domain_sample")
+    return out
+
+
+def to_unsigned(packed_i64: int) -> int:
+    return packed_i64 & 0xFFFFFFFFFFFFFFFF

@@ -1,0 +1,309 @@
+#!/usr/bin/env python
+"""Benchmark of the bayex hot path: acquisition candidate-evals/sec and sample() latency at n=4096 (BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c3|c2|c4] [--candidates M]
+
+One step = one ``Optimizer.sample(key, state, size=M)``: generate M candidates (Threefry), score them against the
+n-observation GP (posterior mean/variance -> acquisition), top-50, multi-start refinement, arg-max.
+  value : whole-job candidate-evals/s with the posterior factor already resident in HBM (cached by the optimiser);
+  e2e   : the same call with a cold cache - host observation buffers are uploaded, the factor is rebuilt
+          (Gram + Cholesky + inverse) and, at N>1, broadcast over NCCL, and the proposal is read back - every step.
+Multi-GPU: launched by torchrun, one rank per GPU; the candidate axis is sharded (strong scaling of a fixed M).
+``--impl reference`` times the CPU restatement of the reference (oracle/, NumPy/SciPy; JAX itself is not installable
+in this image) on the host cores, on a bounded sub-sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (d, n_obs, M, acq, description)
+    "c3": (20, 4096, 1 << 24, "UCB", "C3: 20-D Ackley (domain normalised to [0,1]^20), UCB, n=4096 observations, 2^24 candidates"),
+    "c2": (6, 512, 1 << 20, "EI", "C2: 6-D Hartmann-like, EI, n=512 observations, 2^20 candidates"),
+    "c4": (10, 2048, 1 << 20, "PI", "C4: 10-D synthetic (real part), PI, n=2048 observations, 2^20 candidates"),
+}
+
+
+def ackley(u):
+    x = u * 65.536 - 32.768
+    d = x.shape[1]
+    return (-20.0 * np.exp(-0.2 * np.sqrt(np.sum(x * x, axis=1) / d)) - np.exp(np.sum(np.cos(2 * np.pi * x), axis=1) / d)
+            + 20.0 + np.e).astype(np.float32)
+
+
+def flops_per_candidate(n, d):
+    """triangular contraction n^2 + mean 2n + sum v^2 2n + Gram column (3d+1) n."""
+    return float(n) * n + (3 * d + 5) * float(n)
+
+
+def make_observations(d, n, oracle_domain):
+    from oracle import prng
+    space = oracle_domain.ParamSpace({f"x{i}": oracle_domain.Real(0.0, 1.0) for i in range(d)})
+    P = space.sample_params(prng.key(0), (n,))
+    X = space.to_array(P)
+    return P, X, ackley(X)
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons while the timed region runs."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        self.stop_flag.set()
+        self.join(timeout=6)
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [nm for j, nm in enumerate(names) if any(r[3 + j].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons, "samples": len(sm),
+                "power_w_max": max(float(r[2]) for r in self.rows)}
+
+
+def cpu_baseline(d, n, acq, X, Y, sample=None, budget_s=20.0):
+    """Time the oracle (CPU restatement of gp.py:59-71 + acq.py) on a bounded sample; candidates/s on the host cores."""
+    from oracle import acq as oacq, domain as odom, gp as ogp, prng
+    try:
+        from threadpoolctl import threadpool_info
+        threads = max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
+    except Exception:
+        threads = os.cpu_count()
+    P = ogp.GPParams(np.float32(-8.0), np.float32(0.0), np.zeros(d, np.float32))
+    f = ogp.Factor(P, X, Y, np.ones(n), np.float32)
+    space = odom.ParamSpace({f"x{i}": odom.Real(0.0, 1.0) for i in range(d)})
+    chunk = 8192
+    if sample is None:
+        t0 = time.perf_counter()
+        c = space.to_array(space.sample_params(prng.key(1), (chunk,)))
+        mu, sd = f.predict(c, chunk=chunk)
+        oacq.acq_from_moments(acq, mu, sd, Y, np.ones(n))
+        one = time.perf_counter() - t0
+        sample = int(min(16, max(2, budget_s / max(one, 1e-3)))) * chunk
+    t0 = time.perf_counter()
+    c = space.to_array(space.sample_params(prng.key(1), (sample,)))
+    mu, sd = f.predict(c, chunk=chunk)
+    vals = oacq.acq_from_moments(acq, mu, sd, Y, np.ones(n))
+    int(np.argmax(vals))
+    dt = time.perf_counter() - t0
+    return {"value": sample / dt, "unit": "candidates/s", "cores": int(threads), "kind": "port",
+            "sample": f"{sample} of the workload's candidates (chunks of {chunk}, diagonal-only variance, NumPy/SciPy fp32 "
+                      f"restatement of the reference; JAX unavailable), {dt:.1f} s", "host_cpus": os.cpu_count()}
+
+
+def run_reference(args, d, n, M, acq, desc):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import domain as odom
+    _, X, Y = make_observations(d, n, odom)
+    per_step = []
+    base = None
+    for i in range(args.warmup + args.steps):
+        base = cpu_baseline(d, n, acq, X, Y, sample=args.ref_sample)
+        if i >= args.warmup:
+            per_step.append(base["value"])
+    v = float(np.mean(per_step))
+    base["value"] = v
+    line = {"impl": "reference", "metric": "acq candidate-evals/sec", "value": v, "unit": "candidates/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * args.ref_sample / v, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": desc, "n_obs": n, "d": d, "candidates": M, "acq": acq,
+                       "note": f"each step scores a bounded sample of {args.ref_sample} candidates on the host CPU"},
+            "cpu_baseline": base, "e2e": {"value": v, "unit": "candidates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def measure_tf32_peak(torch, dev):
+    """Dense TF32 cuBLAS GEMM throughput, measured like MEASURED_PEAKS.json's bf16 entry (8192^3, best of 10)."""
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    a = torch.randn(8192, 8192, device=dev)
+    b = torch.randn(8192, 8192, device=dev)
+    best = 0.0
+    for i in range(13):
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        a @ b
+        e.record()
+        e.synchronize()
+        if i >= 3:
+            best = max(best, 2 * 8192.0 ** 3 / (s.elapsed_time(e) * 1e-3) / 1e12)
+    torch.backends.cuda.matmul.allow_tf32 = old
+    del a, b
+    return best
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--candidates", type=int, default=None)
+    ap.add_argument("--engine", default="auto", choices=["auto", "simt", "tcgen05"])
+    ap.add_argument("--ref-sample", type=int, default=32768)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    d, n, M, acq, desc = WORKLOADS[args.workload]
+    if args.candidates:
+        M = args.candidates
+    if args.impl == "reference":
+        return run_reference(args, d, n, M, acq, desc)
+
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    import bayex_b200 as bayex
+    from bayex_b200 import _lib
+    from oracle import domain as odom  # only to draw the synthetic observations identically to the CPU arm
+
+    P, X, Y = make_observations(d, n, odom)
+    dom = {f"x{i}": bayex.domain.Real(0.0, 1.0) for i in range(d)}
+    opt = bayex.Optimizer(dom, acq=acq, maximize=False)
+    opt.engine = {"auto": _lib.ENGINE_AUTO, "simt": _lib.ENGINE_SIMT, "tcgen05": _lib.ENGINE_TCGEN05}[args.engine]
+    t0 = time.perf_counter()
+    state = opt.init(Y, P)  # 100-step hyper-parameter fit + factor (untimed set-up)
+    torch.cuda.synchronize()
+    fit_s = time.perf_counter() - t0
+    post = opt.posterior(state)
+    tf32_peak = measure_tf32_peak(torch, dev) if rank == 0 else 0.0
+    l2_flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    key0 = bayex.random.key(1)
+    # -- the dominant kernel alone (CUDA events on the stream it is launched on), L2 flushed between launches
+    from bayex_b200.optimizer import shard_range
+    m_begin, m_count = shard_range(M, rank, world)
+    kern_ms = []
+    for i in range(max(args.warmup, 3) + args.steps):
+        l2_flush.zero_()
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(post.stream):
+            s.record(post.stream)
+            post.score_generated(bayex.random.fold_in(key0, i), opt._dims, m_begin, m_count, acq, opt.acq_param, 0.0,
+                                 keep_acq=True, engine=opt.engine)
+            e.record(post.stream)
+        e.synchronize()
+        if i >= max(args.warmup, 3):
+            kern_ms.append(s.elapsed_time(e))
+    kern_ms_avg = float(np.mean(kern_ms))
+
+    # -- resident-factor steps (value)
+    for i in range(args.warmup):
+        opt.sample(bayex.random.fold_in(key0, 100 + i), state, size=M)
+    clocks = ClockSampler(local) if rank == 0 else None
+    if clocks:
+        clocks.start()
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        l2_flush.zero_()
+        proposal = opt.sample(bayex.random.fold_in(key0, 200 + i), state, size=M)
+    barrier()
+    t_res = max_over_ranks(time.perf_counter() - t0)
+    clock_summary = clocks.summary() if clocks else None
+
+    # -- end-to-end steps: cold cache => observation upload + factor rebuild (+ broadcast) + proposal read-back
+    for i in range(min(args.warmup, 2)):
+        opt._cache.clear()
+        opt.sample(bayex.random.fold_in(key0, 300 + i), state, size=M)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        opt._cache.clear()
+        proposal = opt.sample(bayex.random.fold_in(key0, 400 + i), state, size=M)
+    barrier()
+    t_e2e = max_over_ranks(time.perf_counter() - t0)
+
+    if rank == 0:
+        hyp = opt.posterior(state).hyp()
+        used_tc = bool(opt.engine == _lib.ENGINE_TCGEN05 or (opt.engine == _lib.ENGINE_AUTO and post._bufs["Thi"] is not None
+                                                              and os.environ.get("BX_TC_READY", "1") == "1"))
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        fl = flops_per_candidate(n, d) * m_count
+        achieved = fl / (kern_ms_avg * 1e-3) / 1e12
+        n_starts = opt.N_STARTS
+        launches_per_step = 1 + 19 + 1 + 4 * (opt.REFINE_ROUNDS + 1) + 1
+        line = {
+            "metric": "acq candidate-evals/sec", "value": M * args.steps / t_res, "unit": "candidates/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_res / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": desc, "n_obs": n, "d": d, "candidates": M, "acq": acq, "n_starts": n_starts,
+                       "refine_rounds": opt.REFINE_ROUNDS, "engine": args.engine, "parallelism": f"candidate-shard x{world}",
+                       "l2": "256 MiB buffer rewritten between timed steps; T (hi+lo) is read from L2/HBM every step",
+                       "sample_latency_ms": 1e3 * t_res / args.steps, "fit_init_s": fit_s,
+                       "hyper": {"amp": float(hyp[0]), "noise": float(hyp[1])}},
+            "e2e": {"value": M * args.steps / t_e2e, "unit": "candidates/s", "ms_per_step": 1e3 * t_e2e / args.steps,
+                    "h2d_bytes_per_step": int(X.nbytes + Y.nbytes + 4 * (d + 2) + 8),
+                    "d2h_bytes_per_step": int(4 * (d + 2) + 16 + 4 * n_starts * d + 4 * d)},
+            "gpu_launches": launches_per_step * args.steps,
+            "roofline": {"bound": "tensor", "kernel": "score (generate -> K* -> T K* -> sum v^2 -> acquisition -> arg-max)",
+                         "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s", "frac": achieved / tf32_peak if tf32_peak else None,
+                         "traffic": None, "kernel_ms": kern_ms_avg, "algorithmic_flops_per_launch": fl,
+                         "peak_source": "dense TF32 cuBLAS 8192^3 measured in this run (MEASURED_PEAKS.json has bf16 only: "
+                                        f"{peaks.get('bf16_tflops')} TF/s); the 3xTF32 split caps algorithmic flops at 1/3 of it"},
+            "clocks": clock_summary,
+            "proposal": {k: float(v[0]) for k, v in list(proposal.items())[:3]},
+        }
+        if not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(d, n, acq, X, Y)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,151 @@
+/*
+ * bayex_b200 - C ABI of the B200-native GP-posterior + acquisition hot path.
+ *
+ * This is the drop-in boundary.  bayex (the reference, /root/reference) has no
+ * FFI of its own: its boundary is the Python API.  Each
+ * entry point below replaces the XLA work behind one reference call site; the
+ * citation after "replaces:" is the reference file:line.  The Python package
+ * `bayex_b200` mirrors the reference's names on top of these with ctypes
+ * (see INTEGRATION.md for the binding a bayex maintainer would add).
+ *
+ * Conventions
+ *   - every pointer named d_* is a DEVICE pointer owned by the caller; the
+ *     library allocates nothing persistent and keeps no global mutable state;
+ *   - `stream` is a cudaStream_t passed as void*; all work is stream-ordered and
+ *     no entry point synchronises the host unless stated;
+ *   - return value: 0 = ok, <0 = bad argument (BX_E_*), >0 = cudaError_t;
+ *     bx_last_error() gives a thread-local message;
+ *   - observations are COMPACTED by the caller (valid rows only, reference mask
+ *     applied on the host side: gp.py:43-47 padding rows carry 1e12 variance and
+ *     contribute <1e-12, tests/test_gp.py:54-99).
+ */
+#ifndef BAYEX_B200_H
+#define BAYEX_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BX_VERSION 100 /* 0.1.0 */
+
+#define BX_E_ARG (-1)       /* null pointer / non-positive size */
+#define BX_E_RANGE (-2)     /* size outside supported range (d > BX_MAX_D, k > BX_MAX_K ...) */
+#define BX_E_WORKSPACE (-3) /* workspace too small */
+#define BX_E_NOTPD (-4)     /* non-finite / non-positive Cholesky pivot (only from bx_check_status) */
+#define BX_E_UNSUPPORTED (-5)
+
+#define BX_MAX_D 64   /* parameter-space dimensions */
+#define BX_MAX_K 1024 /* top-k */
+#define BX_TILE 128   /* observation padding granule: factor matrices are np x np, np = roundup(n, 128) */
+
+/* acquisition ids - names follow bayex.acq (acq.py:8,53,90,124) */
+enum { BX_ACQ_EI = 0, BX_ACQ_PI = 1, BX_ACQ_UCB = 2, BX_ACQ_LCB = 3 };
+/* scoring engines */
+enum { BX_ENGINE_AUTO = 0, BX_ENGINE_SIMT = 1, BX_ENGINE_TCGEN05 = 2 };
+
+/* One dimension of the parameter space - mirrors bayex.domain.Real / Integer (domain.py:22-131). */
+typedef struct {
+  int32_t kind; /* 0 = Real, 1 = Integer */
+  float lo, hi; /* Real bounds as float32 */
+  int32_t ilo, ihi; /* Integer bounds, inclusive */
+} bx_dim_t;
+
+/*
+ * The cached posterior factor (what gp.py:41-49 recomputes on every predict, quirk Q7).
+ * All device memory, caller-owned.  np = roundup(n, 128); rows/cols >= n are zero.
+ */
+typedef struct {
+  int32_t n;          /* valid observations */
+  int32_t np;         /* padded size, multiple of 128 */
+  int32_t d;          /* dimensions */
+  int32_t d4;         /* row stride of d_U, multiple of 4 */
+  const float* d_U;   /* [np x d4] observations * sqrt(log2 e) / lengthscale */
+  const float* d_T;   /* [np x np] row-major, T = L^-1 (lower triangular), K = L L^T */
+  const float* d_Thi; /* [np x np] TF32-exact head of T (tcgen05 engine), may be NULL */
+  const float* d_Tlo; /* [np x np] tail T - Thi, may be NULL */
+  const float* d_alpha; /* [np] K^-1 (y - ymean) */
+  const float* d_scale; /* [d4] sqrt(log2 e) / lengthscale_k */
+  const float* d_hyp;   /* [8] amp, noise, ymean, log2(amp), nlml, logdet(L), quad, status */
+} bx_factor_t;
+
+int32_t bx_version(void);
+const char* bx_last_error(void);
+
+/* Candidate generation - replaces: domain.py:159-161 (split), :74-75 (uniform+clip), :130-131 (randint+round/clip).
+ * Writes candidates [m_begin, m_begin+m_count) of the draw `sample_params(key, (M,))` as float32 [m_count x d]. */
+int32_t bx_threefry_fill(const uint32_t key[2], const bx_dim_t* dims, int32_t d, uint64_t m_begin, uint64_t m_count,
+                         float* d_out, void* stream);
+/* One domain drawn with the key itself - replaces: Real.sample (domain.py:63-75) / Integer.sample (domain.py:119-131). */
+int32_t bx_domain_sample(const uint32_t key[2], const bx_dim_t* dim, uint64_t m_begin, uint64_t m_count, float* d_out,
+                         void* stream);
+/* Regenerate the coordinates of selected candidate indices (top-k start points, optimizer.py:197). */
+int32_t bx_threefry_gather(const uint32_t key[2], const bx_dim_t* dims, int32_t d, const uint32_t* d_idx, int32_t k,
+                           float* d_out, void* stream);
+
+/* Masked pairwise squared-exponential matrix - replaces: gp.py:15-23 exp_quadratic / cov.
+ * x1 [n1 x d], x2 [n2 x d] (already divided by the length scale), masks as float; out [n1 x n2] row-major. */
+int32_t bx_cov(const float* d_x1, int32_t n1, const float* d_x2, int32_t n2, int32_t d, const float* d_m1,
+               const float* d_m2, float* d_out, void* stream);
+
+/* Workspace sizes (bytes) for the fit-path entry points. */
+size_t bx_fit_workspace_bytes(int32_t n, int32_t d);
+
+/* NLML and its gradient - replaces: gp.py:74 marginal_likelihood, gp.py:75 grad_fun, gp.py:78-87 neg_log_likelihood.
+ * d_raw = [noise_raw, amp_raw, ls_raw[d]]; d_out[0]=nlml, [1]=loss, [2..4+d) = d loss/d raw, [4+d..6+2d) = d nlml/d raw. */
+int32_t bx_nlml_grad(const float* d_X, const float* d_y, int32_t n, int32_t d, const float* d_raw, float* d_out,
+                     void* d_ws, size_t ws_bytes, void* stream);
+
+/* Hyper-parameter fit - replaces: gp.py:90-110 posterior_fit (clip_by_global_norm(10) + adamw(lr), fresh moments).
+ * d_raw is updated in place; the whole loop runs on the device (CUDA graph replay, no host sync).
+ * d_trace (optional) receives [steps x (2+d)] raw params before each step. */
+int32_t bx_fit_adamw(const float* d_X, const float* d_y, int32_t n, int32_t d, float* d_raw, float lr, int32_t steps,
+                     float* d_trace, void* d_ws, size_t ws_bytes, int32_t use_graph, void* stream);
+
+/* Posterior factor - replaces: gp.py:41-49 (softplus, centring, Gram, Cholesky, alpha) once per fit.
+ * Outputs are the arrays referenced by bx_factor_t (caller allocates: U np*d4, T np*np, Thi/Tlo optional, alpha np,
+ * scale d4, hyp 8). */
+int32_t bx_factor_build(const float* d_X, const float* d_y, int32_t n, int32_t d, const float* d_raw, float* d_U,
+                        float* d_T, float* d_Thi, float* d_Tlo, float* d_alpha, float* d_scale, float* d_hyp,
+                        void* d_ws, size_t ws_bytes, void* stream);
+
+/* Posterior + acquisition at explicit points - replaces: gp.py:59-71 predict, acq.py:45-50,84-87,120-121,155-156.
+ * d_cand [M x d] raw (unscaled) points.  Any of d_mu / d_sigma / d_acq may be NULL.  d_best (optional) is a
+ * uint64 packed arg-max accumulator (see bx_pack); index = index_base + row. */
+int32_t bx_score_points(const bx_factor_t* f, const float* d_cand, uint64_t M, int32_t acq_id, float acq_param,
+                        float ystar, float* d_mu, float* d_sigma, float* d_acq, uint64_t* d_best,
+                        uint64_t index_base, void* stream);
+
+/* Fused generate -> score -> arg-max over candidates [m_begin, m_begin+m_count) of sample_params(key, (M,)) -
+ * replaces: optimizer.py:183-193 + :205.  No M x n intermediate is written; d_acq (optional, [m_count]) receives the
+ * acquisition values for the top-k pass.  d_best must be zero-initialised by the caller (or hold a running max). */
+int32_t bx_score_generated(const bx_factor_t* f, const uint32_t key[2], const bx_dim_t* dims, uint64_t m_begin,
+                           uint64_t m_count, int32_t acq_id, float acq_param, float ystar, float* d_acq,
+                           uint64_t* d_best, int32_t engine, void* stream);
+
+/* Top-k by (value, index) ascending order, i.e. the last k of a stable argsort - replaces: optimizer.py:196.
+ * NaN sorts last (largest).  Outputs ascending: d_out_idx[k-1] is the arg-max.  index = index_base + position. */
+size_t bx_topk_workspace_bytes(uint64_t M, int32_t k);
+int32_t bx_topk(const float* d_vals, uint64_t M, int32_t k, uint64_t index_base, float* d_out_vals,
+                uint32_t* d_out_idx, void* d_ws, size_t ws_bytes, void* stream);
+
+/* Multi-start refinement - replaces: optimizer.py:39-73,198-199 (L-BFGS, parity unpinned -> monotone analytic-gradient
+ * ascent).  d_x [S x d] start points in, refined points out; d_val [S] acquisition at the result. */
+size_t bx_refine_workspace_bytes(const bx_factor_t* f, int32_t S);
+int32_t bx_refine(const bx_factor_t* f, float* d_x, int32_t S, int32_t rounds, int32_t acq_id, float acq_param,
+                  float ystar, float* d_val, void* d_ws, size_t ws_bytes, void* stream);
+
+/* Packed (value, index) key: max over keys == jnp.argmax (first occurrence, NaN wins) - optimizer.py:205. */
+uint64_t bx_pack(float value, uint32_t index);
+void bx_unpack(uint64_t key, float* value, uint32_t* index);
+
+/* 3xTF32 tcgen05 self-test: D[128 x N] = A[128 x K] * B[N x K]^T through the same descriptors/pipeline pieces the
+ * scoring kernel uses.  Device pointers, row-major. */
+int32_t bx_selftest_umma(const float* d_A, const float* d_B, float* d_D, int32_t N, int32_t K, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BAYEX_B200_H */

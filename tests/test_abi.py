@@ -1,0 +1,56 @@
+"""The C-ABI library loads (no GPU needed) and exports every symbol include/bayex_b200.h declares."""
+import ctypes
+import math
+import os
+import re
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    text = open(os.path.join(ROOT, "include", "bayex_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(bx_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from bayex_b200 import _lib
+    syms = _header_symbols()
+    assert len(syms) >= 18
+    for s in syms:
+        assert hasattr(_lib.lib, s), f"{s} declared in the header but not exported"
+        assert s in _lib.SIGNATURES, f"{s} has no ctypes signature"
+    assert sorted(_lib.SIGNATURES) == syms
+
+
+def test_version_and_error_string():
+    from bayex_b200 import _lib
+    assert _lib.lib.bx_version() == 100
+    assert isinstance(_lib.lib.bx_last_error(), bytes)
+
+
+def test_packed_argmax_key_semantics():
+    """max over packed keys == jnp.argmax: largest value, NaN beats everything, first index among ties."""
+    from bayex_b200 import _lib
+    pack = _lib.lib.bx_pack
+    vals = [-np.inf, -3.5, -0.0, 0.0, 1e-30, 2.0, np.inf]
+    keys = [pack(ctypes.c_float(v), 7) for v in vals]
+    assert keys[2] == keys[3], "-0.0 and +0.0 compare equal"
+    assert keys == sorted(keys)
+    assert pack(ctypes.c_float(float("nan")), 9) > keys[-1]
+    assert pack(ctypes.c_float(1.0), 3) > pack(ctypes.c_float(1.0), 4)  # lower index wins ties
+    for v, i in [(1.5, 0), (-2.25, 123456), (0.0, 2 ** 32 - 1)]:
+        got_v, got_i = _lib.unpack(pack(ctypes.c_float(v), i))
+        assert got_v == v and got_i == i
+    v, _ = _lib.unpack(pack(ctypes.c_float(float("nan")), 1))
+    assert math.isnan(v)
+
+
+def test_bad_arguments_are_rejected_without_a_gpu():
+    from bayex_b200 import _lib
+    assert _lib.lib.bx_fit_workspace_bytes(0, 3) == 0
+    assert _lib.lib.bx_fit_workspace_bytes(100, 3) > 2 * 128 * 128 * 4
+    rc = _lib.lib.bx_topk(None, 10, 5, 0, None, None, None, 0, None)
+    assert rc == -1 and b"null" in _lib.lib.bx_last_error()

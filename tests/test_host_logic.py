@@ -1,0 +1,123 @@
+"""Host-side mirror of the reference interface (no GPU): keys, domains, state machine helpers, error behaviour."""
+import numpy as np
+import pytest
+
+import bayex_b200 as bayex
+from bayex_b200 import optimizer as bopt, random as brandom
+from bayex_b200.domain import Integer, Real
+from oracle import optimizer as oopt, prng
+
+
+def test_key_helpers_match_oracle_threefry():
+    assert brandom.key(42).tolist() == [0, 42] == prng.key(42).tolist()
+    k = brandom.key(42)
+    for step in range(5):
+        k = brandom.fold_in(k, step)
+        assert k.tolist() == prng.fold_in(prng.key(42) if step == 0 else kk, step).tolist()
+        kk = k
+    assert np.array_equal(brandom.split(brandom.key(7), 5), prng.split(prng.key(7), 5))
+    assert brandom.as_key(3).tolist() == [0, 3]
+    with pytest.raises(ValueError):
+        brandom.as_key([1, 2, 3])
+
+
+# -- reference tests/test_domain.py restated (the transform / eq / hash / assert parts need no device) --------------
+@pytest.mark.parametrize("lower, upper", [(0.0, 1.0), (-5.5, 5.5)])
+def test_real_transform_clips_within_bounds(lower, upper):
+    out = Real(lower, upper).transform(np.array([lower - 1, (lower + upper) / 2, upper + 1]))
+    assert np.all(out >= lower) and np.all(out <= upper)
+
+
+@pytest.mark.parametrize("lower, upper", [(0, 5), (-3, 3)])
+def test_integer_transform_and_type(lower, upper):
+    out = Integer(lower, upper).transform(np.array([lower - 2.3, (lower + upper) / 2.0, upper + 2.7]))
+    assert np.issubdtype(out.dtype, np.floating) and out.dtype == np.float32
+    assert np.all(out >= lower) and np.all(out <= upper) and np.all(out == np.round(out))
+    assert Integer(-3, 3).transform(np.array([0.5, 1.5, 2.5, -0.5])).tolist() == [0.0, 2.0, 2.0, -0.0]  # half-to-even
+
+
+def test_domain_equality_and_hash():
+    a, b, c = Real(0.0, 1.0), Real(0.0, 1.0), Real(1.0, 2.0)
+    assert a == b and a != c and hash(a) == hash(b) and hash(a) != hash(c)
+    i1, i2, i3 = Integer(1, 5), Integer(1, 5), Integer(0, 4)
+    assert i1 == i2 and i1 != i3 and hash(i1) == hash(i2) and hash(i1) != hash(i3)
+    assert Real(0, 1).dtype == np.float32 and Integer(0, 1).dtype == np.int32
+
+
+@pytest.mark.parametrize("lower, upper", [(1.0, 1.0), ("a", 1.0), (1.0, "b"), (5.0, 3.0)])
+def test_real_init_invalid(lower, upper):
+    with pytest.raises((AssertionError, TypeError)):
+        Real(lower, upper)
+
+
+@pytest.mark.parametrize("lower, upper", [(5, 5), ("a", 5), (0, "b"), (10, 1)])
+def test_integer_init_invalid(lower, upper):
+    with pytest.raises(AssertionError):
+        Integer(lower, upper)
+
+
+def test_unknown_acq_raises_reference_message():
+    for acq in ["EI", "PI", "UCB", "LCB"]:
+        bayex.Optimizer(domain={"x": bayex.domain.Real(-2, 2)}, acq=acq)
+    for acq in ["random", "magic"]:
+        with pytest.raises(ValueError, match=f"Acquisition function {acq} is not implemented"):
+            bayex.Optimizer(domain={"x": bayex.domain.Real(-2, 2)}, acq=acq)
+
+
+def test_public_surface_matches_reference_exports():
+    assert bayex.__all__ == ["Optimizer", "domain", "acq"]
+    assert bayex.optimizer.OptimizerState._fields == ("params", "ys", "best_score", "best_params", "mask", "gp_params")
+    assert bayex.gp.GPParams._fields == ("noise", "amplitude", "lengthscale")
+    for name in ("expected_improvement", "probability_improvement", "upper_confidence_bounds", "lower_confidence_bounds"):
+        assert callable(getattr(bayex.acq, name))
+    for name in ("MASK_VARIANCE", "GPState", "exp_quadratic", "cov", "softplus", "gaussian_process",
+                 "marginal_likelihood", "predict", "grad_fun", "neg_log_likelihood", "posterior_fit"):
+        assert hasattr(bayex.gp, name)
+
+
+def test_expand_doubles_buffers_like_reference():
+    opt = bayex.Optimizer({"x": Real(0, 1), "k": Integer(0, 9)})
+    oo = oopt.Optimizer({"x": __import__("oracle").domain.Real(0, 1), "k": __import__("oracle").domain.Integer(0, 9)})
+    st = bopt.OptimizerState({"x": np.arange(10, dtype=np.float32), "k": np.arange(10, dtype=np.int32)},
+                             np.arange(10, dtype=np.float32), 9.0, {}, np.ones(10, bool), None)
+    a, b = opt.expand(st), oo.expand(oopt.OptimizerState(*st))
+    assert a.mask.shape == b.mask.shape == (20,) and np.array_equal(a.mask, b.mask)
+    assert np.array_equal(a.ys, b.ys) and a.params["k"].dtype == np.int32
+    st2 = st._replace(mask=np.array([True] * 9 + [False]))
+    assert opt.expand(st2).mask.shape == (10,)
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    opt = bayex.Optimizer({"x": Real(0, 1)})
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        opt.init([0.1, 0.2], {"x": [0.0, 1.0]})
+
+
+def test_shard_range_partitions_the_candidate_axis():
+    for size in (1, 7, 10_000, 2 ** 24):
+        for world in (1, 2, 3, 4, 8):
+            spans = [bopt.shard_range(size, r, world) for r in range(world)]
+            assert sum(c for _, c in spans) == size
+            pos = 0
+            for b, c in spans:
+                assert b == pos or c == 0
+                pos += c
+
+
+def test_merge_topk_equals_global_stable_argsort():
+    rng = np.random.default_rng(0)
+    vals = rng.standard_normal(4000).astype(np.float32)
+    vals[rng.integers(0, 4000, 300)] = 0.25  # ties
+    vals[[5, 77]] = np.nan
+    vals[100] = -0.0
+    want = oopt.jnp_argsort(vals)[-50:]
+    parts_v, parts_i = [], []
+    for r in range(4):
+        b, c = bopt.shard_range(4000, r, 4)
+        loc = oopt.jnp_argsort(vals[b:b + c])[-50:] + b
+        parts_v.append(vals[loc]); parts_i.append(loc.astype(np.int32))
+    v, i = bopt.merge_topk(np.concatenate(parts_v), np.concatenate(parts_i), 50)
+    assert np.array_equal(i, want)
