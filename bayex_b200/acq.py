@@ -29,7 +29,7 @@ def _score(acq, x_pred, xs, ys, mask, gp_params, param):
     xt = np.asarray(x_pred, dtype=np.float32)
     xt = xt[:, None] if xt.ndim == 1 else xt
     out = post.score_points(xt, acq=acq, param=param, ystar=ystar_for(acq, ys, mask), want=("acq",))
-    with torch.cuda.stream(post.stream):
+    with engine.on_stream(post.stream, post.dev):
         return out["acq"].cpu().numpy()
 
 

@@ -1,13 +1,535 @@
-// tcgen05 scoring engine (placeholder until the UMMA pipeline lands in this file).
+// tcgen05 scoring engine: the one dense contraction of the hot path on the 5th-gen tensor cores.
+//
+// Per tile of 128 candidates (UMMA M = 128, one TMEM lane per candidate):
+//     V[cand, row] = sum_obs K*[cand, obs] * T[row, obs]        (gp.py:68 as a GEMM against T = L^-1)
+// A = K*^T tile (128 cand x 32 obs, K-major, SWIZZLE_128B) is *generated* in shared memory by SIMT producer warps
+//     (Threefry candidates -> squared distances -> ex2 -> TF32 head/tail split); it never exists in HBM (gp.py:60-64).
+// B = T tile (128 rows x 32 obs, K-major, SWIZZLE_128B), TMA-loaded from the precomputed head/tail matrices Thi/Tlo.
+// D = fp32 accumulators in TMEM: 4 row blocks x 128 columns = all 512 columns.  3xTF32: hi*hi + lo*hi + hi*lo.
+// Epilogue warps read finished row blocks with tcgen05.ld, square-and-sum per candidate (diag of gp.py:69, quirk Q8),
+// then apply std (gp.py:70), the acquisition closed forms (acq.py) and the packed arg-max (optimizer.py:205).
+//
+// Loop nest per tile: super-blocks of 4 row blocks (512 rows of T); inside, K-blocks J outer so each generated K* tile
+// feeds up to 4 accumulators; the triangular structure of T skips (row block, J) pairs above the diagonal.
+//
+// Warp roles (448 threads): 0 = TMA producer, 1 = MMA issuer (+ TMEM alloc), 2..5 = epilogue, 6..13 = K* producers.
+#include <cuda.h>
+
 #include "internal.h"
+
 namespace bx {
-bool score_tc_supported(const bx_factor_t& f) { (void)f; return false; }
-int32_t launch_score_tc(cudaStream_t, const ScoreArgs&, const SamplerPack&) {
-  set_error("tcgen05 engine not built");
+namespace tc {
+
+constexpr int TM = 128, BN = 128, BK = 32, NACC = 4, SA = 2, SB = 4;
+constexpr int TILE_BYTES = TM * BK * 4;  // 16 KiB: one operand tile (hi or lo)
+constexpr int NTHREADS = 448;
+constexpr int PROD0 = 6 * 32;  // first producer thread
+constexpr int NPROD = 256;
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// Bounded wait: a protocol bug must trap (process dies with a launch failure) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  const long long t0 = clock64();
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) return;
+    if (clock64() - t0 > 4000000000ll) {
+      printf("bayex_b200: mbarrier timeout (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int x, int y) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(dst), "l"((uint64_t)map), "r"(bar), "r"(x), "r"(y)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// 32 lanes x 32 consecutive columns: thread i of the warp receives TMEM lane (lane_base + i), columns [col, col+32)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, SWIZZLE_128B operand tile (rows x 32 fp32): 8-row groups 1024 B apart; descriptor version 1 (sm_100).
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;              // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;    // stride byte offset: 8 rows * 128 B
+  d |= (uint64_t)1 << 46;              // descriptor version
+  d |= (uint64_t)2 << 61;              // SWIZZLE_128B
+  return d;
+}
+// kind::tf32, fp32 accumulate, A and B K-major, M = 128, N = n
+__host__ __device__ constexpr uint32_t make_idesc(int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+}
+// byte offset of 16-byte chunk `q` of row `r` inside a SWIZZLE_128B tile
+__device__ __forceinline__ uint32_t swz(int r, int q) { return (uint32_t)(r * 128 + ((q ^ (r & 7)) << 4)); }
+
+__device__ __forceinline__ void split_store(char* hi_tile, char* lo_tile, int row, int q, float v0, float v1, float v2, float v3) {
+  float4 h, l;
+  h.x = __uint_as_float(__float_as_uint(v0) & 0xFFFFE000u); l.x = v0 - h.x;
+  h.y = __uint_as_float(__float_as_uint(v1) & 0xFFFFE000u); l.y = v1 - h.y;
+  h.z = __uint_as_float(__float_as_uint(v2) & 0xFFFFE000u); l.z = v2 - h.z;
+  h.w = __uint_as_float(__float_as_uint(v3) & 0xFFFFE000u); l.w = v3 - h.w;
+  const uint32_t off = swz(row, q);
+  *reinterpret_cast<float4*>(hi_tile + off) = h;
+  *reinterpret_cast<float4*>(lo_tile + off) = l;
+}
+
+struct Smem {
+  // operand tiles first (1024-byte aligned)
+  char a_hi[SA][TILE_BYTES], a_lo[SA][TILE_BYTES];
+  char b_hi[SB][TILE_BYTES], b_lo[SB][TILE_BYTES];
+  float mean_s[2][TM];
+  unsigned long long full_a[SA], empty_a[SA], full_b[SB], empty_b[SB], tmem_full[NACC], tmem_empty[NACC], mean_full, mean_empty;
+  uint32_t tmem_base;
+};
+
+// ------------------------------------------------------------------------------------------------------------------
+template <int D4>
+__global__ void __launch_bounds__(NTHREADS, 1)
+score_tc_kernel(const __grid_constant__ ScoreArgs a, const __grid_constant__ SamplerPack sp,
+                const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  Smem& S = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // [2][BK * D4 + BK]: observation rows + alpha of the current K-block (16-byte aligned for float4 reads)
+  float* us = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(&S + 1) + 15) & ~(uintptr_t)15);
+  constexpr int US = BK * D4 + BK;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int np = a.f.np;
+  const int nRB = np / BN;                 // row blocks of T
+  const int nSB = (nRB + NACC - 1) / NACC;  // super-blocks
+  const uint64_t ntiles = (a.m_count + TM - 1) / TM;
+
+  if (tid == 0) {
+    for (int i = 0; i < SA; ++i) { mbar_init(smem_u32(&S.full_a[i]), NPROD / 32); mbar_init(smem_u32(&S.empty_a[i]), 1); }
+    for (int i = 0; i < SB; ++i) { mbar_init(smem_u32(&S.full_b[i]), 1); mbar_init(smem_u32(&S.empty_b[i]), 1); }
+    for (int i = 0; i < NACC; ++i) { mbar_init(smem_u32(&S.tmem_full[i]), 1); mbar_init(smem_u32(&S.tmem_empty[i]), 4); }
+    mbar_init(smem_u32(&S.mean_full), NPROD / 32);
+    mbar_init(smem_u32(&S.mean_empty), 4);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(&S.tmem_base), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = S.tmem_base;
+
+  if (warp == 0) {
+    // ===== TMA producer: T tiles (head + tail) =====
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        for (int sb = 0; sb < nSB; ++sb) {
+          const int rb0 = sb * NACC, rb1 = min(rb0 + NACC, nRB);
+          for (int J = 0; J < 4 * rb1; ++J) {
+            for (int rb = max(rb0, J >> 2); rb < rb1; ++rb, ++it) {
+              const uint32_t st = it % SB, ph = (it / SB) & 1;
+              mbar_wait(smem_u32(&S.empty_b[st]), ph ^ 1);
+              const uint32_t bar = smem_u32(&S.full_b[st]);
+              mbar_expect_tx(bar, 2 * TILE_BYTES);
+              tma_load_2d(smem_u32(S.b_hi[st]), &map_hi, bar, J * BK, rb * BN);
+              tma_load_2d(smem_u32(S.b_lo[st]), &map_lo, bar, J * BK, rb * BN);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(BN);
+      uint32_t ita = 0, itb = 0, acc_use[NACC] = {0, 0, 0, 0};
+      for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        for (int sb = 0; sb < nSB; ++sb) {
+          const int rb0 = sb * NACC, rb1 = min(rb0 + NACC, nRB);
+          for (int J = 0; J < 4 * rb1; ++J, ++ita) {
+            const uint32_t sa = ita % SA, pa = (ita / SA) & 1;
+            mbar_wait(smem_u32(&S.full_a[sa]), pa);
+            tc_fence_after();
+            const uint64_t ah = make_desc(smem_u32(S.a_hi[sa])), al = make_desc(smem_u32(S.a_lo[sa]));
+            for (int rb = max(rb0, J >> 2); rb < rb1; ++rb, ++itb) {
+              const int acc = rb - rb0;
+              if (J == 0) {  // first write of this accumulator in this super-block: wait until the epilogue drained it
+                mbar_wait(smem_u32(&S.tmem_empty[acc]), (acc_use[acc] & 1) ^ 1);
+                tc_fence_after();
+              }
+              const uint32_t st = itb % SB, pb = (itb / SB) & 1;
+              mbar_wait(smem_u32(&S.full_b[st]), pb);
+              tc_fence_after();
+              const uint64_t bh = make_desc(smem_u32(S.b_hi[st])), bl = make_desc(smem_u32(S.b_lo[st]));
+              const uint32_t d = tmem + (uint32_t)(acc * BN);
+#pragma unroll
+              for (int ks = 0; ks < BK / 8; ++ks) {  // UMMA K = 8 for tf32 = 32 bytes inside the swizzle atom
+                const uint64_t o = (uint64_t)(ks * 2);
+                umma_tf32(d, ah + o, bh + o, idesc, (J | ks) != 0);
+                umma_tf32(d, al + o, bh + o, idesc, 1u);
+                umma_tf32(d, ah + o, bl + o, idesc, 1u);
+              }
+              umma_commit(smem_u32(&S.empty_b[st]));
+              if (J == 4 * rb + 3) {  // last K-block below the diagonal: this row block of V is complete
+                umma_commit(smem_u32(&S.tmem_full[acc]));
+                ++acc_use[acc];
+              }
+            }
+            umma_commit(smem_u32(&S.empty_a[sa]));
+          }
+        }
+      }
+    }
+  } else if (warp < 6) {
+    // ===== epilogue: TMEM -> sum of squares -> std -> acquisition -> arg-max =====
+    const int q = warp & 3, cl = q * 32 + lane;  // TMEM lane quarter of this warp; candidate within the tile
+    const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
+    const float amp = a.f.d_hyp[HYP_AMP], ymean = a.f.d_hyp[HYP_YMEAN];
+    uint32_t acc_use[NACC] = {0, 0, 0, 0}, tiles_done = 0;
+    unsigned long long best = 0ull;
+    for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tiles_done) {
+      float ss = 0.f;
+      for (int sb = 0; sb < nSB; ++sb) {
+        const int rb0 = sb * NACC, rb1 = min(rb0 + NACC, nRB);
+        for (int acc = 0; acc < rb1 - rb0; ++acc) {
+          mbar_wait(smem_u32(&S.tmem_full[acc]), acc_use[acc] & 1);
+          ++acc_use[acc];
+          tc_fence_after();
+#pragma unroll
+          for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t r[32];
+            tmem_ld32(lane_addr + (uint32_t)(acc * BN + c0), r);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const float v = __uint_as_float(r[i]);
+              ss = fmaf(v, v, ss);
+            }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&S.tmem_empty[acc]));
+        }
+      }
+      mbar_wait(smem_u32(&S.mean_full), tiles_done & 1);
+      const float mu = S.mean_s[0][cl] + S.mean_s[1][cl] + ymean;  // gp.py:67
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&S.mean_empty));
+      const uint64_t row = tile * TM + cl;
+      if (row < a.m_count) {
+        const float var = amp - ss;                    // gp.py:69 (diagonal only)
+        const float sd = sqrtf(fmaxf(var, 1e-10f));    // gp.py:70
+        const float av = acquisition(a.acq_id, mu, sd, a.ystar, a.acq_param);
+        if (a.mu) a.mu[row] = mu;
+        if (a.sigma) a.sigma[row] = sd;
+        if (a.acq) a.acq[row] = av;
+        const unsigned long long key = pack_best(av, (uint32_t)(a.index_base + row));
+        best = key > best ? key : best;
+      }
+    }
+    if (a.best) {
+      best = warp_max_u64(best);
+      if (lane == 0 && best) atomicMax(a.best, best);
+    }
+  } else {
+    // ===== K* producers: 2 threads per candidate, 16 observations each per K-block =====
+    const int pt = tid - PROD0, c = pt & (TM - 1), h = pt >> 7;
+    const float amp = a.f.d_hyp[HYP_AMP];
+    uint32_t ita = 0, tiles_done = 0;
+    for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tiles_done) {
+      float cr[D4];
+      {
+        const uint64_t gidx = a.m_begin + tile * TM + c;
+#pragma unroll
+        for (int k = 0; k < D4; ++k) cr[k] = (k < a.f.d) ? sample_coord(sp.dim[k], gidx) * a.f.d_scale[k] : 0.f;
+      }
+      float mpart = 0.f;
+      for (int sb = 0; sb < nSB; ++sb) {
+        const int rb1 = min(sb * NACC + NACC, nRB);
+        const bool last_sb = (sb == nSB - 1);
+        const int nJ = 4 * rb1;
+        // stage observation rows of K-block 0
+        for (int e = pt; e < US; e += NPROD)
+          us[e] = (e < BK * D4) ? a.f.d_U[e] : a.f.d_alpha[e - BK * D4];
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        for (int J = 0; J < nJ; ++J, ++ita) {
+          const float* u = us + (J & 1) * US;
+          float pre[(US + NPROD - 1) / NPROD];
+          if (J + 1 < nJ) {  // prefetch the next K-block's rows into registers
+#pragma unroll
+            for (int i = 0; i < (US + NPROD - 1) / NPROD; ++i) {
+              const int e = pt + i * NPROD;
+              pre[i] = (e < BK * D4) ? a.f.d_U[(size_t)(J + 1) * BK * D4 + e]
+                                     : (e < US ? a.f.d_alpha[(J + 1) * BK + e - BK * D4] : 0.f);
+            }
+          }
+          const uint32_t sa = ita % SA, pa = (ita / SA) & 1;
+          mbar_wait(smem_u32(&S.empty_a[sa]), pa ^ 1);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {  // 4 groups of 4 observations -> one 16-byte chunk of the A row each
+            float kv[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int kk = h * 16 + g * 4 + i;
+              float s = 0.f;
+#pragma unroll
+              for (int k4 = 0; k4 < D4; k4 += 4) {
+                const float4 uv = *reinterpret_cast<const float4*>(u + kk * D4 + k4);
+                const float d0 = uv.x - cr[k4], d1 = uv.y - cr[k4 + 1], d2 = uv.z - cr[k4 + 2], d3 = uv.w - cr[k4 + 3];
+                s = fmaf(-d0, d0, s); s = fmaf(-d1, d1, s); s = fmaf(-d2, d2, s); s = fmaf(-d3, d3, s);
+              }
+              kv[i] = amp * ex2_approx(s);  // gp.py:64 with the length scale and log2(e) folded into the coordinates
+              if (last_sb) mpart = fmaf(u[BK * D4 + kk], kv[i], mpart);  // gp.py:66-67
+            }
+            split_store(S.a_hi[sa], S.a_lo[sa], c, h * 4 + g, kv[0], kv[1], kv[2], kv[3]);
+          }
+          fence_proxy_async();  // generic-proxy stores -> visible to the tensor core (async proxy)
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&S.full_a[sa]));
+          if (J + 1 < nJ) {
+            float* un = us + ((J + 1) & 1) * US;
+#pragma unroll
+            for (int i = 0; i < (US + NPROD - 1) / NPROD; ++i) {
+              const int e = pt + i * NPROD;
+              if (e < US) un[e] = pre[i];
+            }
+          }
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+        }
+      }
+      mbar_wait(smem_u32(&S.mean_empty), (tiles_done & 1) ^ 1);
+      S.mean_s[h][c] = mpart;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&S.mean_full));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+// ---- host side ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// fp32 row-major [rows x cols] matrix, box = 128 rows x 32 columns, SWIZZLE_128B
+static int32_t make_map(CUtensorMap* m, const float* base, uint64_t rows, uint64_t cols, uint64_t ld) {
+  EncodeTiledFn fn = encode_fn();
+  BX_CHECK_ARG(fn, BX_E_UNSUPPORTED, "cuTensorMapEncodeTiled not available from the driver");
+  const cuuint64_t dims[2] = {cols, rows};
+  const cuuint64_t strides[1] = {ld * sizeof(float)};
+  const cuuint32_t box[2] = {BK, BN};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  BX_CHECK_ARG(r == CUDA_SUCCESS, BX_E_UNSUPPORTED, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return 0;
+}
+
+template <int D4>
+static int32_t launch_d4(cudaStream_t s, const ScoreArgs& a, const SamplerPack& sp, const CUtensorMap& mh, const CUtensorMap& ml) {
+  const size_t smem = sizeof(Smem) + 1024 + 16 + sizeof(float) * 2 * (BK * D4 + BK);
+  BX_CUDA(cudaFuncSetAttribute(score_tc_kernel<D4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int dev = 0, sms = 0;
+  BX_CUDA(cudaGetDevice(&dev));
+  BX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const uint64_t ntiles = (a.m_count + TM - 1) / TM;
+  const unsigned grid = (unsigned)(ntiles < (uint64_t)sms ? ntiles : (uint64_t)sms);
+  score_tc_kernel<D4><<<grid, NTHREADS, smem, s>>>(a, sp, mh, ml);
+  BX_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace tc
+
+bool score_tc_supported(const bx_factor_t& f) { return f.d_Thi && f.d_Tlo && f.d4 <= 32; }
+
+int32_t launch_score_tc(cudaStream_t s, const ScoreArgs& a, const SamplerPack& sp) {
+  CUtensorMap mh, ml;
+  int32_t rc = tc::make_map(&mh, a.f.d_Thi, a.f.np, a.f.np, a.f.np);
+  if (rc) return rc;
+  rc = tc::make_map(&ml, a.f.d_Tlo, a.f.np, a.f.np, a.f.np);
+  if (rc) return rc;
+  switch (a.f.d4) {
+    case 4: return tc::launch_d4<4>(s, a, sp, mh, ml);
+    case 8: return tc::launch_d4<8>(s, a, sp, mh, ml);
+    case 12: return tc::launch_d4<12>(s, a, sp, mh, ml);
+    case 16: return tc::launch_d4<16>(s, a, sp, mh, ml);
+    case 20: return tc::launch_d4<20>(s, a, sp, mh, ml);
+    case 24: return tc::launch_d4<24>(s, a, sp, mh, ml);
+    case 28: return tc::launch_d4<28>(s, a, sp, mh, ml);
+    case 32: return tc::launch_d4<32>(s, a, sp, mh, ml);
+  }
+  set_error("tcgen05 engine supports d <= 32 (d4=%d)", a.f.d4);
   return BX_E_UNSUPPORTED;
 }
+
+// ---- self-test: D[128 x 128] = A[128 x K] * B[128 x K]^T with the same descriptors / swizzle / TMA / tcgen05.ld -----
+namespace tc {
+
+struct SelfSmem {
+  char a_hi[TILE_BYTES], a_lo[TILE_BYTES], b_hi[TILE_BYTES], b_lo[TILE_BYTES];
+  unsigned long long full_b, mma_done;
+  uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(128, 1)
+selftest_kernel(const float* __restrict__ A, float* __restrict__ D, int K, const __grid_constant__ CUtensorMap map_hi,
+                const __grid_constant__ CUtensorMap map_lo) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  SelfSmem& S = *reinterpret_cast<SelfSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    mbar_init(smem_u32(&S.full_b), 1);
+    mbar_init(smem_u32(&S.mma_done), 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(smem_u32(&S.tmem_base), 128);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = S.tmem_base;
+  const uint32_t idesc = make_idesc(BN);
+  for (int kb = 0; kb < K / BK; ++kb) {
+    if (tid == 0) {
+      const uint32_t bar = smem_u32(&S.full_b);
+      mbar_expect_tx(bar, 2 * TILE_BYTES);
+      tma_load_2d(smem_u32(S.b_hi), &map_hi, bar, kb * BK, 0);
+      tma_load_2d(smem_u32(S.b_lo), &map_lo, bar, kb * BK, 0);
+    }
+    for (int qd = 0; qd < 8; ++qd) {  // row `tid` of A, 8 chunks of 4 floats
+      const float4 v = *reinterpret_cast<const float4*>(A + (size_t)tid * K + kb * BK + qd * 4);
+      split_store(S.a_hi, S.a_lo, tid, qd, v.x, v.y, v.z, v.w);
+    }
+    fence_proxy_async();
+    __syncthreads();
+    if (tid == 0) {
+      mbar_wait(smem_u32(&S.full_b), kb & 1);
+      tc_fence_after();
+      const uint64_t ah = make_desc(smem_u32(S.a_hi)), al = make_desc(smem_u32(S.a_lo));
+      const uint64_t bh = make_desc(smem_u32(S.b_hi)), bl = make_desc(smem_u32(S.b_lo));
+      for (int ks = 0; ks < BK / 8; ++ks) {
+        const uint64_t o = (uint64_t)(ks * 2);
+        umma_tf32(tmem, ah + o, bh + o, idesc, (kb | ks) != 0);
+        umma_tf32(tmem, al + o, bh + o, idesc, 1u);
+        umma_tf32(tmem, ah + o, bl + o, idesc, 1u);
+      }
+      umma_commit(smem_u32(&S.mma_done));
+    }
+    mbar_wait(smem_u32(&S.mma_done), kb & 1);  // operands consumed: the tiles may be overwritten
+    tc_fence_after();
+  }
+  const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
+  for (int c0 = 0; c0 < BN; c0 += 32) {
+    uint32_t r[32];
+    tmem_ld32(lane_addr + (uint32_t)c0, r);
+    for (int i = 0; i < 32; ++i) D[(size_t)(warp * 32 + lane) * BN + c0 + i] = __uint_as_float(r[i]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 128);
+  }
+}
+
+__global__ void split_kernel(const float* __restrict__ x, size_t n, float* hi, float* lo) {
+  const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  const float h = __uint_as_float(__float_as_uint(x[e]) & 0xFFFFE000u);
+  hi[e] = h;
+  lo[e] = x[e] - h;
+}
+
+}  // namespace tc
 }  // namespace bx
-extern "C" int32_t bx_selftest_umma(const float*, const float*, float*, int32_t, int32_t, void*) {
-  bx::set_error("tcgen05 engine not built");
-  return BX_E_UNSUPPORTED;
+
+extern "C" int32_t bx_selftest_umma(const float* d_A, const float* d_B, float* d_D, int32_t N, int32_t K, void* stream) {
+  using namespace bx;
+  BX_CHECK_ARG(d_A && d_B && d_D, BX_E_ARG, "null pointer argument");
+  BX_CHECK_ARG(N == tc::BN && K > 0 && K % tc::BK == 0, BX_E_RANGE, "self-test needs N == 128 and K a multiple of 32");
+  cudaStream_t s = (cudaStream_t)stream;
+  float *hi = nullptr, *lo = nullptr;
+  const size_t n = (size_t)N * K;
+  BX_CUDA(cudaMallocAsync(&hi, n * sizeof(float), s));
+  BX_CUDA(cudaMallocAsync(&lo, n * sizeof(float), s));
+  tc::split_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d_B, n, hi, lo);
+  BX_LAUNCH_CHECK();
+  CUtensorMap mh, ml;
+  int32_t rc = tc::make_map(&mh, hi, N, K, K);
+  if (rc == 0) rc = tc::make_map(&ml, lo, N, K, K);
+  if (rc == 0) {
+    const size_t smem = sizeof(tc::SelfSmem) + 1024;
+    cudaFuncSetAttribute(tc::selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    tc::selftest_kernel<<<1, 128, smem, s>>>(d_A, d_D, K, mh, ml);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { set_error("selftest launch failed: %s", cudaGetErrorString(e)); rc = (int32_t)e; }
+  }
+  cudaFreeAsync(hi, s);
+  cudaFreeAsync(lo, s);
+  return rc;
 }

@@ -7,6 +7,7 @@ torch is used for device memory, streams and (optionally) ``torch.distributed``;
 from __future__ import annotations
 
 import ctypes as C
+from contextlib import contextmanager
 
 import numpy as np
 import torch
@@ -30,6 +31,17 @@ def stream(dev: torch.device) -> torch.cuda.Stream:
     if s is None:
         s = _STREAMS[dev.index] = torch.cuda.Stream(device=dev)
     return s
+
+
+@contextmanager
+def on_stream(st: torch.cuda.Stream, dev: torch.device):
+    """Run on the library's private stream, ordered after the caller's current stream on entry and before it on exit,
+    so tensors handed in or returned can be used on the caller's stream without further synchronisation."""
+    cur = torch.cuda.current_stream(dev)
+    st.wait_stream(cur)
+    with torch.cuda.stream(st):
+        yield
+    cur.wait_stream(st)
 
 
 def _ptr(t):
@@ -93,7 +105,7 @@ class Posterior:
         self.np_ = (self.n + _lib.TILE - 1) // _lib.TILE * _lib.TILE
         self.d4 = (self.d + 3) // 4 * 4
         self.want_tc = want_tc
-        with torch.cuda.stream(self.stream):
+        with on_stream(self.stream, self.dev):
             self.X = torch.from_numpy(x).to(self.dev, non_blocking=False)
             self.y = torch.from_numpy(np.ascontiguousarray(y, dtype=np.float32)).to(self.dev)
             self.raw = torch.from_numpy(np.ascontiguousarray(raw, dtype=np.float32)).to(self.dev)
@@ -108,8 +120,8 @@ class Posterior:
     def fit_hypers(self, lr=1e-3, steps=100, trace=False, use_graph=True):
         """gp.py:90-110 on the device; updates ``self.raw`` in place."""
         ws, nbytes = self._ws()
-        tr = torch.empty((steps, self.d + 2), dtype=torch.float32, device=self.dev) if trace else None
-        with torch.cuda.stream(self.stream):
+        with on_stream(self.stream, self.dev):
+            tr = torch.empty((steps, self.d + 2), dtype=torch.float32, device=self.dev) if trace else None
             check(lib.bx_fit_adamw(_ptr(self.X), _ptr(self.y), self.n, self.d, _ptr(self.raw), lr, steps, _ptr(tr),
                                    _ptr(ws), nbytes, 1 if use_graph else 0, C.c_void_p(self.stream.cuda_stream)),
                   "bx_fit_adamw")
@@ -119,8 +131,8 @@ class Posterior:
     def nlml_grad(self):
         """(nlml, loss, dloss/draw, dnlml/draw) at the current raw hypers (gp.py:74-87)."""
         ws, nbytes = self._ws()
-        out = torch.empty(2 + 2 * (self.d + 2), dtype=torch.float32, device=self.dev)
-        with torch.cuda.stream(self.stream):
+        with on_stream(self.stream, self.dev):
+            out = torch.empty(2 + 2 * (self.d + 2), dtype=torch.float32, device=self.dev)
             check(lib.bx_nlml_grad(_ptr(self.X), _ptr(self.y), self.n, self.d, _ptr(self.raw), _ptr(out), _ptr(ws),
                                    nbytes, C.c_void_p(self.stream.cuda_stream)), "bx_nlml_grad")
             o = out.cpu().numpy()
@@ -131,7 +143,7 @@ class Posterior:
         """gp.py:41-49 once: factor arrays for every later scoring call."""
         ws, nbytes = self._ws()
         np_, d4 = self.np_, self.d4
-        with torch.cuda.stream(self.stream):
+        with on_stream(self.stream, self.dev):
             if self._bufs is None:
                 e = lambda *s: torch.empty(s, dtype=torch.float32, device=self.dev)
                 self._bufs = dict(U=e(np_, d4), T=e(np_, np_), alpha=e(np_), scale=e(d4), hyp=e(8),
@@ -153,11 +165,11 @@ class Posterior:
 
     def hyp(self) -> np.ndarray:
         self._need_factor()
-        with torch.cuda.stream(self.stream):
+        with on_stream(self.stream, self.dev):
             return self._bufs["hyp"].cpu().numpy()
 
     def raw_host(self) -> np.ndarray:
-        with torch.cuda.stream(self.stream):
+        with on_stream(self.stream, self.dev):
             return self.raw.cpu().numpy()
 
     def _need_factor(self):
@@ -185,7 +197,7 @@ class Posterior:
     def score_points(self, cand, acq="UCB", param=0.0, ystar=0.0, want=("mu", "sigma", "acq"), best=False):
         """Posterior moments / acquisition at explicit points (gp.py:59-71, acq.py).  Returns device tensors."""
         self._need_factor()
-        with torch.cuda.stream(self.stream):
+        with on_stream(self.stream, self.dev):
             if not isinstance(cand, torch.Tensor):
                 cand = torch.from_numpy(np.ascontiguousarray(cand, dtype=np.float32)).to(self.dev)
             cand = cand.contiguous()
@@ -203,7 +215,7 @@ class Posterior:
                         best=None):
         """Fused Threefry -> posterior -> acquisition -> arg-max over a slice of the candidate draw."""
         self._need_factor()
-        with torch.cuda.stream(self.stream):
+        with on_stream(self.stream, self.dev):
             vals = torch.empty(m_count, dtype=torch.float32, device=self.dev) if keep_acq else None
             if best is None:
                 best = torch.zeros(1, dtype=torch.int64, device=self.dev)
@@ -213,7 +225,7 @@ class Posterior:
         return vals, best
 
     def topk(self, vals: torch.Tensor, k: int, index_base=0):
-        with torch.cuda.stream(self.stream):
+        with on_stream(self.stream, self.dev):
             M = vals.numel()
             nbytes = lib.bx_topk_workspace_bytes(M, k)
             ws = torch.empty(nbytes, dtype=torch.uint8, device=self.dev)
@@ -224,7 +236,7 @@ class Posterior:
         return ov, oi
 
     def gather(self, key, dims, idx: torch.Tensor):
-        with torch.cuda.stream(self.stream):
+        with on_stream(self.stream, self.dev):
             k = idx.numel()
             out = torch.empty((k, self.d), dtype=torch.float32, device=self.dev)
             check(lib.bx_threefry_gather(_lib.key_words(key), dims, self.d, _ptr(idx), k, _ptr(out),
@@ -233,7 +245,7 @@ class Posterior:
 
     def refine(self, starts: torch.Tensor, rounds, acq, param, ystar):
         self._need_factor()
-        with torch.cuda.stream(self.stream):
+        with on_stream(self.stream, self.dev):
             x = starts.clone().contiguous()
             S = x.shape[0]
             nbytes = lib.bx_refine_workspace_bytes(C.byref(self.factor), S)
@@ -249,7 +261,7 @@ def threefry_fill(key, dims, d, m_begin, m_count, dev=None) -> torch.Tensor:
     """Candidates [m_begin, m_begin+m_count) of ``sample_params(key, (M,))`` as a device tensor [m_count, d]."""
     dev = device() if dev is None else dev
     st = stream(dev)
-    with torch.cuda.stream(st):
+    with on_stream(st, dev):
         out = torch.empty((m_count, d), dtype=torch.float32, device=dev)
         check(lib.bx_threefry_fill(_lib.key_words(key), dims, d, int(m_begin), int(m_count), _ptr(out),
                                    C.c_void_p(st.cuda_stream)), "bx_threefry_fill")
@@ -260,7 +272,7 @@ def domain_sample(key, dims, count, dev=None) -> torch.Tensor:
     """``Domain.sample(key, (count,))``: one domain, the key used as is (domain.py:74,130)."""
     dev = device() if dev is None else dev
     st = stream(dev)
-    with torch.cuda.stream(st):
+    with on_stream(st, dev):
         out = torch.empty((count,), dtype=torch.float32, device=dev)
         check(lib.bx_domain_sample(_lib.key_words(key), dims, 0, int(count), _ptr(out), C.c_void_p(st.cuda_stream)),
               "bx_domain_sample")

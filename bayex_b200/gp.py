@@ -37,7 +37,7 @@ def cov(x1, x2, mask1, mask2):
     b = b[:, None] if b.ndim == 1 else b
     m1 = np.asarray(mask1, dtype=np.float32).reshape(-1)
     m2 = np.asarray(mask2, dtype=np.float32).reshape(-1)
-    with torch.cuda.stream(st):
+    with engine.on_stream(st, dev):
         ta, tb, t1, t2 = (torch.from_numpy(np.ascontiguousarray(v)).to(dev) for v in (a, b, m1, m2))
         out = torch.empty((a.shape[0], b.shape[0]), dtype=torch.float32, device=dev)
         check(lib.bx_cov(engine._ptr(ta), a.shape[0], engine._ptr(tb), b.shape[0], a.shape[1], engine._ptr(t1),
@@ -66,7 +66,7 @@ def gaussian_process(params, x, y, mask, xt=None, compute_ml=False):
     xt = np.asarray(xt, dtype=np.float32)
     xt = xt[:, None] if xt.ndim == 1 else xt
     out = post.score_points(xt, want=("mu", "sigma"))
-    with torch.cuda.stream(post.stream):
+    with engine.on_stream(post.stream, post.dev):
         return out["mu"].cpu().numpy(), out["sigma"].cpu().numpy()
 
 

@@ -168,7 +168,7 @@ class Optimizer:
         starts = post.gather(key, self._dims, ti)  # optimizer.py:197
         optimized, _ = post.refine(starts, refine_rounds, name, param, ystar)  # optimizer.py:198-199
         sc = post.score_points(optimized, acq=name, param=param, ystar=ystar, want=("acq",), best=True)  # :200
-        with torch.cuda.stream(post.stream):
+        with engine.on_stream(post.stream, post.dev):
             b_opt = engine.to_unsigned(int(sc["best"].item()))
             b_rnd = engine.to_unsigned(int(best.item()))
             opt_host = optimized.cpu().numpy()
@@ -179,13 +179,13 @@ class Optimizer:
         else:
             _, j = _lib.unpack(b_rnd)
             idx = torch.tensor([j], dtype=torch.int64).to(torch.int32).to(post.dev)
-            with torch.cuda.stream(post.stream):
+            with engine.on_stream(post.stream, post.dev):
                 point = post.gather(key, self._dims, idx).cpu().numpy()[0]
             chosen = len(opt_host) + j
         best_params = self.param_space.to_dict(point[None])  # optimizer.py:207
         best_params = {k: np.asarray(v, dtype=np.float32) for k, v in best_params.items()}
         if details:
-            with torch.cuda.stream(post.stream):
+            with engine.on_stream(post.stream, post.dev):
                 info = dict(acq_vals=vals.cpu().numpy(), top_idxs=ti.cpu().numpy(), top_vals=tv.cpu().numpy(),
                             optimized=opt_host, opt_vals=sc["acq"].cpu().numpy(), chosen=chosen,
                             best_opt=_lib.unpack(b_opt), best_rnd=_lib.unpack(b_rnd), m_begin=m_begin, m_count=m_count)

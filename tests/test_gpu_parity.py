@@ -31,6 +31,28 @@ def assert_close(got, ref64, ref32=None, rtol=RTOL, what=""):
                            f"(tol there {tol[np.argmax(err)]:.3e}, ref {ref64.ravel()[np.argmax(err)]:.6e})")
 
 
+def check_acq(acq, got, mu_gpu, sd_gpu, mu64, sd64, mu32, sd32, ys, mask):
+    """Acquisition parity in two parts: (1) the closed form itself, evaluated in fp64 on the GPU's own moments, to
+    2e-5 of scale; (2) against the fp64 oracle, with the tolerance the moments' own 1e-4 budget propagates to through
+    the closed form (EI/PI amplify a relative sigma error by |z| phi(z)), or the fp32 oracle's own error."""
+    ys64 = np.asarray(ys, np.float64)
+    closed = oacq.acq_from_moments(acq, mu_gpu.astype(np.float64), sd_gpu.astype(np.float64), ys64, mask)
+    scale = np.maximum(np.abs(closed), np.abs(closed).mean())
+    assert np.all(np.abs(got - closed) <= 2e-5 * scale + 1e-7), f"{acq} closed form: {np.abs(got - closed).max():.3e}"
+    a64 = oacq.acq_from_moments(acq, mu64, sd64, ys64, mask)
+    a32 = oacq.acq_from_moments(acq, mu32, sd32, np.asarray(ys, np.float32), mask)
+    tmu = np.maximum(RTOL * np.maximum(np.abs(mu64), np.abs(mu64).mean()), 4 * np.abs(mu32 - mu64))
+    tsd = np.maximum(RTOL * sd64, 4 * np.abs(sd32.astype(np.float64) - sd64))
+    prop = np.zeros_like(a64)
+    for smu in (-1, 1):
+        for ssd in (-1, 1):
+            prop = np.maximum(prop, np.abs(oacq.acq_from_moments(acq, mu64 + smu * tmu, np.maximum(sd64 + ssd * tsd, 1e-12),
+                                                                 ys64, mask) - a64))
+    tol = np.maximum.reduce([RTOL * np.maximum(np.abs(a64), np.abs(a64).mean()), 4 * np.abs(a32 - a64), 2 * prop])
+    err = np.abs(got - a64)
+    assert np.all(err <= tol), f"{acq}: {np.sum(err > tol)} outside tolerance, worst {err.max():.3e}"
+
+
 def make_problem(n, d, seed, lo=0.0, hi=1.0, noise_raw=-4.0):
     rng = np.random.default_rng(seed)
     X = rng.uniform(lo, hi, (n, d)).astype(np.float32)
@@ -180,9 +202,7 @@ def test_score_points_vs_oracle(n, d, M, acq):
     assert_close(out["mu"].cpu().numpy(), mu64, mu32, what="mean")
     got_var = out["sigma"].cpu().numpy().astype(np.float64) ** 2
     assert_close(got_var, np.maximum(var64, 1e-10), np.maximum(var32, 1e-10), what="var")
-    a64 = oacq.acq_from_moments(acq, mu64, sd64, Y.astype(np.float64), mask)
-    a32 = oacq.acq_from_moments(acq, mu32, sd32, Y, mask)
-    assert_close(out["acq"].cpu().numpy(), a64, a32, rtol=2e-4, what=acq)
+    check_acq(acq, out["acq"].cpu().numpy(), out["mu"].cpu().numpy(), out["sigma"].cpu().numpy(), mu64, sd64, mu32, sd32, Y, mask)
 
 
 @pytest.mark.parametrize("space,n,M,acq", [("real6", 512, 20000, "EI"), ("mixed10", 2048, 8192, "PI"),
@@ -217,7 +237,8 @@ def test_fused_generated_scoring_argmax_and_topk(space, n, M, acq):
     mu32, sd32 = f32.predict(ocand)
     a64 = oacq.acq_from_moments(acq, mu64, sd64, ypad.astype(np.float64), mpad)
     a32 = oacq.acq_from_moments(acq, mu32, sd32, ypad, mpad)
-    assert_close(got, a64, a32, rtol=2e-4, what=acq)
+    mom = post.score_points(cand, acq=acq, param=param, ystar=ystar, want=("mu", "sigma"))
+    check_acq(acq, got, mom["mu"].cpu().numpy(), mom["sigma"].cpu().numpy(), mu64, sd64, mu32, sd32, ypad, mpad)
     # arg-max: the packed key must name the first maximum of the CUDA values, and agree with the oracle's
     # arg-max unless the two leaders tie within tolerance
     v, i = _lib.unpack(engine.to_unsigned(int(best.item())))
@@ -292,14 +313,16 @@ def test_refinement_contract(acq):
     X, Y, raw, P = make_problem(n, d, seed=99)
     post = engine.Posterior(X, Y, raw, want_tc=False).build()
     rng = np.random.default_rng(1)
-    starts = rng.uniform(0, 1, (50, d)).astype(np.float32)
+    pool = rng.uniform(0, 1, (5000, d)).astype(np.float32)
     ystar = bayex.acq.ystar_for(acq, Y, np.ones(n))
     param = bayex.acq.DEFAULT_PARAM[acq]
+    pv = post.score_points(pool, acq=acq, param=param, ystar=ystar, want=("acq",))["acq"].cpu().numpy()
+    starts = pool[oopt.jnp_argsort(pv)[-50:]]  # what sample() refines: the 50 best random candidates (optimizer.py:196)
     v0 = post.score_points(starts, acq=acq, param=param, ystar=ystar, want=("acq",))["acq"].cpu().numpy()
     xr, vr = post.refine(torch.from_numpy(starts).cuda(), 30, acq, param, ystar)
     v1 = post.score_points(xr, acq=acq, param=param, ystar=ystar, want=("acq",))["acq"].cpu().numpy()
-    assert np.all(v1 >= v0 - 1e-6 * np.abs(v0)), "refinement made a start worse"
-    assert np.mean(v1 > v0) > 0.5, "refinement did not move most starts"
+    assert np.all(v1 >= v0 - 1e-5 * np.abs(v0) - 1e-7), f"refinement made a start worse: {np.min(v1 - v0)}"
+    assert np.mean(v1 > v0) > 0.5, f"refinement did not move most starts: {np.mean(v1 > v0)}"
     assert np.allclose(vr.cpu().numpy(), v1, rtol=2e-4, atol=1e-7)
     # same algorithm restated in the oracle (fp64): reaches comparable values
     f64 = ogp.Factor(P, X, Y, np.ones(n), np.float64)
@@ -400,3 +423,65 @@ def test_state_rebuilds_factor_when_cache_is_cold():
     opt._cache.clear()
     b = bayex.Optimizer(dom, acq="UCB").sample(bayex.random.key(3), st, size=2000)
     assert all(np.array_equal(a[k], b[k]) for k in dom)
+
+
+# ---- tcgen05 engine ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("K", [32, 64, 512])
+def test_umma_selftest_3xtf32(K):
+    """D = A B^T through the same UMMA descriptors / SWIZZLE_128B layout / TMA map / tcgen05.ld path as the scoring
+    kernel; 3xTF32 must hold fp32-level accuracy (plain TF32 would sit at ~1e-3)."""
+    import ctypes as C
+    rng = np.random.default_rng(K)
+    A = rng.standard_normal((128, K)).astype(np.float32)
+    B = (rng.standard_normal((128, K)) * np.exp(rng.uniform(-6, 2, (128, 1)))).astype(np.float32)
+    dA, dB = torch.from_numpy(A).cuda(), torch.from_numpy(B).cuda()
+    dD = torch.full((128, 128), float("nan"), device="cuda")
+    torch.cuda.synchronize()
+    rc = _lib.lib.bx_selftest_umma(C.c_void_p(dA.data_ptr()), C.c_void_p(dB.data_ptr()), C.c_void_p(dD.data_ptr()), 128, K,
+                                   C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    _lib.check(rc, "bx_selftest_umma")
+    torch.cuda.synchronize()
+    got = dD.cpu().numpy().astype(np.float64)
+    want = A.astype(np.float64) @ B.astype(np.float64).T
+    scale = np.abs(A).astype(np.float64) @ np.abs(B).astype(np.float64).T
+    err = np.abs(got - want) / scale
+    assert np.all(np.isfinite(got)), "self-test left NaNs: tiles not written"
+    assert err.max() < 2e-6, f"3xTF32 error {err.max():.3e} (plain TF32 would be ~5e-4)"
+
+
+@pytest.mark.parametrize("n,d,M,acq", [(200, 3, 1000, "UCB"), (512, 6, 37965, "EI"), (1000, 10, 5000, "LCB"),
+                                       (2048, 20, 4096, "LCB"), (1300, 20, 3000, "PI")])
+def test_tcgen05_engine_matches_simt_engine_and_oracle(n, d, M, acq):
+    X, Y, raw, P = make_problem(n, d, seed=n * 3 + d)
+    dom = {f"x{i}": bayex.domain.Real(-0.1, 1.1) for i in range(d)}
+    dims = engine.dims_array(dom)
+    post = engine.Posterior(X, Y, raw, want_tc=True).build()
+    ystar = bayex.acq.ystar_for(acq, Y, np.ones(n))
+    param = bayex.acq.DEFAULT_PARAM[acq]
+    key = prng.key(n)
+    v_s, b_s = post.score_generated(key, dims, 5, M, acq, param, ystar, engine=_lib.ENGINE_SIMT)
+    v_t, b_t = post.score_generated(key, dims, 5, M, acq, param, ystar, engine=_lib.ENGINE_TCGEN05)
+    s, t = v_s.cpu().numpy().astype(np.float64), v_t.cpu().numpy().astype(np.float64)
+    assert np.all(np.isfinite(t))
+    cand = engine.threefry_fill(key, dims, d, 5, M).cpu().numpy()
+    f64, f32 = ogp.Factor(P, X, Y, np.ones(n), np.float64), ogp.Factor(P, X, Y, np.ones(n), np.float32)
+    mu64, sd64 = f64.predict(cand.astype(np.float64))
+    mu32, sd32 = f32.predict(cand)
+    mom = post.score_points(cand, acq=acq, param=param, ystar=ystar, want=("mu", "sigma"))
+    # the tensor-core engine is held to the same bar as the SIMT engine: the oracle, not just its sibling
+    a64 = oacq.acq_from_moments(acq, mu64, sd64, Y.astype(np.float64), np.ones(n))
+    a32 = oacq.acq_from_moments(acq, mu32, sd32, Y, np.ones(n))
+    tmu = np.maximum(RTOL * np.maximum(np.abs(mu64), np.abs(mu64).mean()), 4 * np.abs(mu32 - mu64))
+    tsd = np.maximum(RTOL * sd64, 4 * np.abs(sd32.astype(np.float64) - sd64))
+    prop = np.zeros_like(a64)
+    for smu in (-1, 1):
+        for ssd in (-1, 1):
+            prop = np.maximum(prop, np.abs(oacq.acq_from_moments(acq, mu64 + smu * tmu, np.maximum(sd64 + ssd * tsd, 1e-12),
+                                                                 Y.astype(np.float64), np.ones(n)) - a64))
+    tol = np.maximum.reduce([RTOL * np.maximum(np.abs(a64), np.abs(a64).mean()), 4 * np.abs(a32 - a64), 2 * prop])
+    for name, got in (("simt", s), ("tcgen05", t)):
+        err = np.abs(got - a64)
+        assert np.all(err <= tol), f"{name}: {np.sum(err > tol)}/{M} outside tolerance, worst {err.max():.3e} at {np.argmax(err)}"
+    assert np.abs(s - t).max() <= 2 * tol.max()
+    vt, it = _lib.unpack(engine.to_unsigned(int(b_t.item())))
+    assert it == 5 + oopt.jnp_argmax(v_t.cpu().numpy()) and np.float32(vt) == v_t.cpu().numpy()[it - 5]
