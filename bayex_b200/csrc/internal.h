@@ -66,6 +66,7 @@ struct ScoreArgs {
   float* acq;
   unsigned long long* best;
   uint64_t index_base;
+  int debug;  // profiling ablations of the tcgen05 engine (env BX_TC_ABLATE): 1 = skip K* math, 2 = skip MMA issue
 };
 
 }  // namespace bx

@@ -14,14 +14,18 @@
 //
 // Warp roles (448 threads): 0 = TMA producer, 1 = MMA issuer (+ TMEM alloc), 2..5 = epilogue, 6..13 = K* producers.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "internal.h"
 
 namespace bx {
 namespace tc {
 
-constexpr int TM = 128, BN = 128, BK = 32, NACC = 4, SA = 2, SB = 4;
-constexpr int TILE_BYTES = TM * BK * 4;  // 16 KiB: one operand tile (hi or lo)
+constexpr int TM = 128, BN = 256, BK = 32, NACC = 2, SA = 2, SB = 2;
+constexpr int KPR = BN / BK;               // K-blocks per row block (the diagonal of T crosses a row block in KPR steps)
+constexpr int TILE_BYTES = TM * BK * 4;   // 16 KiB: one K* operand tile (hi or lo)
+constexpr int BTILE_BYTES = BN * BK * 4;  // 32 KiB: one T operand tile (hi or lo)
+constexpr int SELF_N = 128;               // accumulator width of the self-test
 constexpr int NTHREADS = 448;
 constexpr int PROD0 = 6 * 32;  // first producer thread
 constexpr int NPROD = 256;
@@ -38,9 +42,11 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
 // Bounded wait: a protocol bug must trap (process dies with a launch failure) instead of hanging the GPU.
+// SLEEP_NS > 0 backs off between probes so long waits (epilogue, TMA) do not steal issue slots from the producers.
+template <int SLEEP_NS = 0>
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done = 0;
-  const long long t0 = clock64();
+  uint32_t done = 0, spins = 0;
+  long long t0 = 0;
   while (true) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -50,12 +56,51 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "r"(bar), "r"(parity)
         : "memory");
     if (done) return;
-    if (clock64() - t0 > 4000000000ll) {
-      printf("bayex_b200: mbarrier timeout (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
-      __trap();
+    if (SLEEP_NS > 0) __nanosleep(SLEEP_NS);
+    if ((++spins & 0xFFFu) == 0) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000ll) {
+        printf("bayex_b200: mbarrier timeout (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
+        __trap();
+      }
     }
   }
 }
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+// packed fp32x2 arithmetic (sm_100): two lanes per instruction halve the producers' issue pressure
+__device__ __forceinline__ void lds_2x64(uint32_t addr, uint64_t& a, uint64_t& b) {
+  asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "r"(addr));
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t pack2(float x, float y) {
+  uint64_t d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(x), "f"(y));
+  return d;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& x, float& y) { asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(v)); }
+__device__ __forceinline__ float lds32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -116,21 +161,21 @@ __host__ __device__ constexpr uint32_t make_idesc(int n) {
 // byte offset of 16-byte chunk `q` of row `r` inside a SWIZZLE_128B tile
 __device__ __forceinline__ uint32_t swz(int r, int q) { return (uint32_t)(r * 128 + ((q ^ (r & 7)) << 4)); }
 
-__device__ __forceinline__ void split_store(char* hi_tile, char* lo_tile, int row, int q, float v0, float v1, float v2, float v3) {
+__device__ __forceinline__ void split_store(uint32_t hi_tile, uint32_t lo_tile, int row, int q, float v0, float v1, float v2, float v3) {
   float4 h, l;
   h.x = __uint_as_float(__float_as_uint(v0) & 0xFFFFE000u); l.x = v0 - h.x;
   h.y = __uint_as_float(__float_as_uint(v1) & 0xFFFFE000u); l.y = v1 - h.y;
   h.z = __uint_as_float(__float_as_uint(v2) & 0xFFFFE000u); l.z = v2 - h.z;
   h.w = __uint_as_float(__float_as_uint(v3) & 0xFFFFE000u); l.w = v3 - h.w;
   const uint32_t off = swz(row, q);
-  *reinterpret_cast<float4*>(hi_tile + off) = h;
-  *reinterpret_cast<float4*>(lo_tile + off) = l;
+  sts128(hi_tile + off, h);
+  sts128(lo_tile + off, l);
 }
 
-struct Smem {
+struct __align__(16) Smem {
   // operand tiles first (1024-byte aligned)
   char a_hi[SA][TILE_BYTES], a_lo[SA][TILE_BYTES];
-  char b_hi[SB][TILE_BYTES], b_lo[SB][TILE_BYTES];
+  char b_hi[SB][BTILE_BYTES], b_lo[SB][BTILE_BYTES];
   float mean_s[2][TM];
   unsigned long long full_a[SA], empty_a[SA], full_b[SB], empty_b[SB], tmem_full[NACC], tmem_empty[NACC], mean_full, mean_empty;
   uint32_t tmem_base;
@@ -142,14 +187,16 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 score_tc_kernel(const __grid_constant__ ScoreArgs a, const __grid_constant__ SamplerPack sp,
                 const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
-  Smem& S = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  // [2][BK * D4 + BK]: observation rows + alpha of the current K-block (16-byte aligned for float4 reads)
-  float* us = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(&S + 1) + 15) & ~(uintptr_t)15);
+  Smem& S = *reinterpret_cast<Smem*>(smem_raw);  // SWIZZLE_128B tiles need the 1024-byte alignment declared above
   constexpr int US = BK * D4 + BK;
+  // [2][US] observation rows + alpha of the current K-block, right behind the struct (sizeof(Smem) % 16 == 0)
+  const uint32_t us_addr = smem_u32(smem_raw) + (uint32_t)sizeof(Smem);
+  if ((smem_u32(smem_raw) & 1023u) != 0u) __trap();
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int np = a.f.np;
-  const int nRB = np / BN;                 // row blocks of T
+  const int nRB = (np + BN - 1) / BN;       // row blocks of T (rows past np are zero-filled by TMA)
+  const int nJtot = np / BK;                // K-blocks in total
   const int nSB = (nRB + NACC - 1) / NACC;  // super-blocks
   const uint64_t ntiles = (a.m_count + TM - 1) / TM;
 
@@ -174,12 +221,12 @@ score_tc_kernel(const __grid_constant__ ScoreArgs a, const __grid_constant__ Sam
       for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         for (int sb = 0; sb < nSB; ++sb) {
           const int rb0 = sb * NACC, rb1 = min(rb0 + NACC, nRB);
-          for (int J = 0; J < 4 * rb1; ++J) {
-            for (int rb = max(rb0, J >> 2); rb < rb1; ++rb, ++it) {
+          for (int J = 0; J < min(KPR * rb1, nJtot); ++J) {
+            for (int rb = max(rb0, J / KPR); rb < rb1; ++rb, ++it) {
               const uint32_t st = it % SB, ph = (it / SB) & 1;
-              mbar_wait(smem_u32(&S.empty_b[st]), ph ^ 1);
+              mbar_wait<64>(smem_u32(&S.empty_b[st]), ph ^ 1);
               const uint32_t bar = smem_u32(&S.full_b[st]);
-              mbar_expect_tx(bar, 2 * TILE_BYTES);
+              mbar_expect_tx(bar, 2 * BTILE_BYTES);
               tma_load_2d(smem_u32(S.b_hi[st]), &map_hi, bar, J * BK, rb * BN);
               tma_load_2d(smem_u32(S.b_lo[st]), &map_lo, bar, J * BK, rb * BN);
             }
@@ -191,16 +238,16 @@ score_tc_kernel(const __grid_constant__ ScoreArgs a, const __grid_constant__ Sam
     // ===== MMA issuer =====
     if (lane == 0) {
       const uint32_t idesc = make_idesc(BN);
-      uint32_t ita = 0, itb = 0, acc_use[NACC] = {0, 0, 0, 0};
+      uint32_t ita = 0, itb = 0, acc_use[NACC] = {};
       for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         for (int sb = 0; sb < nSB; ++sb) {
           const int rb0 = sb * NACC, rb1 = min(rb0 + NACC, nRB);
-          for (int J = 0; J < 4 * rb1; ++J, ++ita) {
+          for (int J = 0; J < min(KPR * rb1, nJtot); ++J, ++ita) {
             const uint32_t sa = ita % SA, pa = (ita / SA) & 1;
             mbar_wait(smem_u32(&S.full_a[sa]), pa);
             tc_fence_after();
             const uint64_t ah = make_desc(smem_u32(S.a_hi[sa])), al = make_desc(smem_u32(S.a_lo[sa]));
-            for (int rb = max(rb0, J >> 2); rb < rb1; ++rb, ++itb) {
+            for (int rb = max(rb0, J / KPR); rb < rb1; ++rb, ++itb) {
               const int acc = rb - rb0;
               if (J == 0) {  // first write of this accumulator in this super-block: wait until the epilogue drained it
                 mbar_wait(smem_u32(&S.tmem_empty[acc]), (acc_use[acc] & 1) ^ 1);
@@ -211,6 +258,7 @@ score_tc_kernel(const __grid_constant__ ScoreArgs a, const __grid_constant__ Sam
               tc_fence_after();
               const uint64_t bh = make_desc(smem_u32(S.b_hi[st])), bl = make_desc(smem_u32(S.b_lo[st]));
               const uint32_t d = tmem + (uint32_t)(acc * BN);
+              if (!(a.debug & 2))
 #pragma unroll
               for (int ks = 0; ks < BK / 8; ++ks) {  // UMMA K = 8 for tf32 = 32 bytes inside the swizzle atom
                 const uint64_t o = (uint64_t)(ks * 2);
@@ -219,7 +267,7 @@ score_tc_kernel(const __grid_constant__ ScoreArgs a, const __grid_constant__ Sam
                 umma_tf32(d, ah + o, bl + o, idesc, 1u);
               }
               umma_commit(smem_u32(&S.empty_b[st]));
-              if (J == 4 * rb + 3) {  // last K-block below the diagonal: this row block of V is complete
+              if (J == min(KPR * rb + KPR, nJtot) - 1) {  // last K-block below the diagonal: this row block of V is complete
                 umma_commit(smem_u32(&S.tmem_full[acc]));
                 ++acc_use[acc];
               }
@@ -234,14 +282,14 @@ score_tc_kernel(const __grid_constant__ ScoreArgs a, const __grid_constant__ Sam
     const int q = warp & 3, cl = q * 32 + lane;  // TMEM lane quarter of this warp; candidate within the tile
     const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
     const float amp = a.f.d_hyp[HYP_AMP], ymean = a.f.d_hyp[HYP_YMEAN];
-    uint32_t acc_use[NACC] = {0, 0, 0, 0}, tiles_done = 0;
+    uint32_t acc_use[NACC] = {}, tiles_done = 0;
     unsigned long long best = 0ull;
     for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tiles_done) {
       float ss = 0.f;
       for (int sb = 0; sb < nSB; ++sb) {
         const int rb0 = sb * NACC, rb1 = min(rb0 + NACC, nRB);
         for (int acc = 0; acc < rb1 - rb0; ++acc) {
-          mbar_wait(smem_u32(&S.tmem_full[acc]), acc_use[acc] & 1);
+          mbar_wait<128>(smem_u32(&S.tmem_full[acc]), acc_use[acc] & 1);
           ++acc_use[acc];
           tc_fence_after();
 #pragma unroll
@@ -259,7 +307,7 @@ score_tc_kernel(const __grid_constant__ ScoreArgs a, const __grid_constant__ Sam
           if (lane == 0) mbar_arrive(smem_u32(&S.tmem_empty[acc]));
         }
       }
-      mbar_wait(smem_u32(&S.mean_full), tiles_done & 1);
+      mbar_wait<128>(smem_u32(&S.mean_full), tiles_done & 1);
       const float mu = S.mean_s[0][cl] + S.mean_s[1][cl] + ymean;  // gp.py:67
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&S.mean_empty));
@@ -285,61 +333,74 @@ score_tc_kernel(const __grid_constant__ ScoreArgs a, const __grid_constant__ Sam
     const float amp = a.f.d_hyp[HYP_AMP];
     uint32_t ita = 0, tiles_done = 0;
     for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tiles_done) {
-      float cr[D4];
+      uint64_t ncr[D4 / 2];  // (-c_k, -c_{k+1}) packed: the squared distance runs on add.f32x2 / fma.f32x2
       {
         const uint64_t gidx = a.m_begin + tile * TM + c;
 #pragma unroll
-        for (int k = 0; k < D4; ++k) cr[k] = (k < a.f.d) ? sample_coord(sp.dim[k], gidx) * a.f.d_scale[k] : 0.f;
+        for (int k = 0; k < D4; k += 2) {
+          const float c0 = (k < a.f.d) ? sample_coord(sp.dim[k], gidx) * a.f.d_scale[k] : 0.f;
+          const float c1 = (k + 1 < a.f.d) ? sample_coord(sp.dim[k + 1], gidx) * a.f.d_scale[k + 1] : 0.f;
+          ncr[k / 2] = pack2(-c0, -c1);
+        }
       }
       float mpart = 0.f;
       for (int sb = 0; sb < nSB; ++sb) {
         const int rb1 = min(sb * NACC + NACC, nRB);
         const bool last_sb = (sb == nSB - 1);
-        const int nJ = 4 * rb1;
-        // stage observation rows of K-block 0
+        const int nJ = min(KPR * rb1, nJtot);
+        // stage observation rows (+ alpha) of K-block 0
         for (int e = pt; e < US; e += NPROD)
-          us[e] = (e < BK * D4) ? a.f.d_U[e] : a.f.d_alpha[e - BK * D4];
+          sts32(us_addr + 4u * e, (e < BK * D4) ? a.f.d_U[e] : a.f.d_alpha[e - BK * D4]);
         asm volatile("bar.sync 1, 256;" ::: "memory");
         for (int J = 0; J < nJ; ++J, ++ita) {
-          const float* u = us + (J & 1) * US;
+          const uint32_t u = us_addr + (uint32_t)((J & 1) * US * 4);
           float pre[(US + NPROD - 1) / NPROD];
           if (J + 1 < nJ) {  // prefetch the next K-block's rows into registers
 #pragma unroll
             for (int i = 0; i < (US + NPROD - 1) / NPROD; ++i) {
               const int e = pt + i * NPROD;
-              pre[i] = (e < BK * D4) ? a.f.d_U[(size_t)(J + 1) * BK * D4 + e]
-                                     : (e < US ? a.f.d_alpha[(J + 1) * BK + e - BK * D4] : 0.f);
+              pre[i] = (e < BK * D4) ? __ldg(a.f.d_U + (size_t)(J + 1) * BK * D4 + e)
+                                     : (e < US ? __ldg(a.f.d_alpha + (J + 1) * BK + e - BK * D4) : 0.f);
             }
           }
           const uint32_t sa = ita % SA, pa = (ita / SA) & 1;
           mbar_wait(smem_u32(&S.empty_a[sa]), pa ^ 1);
+          const uint32_t a_hi = smem_u32(S.a_hi[sa]), a_lo = smem_u32(S.a_lo[sa]);
+          if (!(a.debug & 1))
 #pragma unroll
           for (int g = 0; g < 4; ++g) {  // 4 groups of 4 observations -> one 16-byte chunk of the A row each
             float kv[4];
+            const int kk0 = h * 16 + g * 4;
+            uint64_t s01[4] = {0ull, 0ull, 0ull, 0ull}, s23[4] = {0ull, 0ull, 0ull, 0ull};  // 16 independent chains
+#pragma unroll
+            for (int k4 = 0; k4 < D4; k4 += 4) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                uint64_t u01, u23;
+                lds_2x64(u + (uint32_t)(((kk0 + i) * D4 + k4) * 4), u01, u23);
+                const uint64_t d01 = add2(u01, ncr[k4 / 2]), d23 = add2(u23, ncr[k4 / 2 + 1]);
+                s01[i] = fma2(d01, d01, s01[i]);
+                s23[i] = fma2(d23, d23, s23[i]);
+              }
+            }
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              const int kk = h * 16 + g * 4 + i;
-              float s = 0.f;
-#pragma unroll
-              for (int k4 = 0; k4 < D4; k4 += 4) {
-                const float4 uv = *reinterpret_cast<const float4*>(u + kk * D4 + k4);
-                const float d0 = uv.x - cr[k4], d1 = uv.y - cr[k4 + 1], d2 = uv.z - cr[k4 + 2], d3 = uv.w - cr[k4 + 3];
-                s = fmaf(-d0, d0, s); s = fmaf(-d1, d1, s); s = fmaf(-d2, d2, s); s = fmaf(-d3, d3, s);
-              }
-              kv[i] = amp * ex2_approx(s);  // gp.py:64 with the length scale and log2(e) folded into the coordinates
-              if (last_sb) mpart = fmaf(u[BK * D4 + kk], kv[i], mpart);  // gp.py:66-67
+              float sx, sy;
+              unpack2(add2(s01[i], s23[i]), sx, sy);
+              kv[i] = amp * ex2_approx(-sx - sy);  // gp.py:64 with the length scale and log2(e) folded into the coordinates
+              if (last_sb) mpart = fmaf(lds32(u + (uint32_t)((BK * D4 + kk0 + i) * 4)), kv[i], mpart);  // gp.py:66-67
             }
-            split_store(S.a_hi[sa], S.a_lo[sa], c, h * 4 + g, kv[0], kv[1], kv[2], kv[3]);
+            split_store(a_hi, a_lo, c, h * 4 + g, kv[0], kv[1], kv[2], kv[3]);
           }
           fence_proxy_async();  // generic-proxy stores -> visible to the tensor core (async proxy)
           __syncwarp();
           if (lane == 0) mbar_arrive(smem_u32(&S.full_a[sa]));
           if (J + 1 < nJ) {
-            float* un = us + ((J + 1) & 1) * US;
+            const uint32_t un = us_addr + (uint32_t)(((J + 1) & 1) * US * 4);
 #pragma unroll
             for (int i = 0; i < (US + NPROD - 1) / NPROD; ++i) {
               const int e = pt + i * NPROD;
-              if (e < US) un[e] = pre[i];
+              if (e < US) sts32(un + 4u * e, pre[i]);
             }
           }
           asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -376,12 +437,12 @@ static EncodeTiledFn encode_fn() {
 }
 
 // fp32 row-major [rows x cols] matrix, box = 128 rows x 32 columns, SWIZZLE_128B
-static int32_t make_map(CUtensorMap* m, const float* base, uint64_t rows, uint64_t cols, uint64_t ld) {
+static int32_t make_map(CUtensorMap* m, const float* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
   EncodeTiledFn fn = encode_fn();
   BX_CHECK_ARG(fn, BX_E_UNSUPPORTED, "cuTensorMapEncodeTiled not available from the driver");
   const cuuint64_t dims[2] = {cols, rows};
   const cuuint64_t strides[1] = {ld * sizeof(float)};
-  const cuuint32_t box[2] = {BK, BN};
+  const cuuint32_t box[2] = {BK, box_rows};
   const cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -392,7 +453,7 @@ static int32_t make_map(CUtensorMap* m, const float* base, uint64_t rows, uint64
 
 template <int D4>
 static int32_t launch_d4(cudaStream_t s, const ScoreArgs& a, const SamplerPack& sp, const CUtensorMap& mh, const CUtensorMap& ml) {
-  const size_t smem = sizeof(Smem) + 1024 + 16 + sizeof(float) * 2 * (BK * D4 + BK);
+  const size_t smem = sizeof(Smem) + sizeof(float) * 2 * (BK * D4 + BK);
   BX_CUDA(cudaFuncSetAttribute(score_tc_kernel<D4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int dev = 0, sms = 0;
   BX_CUDA(cudaGetDevice(&dev));
@@ -408,11 +469,13 @@ static int32_t launch_d4(cudaStream_t s, const ScoreArgs& a, const SamplerPack& 
 
 bool score_tc_supported(const bx_factor_t& f) { return f.d_Thi && f.d_Tlo && f.d4 <= 32; }
 
-int32_t launch_score_tc(cudaStream_t s, const ScoreArgs& a, const SamplerPack& sp) {
+int32_t launch_score_tc(cudaStream_t s, const ScoreArgs& a_in, const SamplerPack& sp) {
+  ScoreArgs a = a_in;
+  if (const char* e = getenv("BX_TC_ABLATE")) a.debug = atoi(e);
   CUtensorMap mh, ml;
-  int32_t rc = tc::make_map(&mh, a.f.d_Thi, a.f.np, a.f.np, a.f.np);
+  int32_t rc = tc::make_map(&mh, a.f.d_Thi, a.f.np, a.f.np, a.f.np, tc::BN);
   if (rc) return rc;
-  rc = tc::make_map(&ml, a.f.d_Tlo, a.f.np, a.f.np, a.f.np);
+  rc = tc::make_map(&ml, a.f.d_Tlo, a.f.np, a.f.np, a.f.np, tc::BN);
   if (rc) return rc;
   switch (a.f.d4) {
     case 4: return tc::launch_d4<4>(s, a, sp, mh, ml);
@@ -441,7 +504,8 @@ __global__ void __launch_bounds__(128, 1)
 selftest_kernel(const float* __restrict__ A, float* __restrict__ D, int K, const __grid_constant__ CUtensorMap map_hi,
                 const __grid_constant__ CUtensorMap map_lo) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
-  SelfSmem& S = *reinterpret_cast<SelfSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  SelfSmem& S = *reinterpret_cast<SelfSmem*>(smem_raw);
+  if ((smem_u32(smem_raw) & 1023u) != 0u) __trap();
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
     mbar_init(smem_u32(&S.full_b), 1);
@@ -453,7 +517,7 @@ selftest_kernel(const float* __restrict__ A, float* __restrict__ D, int K, const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = S.tmem_base;
-  const uint32_t idesc = make_idesc(BN);
+  const uint32_t idesc = make_idesc(SELF_N);
   for (int kb = 0; kb < K / BK; ++kb) {
     if (tid == 0) {
       const uint32_t bar = smem_u32(&S.full_b);
@@ -463,7 +527,7 @@ selftest_kernel(const float* __restrict__ A, float* __restrict__ D, int K, const
     }
     for (int qd = 0; qd < 8; ++qd) {  // row `tid` of A, 8 chunks of 4 floats
       const float4 v = *reinterpret_cast<const float4*>(A + (size_t)tid * K + kb * BK + qd * 4);
-      split_store(S.a_hi, S.a_lo, tid, qd, v.x, v.y, v.z, v.w);
+      split_store(smem_u32(S.a_hi), smem_u32(S.a_lo), tid, qd, v.x, v.y, v.z, v.w);
     }
     fence_proxy_async();
     __syncthreads();
@@ -484,10 +548,10 @@ selftest_kernel(const float* __restrict__ A, float* __restrict__ D, int K, const
     tc_fence_after();
   }
   const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
-  for (int c0 = 0; c0 < BN; c0 += 32) {
+  for (int c0 = 0; c0 < SELF_N; c0 += 32) {
     uint32_t r[32];
     tmem_ld32(lane_addr + (uint32_t)c0, r);
-    for (int i = 0; i < 32; ++i) D[(size_t)(warp * 32 + lane) * BN + c0 + i] = __uint_as_float(r[i]);
+    for (int i = 0; i < 32; ++i) D[(size_t)(warp * 32 + lane) * SELF_N + c0 + i] = __uint_as_float(r[i]);
   }
   tc_fence_before();
   __syncthreads();
@@ -511,7 +575,7 @@ __global__ void split_kernel(const float* __restrict__ x, size_t n, float* hi, f
 extern "C" int32_t bx_selftest_umma(const float* d_A, const float* d_B, float* d_D, int32_t N, int32_t K, void* stream) {
   using namespace bx;
   BX_CHECK_ARG(d_A && d_B && d_D, BX_E_ARG, "null pointer argument");
-  BX_CHECK_ARG(N == tc::BN && K > 0 && K % tc::BK == 0, BX_E_RANGE, "self-test needs N == 128 and K a multiple of 32");
+  BX_CHECK_ARG(N == tc::SELF_N && K > 0 && K % tc::BK == 0, BX_E_RANGE, "self-test needs N == 128 and K a multiple of 32");
   cudaStream_t s = (cudaStream_t)stream;
   float *hi = nullptr, *lo = nullptr;
   const size_t n = (size_t)N * K;
@@ -520,10 +584,10 @@ extern "C" int32_t bx_selftest_umma(const float* d_A, const float* d_B, float* d
   tc::split_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d_B, n, hi, lo);
   BX_LAUNCH_CHECK();
   CUtensorMap mh, ml;
-  int32_t rc = tc::make_map(&mh, hi, N, K, K);
-  if (rc == 0) rc = tc::make_map(&ml, lo, N, K, K);
+  int32_t rc = tc::make_map(&mh, hi, N, K, K, tc::SELF_N);
+  if (rc == 0) rc = tc::make_map(&ml, lo, N, K, K, tc::SELF_N);
   if (rc == 0) {
-    const size_t smem = sizeof(tc::SelfSmem) + 1024;
+    const size_t smem = sizeof(tc::SelfSmem);
     cudaFuncSetAttribute(tc::selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     tc::selftest_kernel<<<1, 128, smem, s>>>(d_A, d_D, K, mh, ml);
     cudaError_t e = cudaGetLastError();

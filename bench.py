@@ -243,12 +243,14 @@ def main():
     if clocks:
         clocks.start()
     barrier()
+    torch.cuda.nvtx.range_push("bx_timed")  # lets `ncu --nvtx --nvtx-include "bx_timed/"` list exactly these launches
     t0 = time.perf_counter()
     for i in range(args.steps):
         l2_flush.zero_()
         proposal = opt.sample(bayex.random.fold_in(key0, 200 + i), state, size=M)
     barrier()
     t_res = max_over_ranks(time.perf_counter() - t0)
+    torch.cuda.nvtx.range_pop()
     clock_summary = clocks.summary() if clocks else None
 
     # -- end-to-end steps: cold cache => observation upload + factor rebuild (+ broadcast) + proposal read-back
