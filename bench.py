@@ -169,7 +169,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--candidates", type=int, default=None)
-    ap.add_argument("--engine", default="auto", choices=["auto", "simt", "tcgen05"])
+    ap.add_argument("--engine", default="auto", choices=["auto", "simt", "tcgen05", "tcgen05_pair"])
     ap.add_argument("--ref-sample", type=int, default=32768)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -195,7 +195,8 @@ def main():
     P, X, Y = make_observations(d, n, odom)
     dom = {f"x{i}": bayex.domain.Real(0.0, 1.0) for i in range(d)}
     opt = bayex.Optimizer(dom, acq=acq, maximize=False)
-    opt.engine = {"auto": _lib.ENGINE_AUTO, "simt": _lib.ENGINE_SIMT, "tcgen05": _lib.ENGINE_TCGEN05}[args.engine]
+    opt.engine = {"auto": _lib.ENGINE_AUTO, "simt": _lib.ENGINE_SIMT, "tcgen05": _lib.ENGINE_TCGEN05,
+                  "tcgen05_pair": _lib.ENGINE_TCGEN05_PAIR}[args.engine]
     t0 = time.perf_counter()
     state = opt.init(Y, P)  # 100-step hyper-parameter fit + factor (untimed set-up)
     torch.cuda.synchronize()

@@ -44,7 +44,7 @@ extern "C" {
 /* acquisition ids - names follow bayex.acq (acq.py:8,53,90,124) */
 enum { BX_ACQ_EI = 0, BX_ACQ_PI = 1, BX_ACQ_UCB = 2, BX_ACQ_LCB = 3 };
 /* scoring engines */
-enum { BX_ENGINE_AUTO = 0, BX_ENGINE_SIMT = 1, BX_ENGINE_TCGEN05 = 2 };
+enum { BX_ENGINE_AUTO = 0, BX_ENGINE_SIMT = 1, BX_ENGINE_TCGEN05 = 2 /* one CTA per tile */, BX_ENGINE_TCGEN05_PAIR = 3 /* cta_group::2 */ };
 
 /* One dimension of the parameter space - mirrors bayex.domain.Real / Integer (domain.py:22-131). */
 typedef struct {
