@@ -72,24 +72,33 @@ __global__ void __launch_bounds__(256) gemm64_kernel(GemmArgs g) {
 #pragma unroll
     for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
 
+  // Register-staged software pipeline: the global loads of k-step i+1 are in flight while k-step i is multiplied
+  // (the fit / refinement GEMMs are skinny and latency-bound without it).
+  const int a_r = TA ? (tid >> 4) : (tid >> 2), a_c = TA ? (tid & 15) * 4 : (tid & 3) * 4;
+  const int b_r = TB ? (tid >> 2) : (tid >> 4), b_c = TB ? (tid & 3) * 4 : (tid & 15) * 4;
+  auto load_a = [&](int k0) -> float4 {
+    return TA ? *reinterpret_cast<const float4*>(A + (size_t)(k0 + a_r) * g.lda + i0 + a_c)
+              : *reinterpret_cast<const float4*>(A + (size_t)(i0 + a_r) * g.lda + k0 + a_c);
+  };
+  auto load_b = [&](int k0) -> float4 {
+    return TB ? *reinterpret_cast<const float4*>(B + (size_t)(j0 + b_r) * g.ldb + k0 + b_c)
+              : *reinterpret_cast<const float4*>(B + (size_t)(k0 + b_r) * g.ldb + j0 + b_c);
+  };
+  float4 ra = make_float4(0.f, 0.f, 0.f, 0.f), rb = ra;
+  if (k_lo < k_hi) { ra = load_a(k_lo); rb = load_b(k_lo); }
   for (int k0 = k_lo; k0 < k_hi; k0 += GK) {
-    if (!TA) {  // A is [M x K]
-      const int r = tid >> 2, kk = (tid & 3) * 4;
-      const float4 v = *reinterpret_cast<const float4*>(A + (size_t)(i0 + r) * g.lda + k0 + kk);
-      As[kk + 0][r] = v.x; As[kk + 1][r] = v.y; As[kk + 2][r] = v.z; As[kk + 3][r] = v.w;
+    if (!TA) {  // A is [M x K]: transpose into As[k][row]
+      As[a_c + 0][a_r] = ra.x; As[a_c + 1][a_r] = ra.y; As[a_c + 2][a_r] = ra.z; As[a_c + 3][a_r] = ra.w;
     } else {    // A is [K x M]
-      const int kk = tid >> 4, m = (tid & 15) * 4;
-      *reinterpret_cast<float4*>(&As[kk][m]) = *reinterpret_cast<const float4*>(A + (size_t)(k0 + kk) * g.lda + i0 + m);
+      *reinterpret_cast<float4*>(&As[a_r][a_c]) = ra;
     }
     if (!TB) {  // B is [K x N]
-      const int kk = tid >> 4, n = (tid & 15) * 4;
-      *reinterpret_cast<float4*>(&Bs[kk][n]) = *reinterpret_cast<const float4*>(B + (size_t)(k0 + kk) * g.ldb + j0 + n);
-    } else {    // B is [N x K]
-      const int r = tid >> 2, kk = (tid & 3) * 4;
-      const float4 v = *reinterpret_cast<const float4*>(B + (size_t)(j0 + r) * g.ldb + k0 + kk);
-      Bs[kk + 0][r] = v.x; Bs[kk + 1][r] = v.y; Bs[kk + 2][r] = v.z; Bs[kk + 3][r] = v.w;
+      *reinterpret_cast<float4*>(&Bs[b_r][b_c]) = rb;
+    } else {    // B is [N x K]: transpose into Bs[k][col]
+      Bs[b_c + 0][b_r] = rb.x; Bs[b_c + 1][b_r] = rb.y; Bs[b_c + 2][b_r] = rb.z; Bs[b_c + 3][b_r] = rb.w;
     }
     __syncthreads();
+    if (k0 + GK < k_hi) { ra = load_a(k0 + GK); rb = load_b(k0 + GK); }
 #pragma unroll
     for (int kk = 0; kk < GK; ++kk) {
       const float4 a = *reinterpret_cast<const float4*>(&As[kk][rg * 4]);

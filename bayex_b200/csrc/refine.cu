@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(256) refine_kstar_kernel(bx_factor_t f, const 
       const float df = f.d_U[(size_t)j * f.d4 + k] - xt[(size_t)s * f.d + k] * f.d_scale[k];
       acc = fmaf(df, df, acc);
     }
-    v = f.d_hyp[HYP_AMP] * exp2f(-acc);
+    v = f.d_hyp[HYP_AMP] * ex2_approx(-acc);  // same ex2 as the scoring kernels
   }
   Kst[e] = v;
 }

@@ -166,12 +166,15 @@ class Optimizer:
             tv, ti = merge_topk(gv, gi, min(n_starts, size))
             tv, ti = torch.from_numpy(tv).to(post.dev), torch.from_numpy(ti).to(post.dev)
         starts = post.gather(key, self._dims, ti)  # optimizer.py:197
-        optimized, _ = post.refine(starts, refine_rounds, name, param, ystar)  # optimizer.py:198-199
-        sc = post.score_points(optimized, acq=name, param=param, ystar=ystar, want=("acq",), best=True)  # :200
+        # optimizer.py:198-200: refined points and their acquisition values (bx_refine evaluates the same closed forms
+        # with the same ex2 path as the scoring kernels; the values at the returned points come back with them)
+        optimized, opt_vals = post.refine(starts, refine_rounds, name, param, ystar)
         with engine.on_stream(post.stream, post.dev):
-            b_opt = engine.to_unsigned(int(sc["best"].item()))
             b_rnd = engine.to_unsigned(int(best.item()))
             opt_host = optimized.cpu().numpy()
+            ov_host = opt_vals.cpu().numpy()
+        j_opt = argmax_first(ov_host)
+        b_opt = int(_lib.lib.bx_pack(_lib.C.c_float(float(ov_host[j_opt])), j_opt))
         # argmax over concat(optimised, random): first occurrence => optimised points win ties (optimizer.py:203-205)
         if (b_opt >> 32) >= (b_rnd >> 32):
             _, j = _lib.unpack(b_opt)
@@ -187,7 +190,7 @@ class Optimizer:
         if details:
             with engine.on_stream(post.stream, post.dev):
                 info = dict(acq_vals=vals.cpu().numpy(), top_idxs=ti.cpu().numpy(), top_vals=tv.cpu().numpy(),
-                            optimized=opt_host, opt_vals=sc["acq"].cpu().numpy(), chosen=chosen,
+                            optimized=opt_host, opt_vals=ov_host, chosen=chosen,
                             best_opt=_lib.unpack(b_opt), best_rnd=_lib.unpack(b_rnd), m_begin=m_begin, m_count=m_count)
             return best_params, info
         return best_params
@@ -226,6 +229,12 @@ class Optimizer:
         best_params = {k: v[best_idx] for k, v in params.items()}
         return OptimizerState(params=params, ys=ys, best_score=self.sign * best_score, best_params=best_params,
                               mask=mask, gp_params=params_from_raw(raw, xs.shape[1]))
+
+
+def argmax_first(v: np.ndarray) -> int:
+    """``jnp.argmax``: first occurrence, NaN counts as the maximum (optimizer.py:205)."""
+    nan = np.isnan(v)
+    return int(np.argmax(nan)) if nan.any() else int(np.argmax(v))
 
 
 def shard_range(size: int, rank: int, world: int):
