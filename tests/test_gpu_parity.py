@@ -487,3 +487,87 @@ def test_tcgen05_engine_matches_simt_engine_and_oracle(n, d, M, acq):
     for vv, bb in ((v_t, b_t), (v_p, b_p)):
         vt, it = _lib.unpack(engine.to_unsigned(int(bb.item())))
         assert it == 5 + oopt.jnp_argmax(vv.cpu().numpy()) and np.float32(vt) == vv.cpu().numpy()[it - 5]
+
+
+# ---- BASELINE.json configurations at full size: size-independent properties + oracle spot checks ------------------
+def _config_problem(d, n, seed=0):
+    space = odom.ParamSpace({f"x{i}": odom.Real(0.0, 1.0) for i in range(d)})
+    X = space.to_array(space.sample_params(prng.key(seed), (n,)))
+    Y = (np.sin(3 * X.sum(1)) + 0.5 * np.cos(7 * X[:, 0])).astype(np.float32)
+    return X, Y
+
+
+def test_config3_full_size_properties():
+    """C3: d=20, n=4096, UCB, 2^24 candidates on one GPU.  Arg-max == max of the stored acquisition vector; a slice
+    rescored alone is bit-identical (sharding invariance); a 4096-candidate sample agrees with the fp64 oracle."""
+    d, n, M = 20, 4096, 1 << 24
+    X, Y = _config_problem(d, n)
+    raw = np.concatenate([[-8.0], [0.0], np.zeros(d)]).astype(np.float32)
+    dom = {f"x{i}": bayex.domain.Real(0.0, 1.0) for i in range(d)}
+    dims = engine.dims_array(dom)
+    post = engine.Posterior(X, Y, raw).build()
+    assert post.hyp()[7] == 0.0
+    key = prng.key(1)
+    vals, best = post.score_generated(key, dims, 0, M, "UCB", 0.01, 0.0)
+    v, i = _lib.unpack(engine.to_unsigned(int(best.item())))
+    vmax, imax = torch.max(vals, dim=0)
+    assert np.float32(v) == vmax.item() and vals[i].item() == vmax.item()
+    assert i == int((vals == vmax).nonzero()[0].item()), "arg-max must be the first occurrence"
+    assert torch.isfinite(vals).all()
+    # one shard of an 8-way split, rescored on its own
+    b, c = bayex.optimizer.shard_range(M, 5, 8)
+    v5, b5 = post.score_generated(key, dims, b, c, "UCB", 0.01, 0.0)
+    assert torch.equal(v5, vals[b:b + c])
+    tv, ti = post.topk(vals, 50)
+    t5, i5 = post.topk(v5, 50, index_base=b)
+    assert set(i5.cpu().numpy().tolist()) >= set(int(x) for x in ti.cpu().numpy() if b <= x < b + c)
+    # oracle spot check on a strided sample of the same draw
+    sel = torch.arange(0, M, M // 4096, dtype=torch.int32, device="cuda")[:4096]
+    cand = post.gather(key, dims, sel).cpu().numpy()
+    P = ogp.GPParams(raw[0], raw[1], raw[2:])
+    f64 = ogp.Factor(P, X, Y, np.ones(n), np.float64)
+    mu64, sd64 = f64.predict(cand.astype(np.float64))
+    want = mu64 + 0.01 * sd64
+    got = vals[sel.long()].cpu().numpy()
+    assert_close(got, want, rtol=2e-4, what="UCB @ C3")
+
+
+def test_config2_sample_with_64_starts():
+    """C2: 6-D, EI, n=512, 2^20 candidates + 64-start refinement through the public API."""
+    d, n = 6, 512
+    X, Y = _config_problem(d, n, seed=2)
+    dom = {f"x{i}": bayex.domain.Real(0.0, 1.0) for i in range(d)}
+    opt = bayex.Optimizer(dom, acq="EI", maximize=True)
+    st = opt.init(Y, {f"x{i}": X[:, i] for i in range(d)})
+    new, info = opt.sample(bayex.random.key(1), st, size=1 << 20, n_starts=64, details=True)
+    assert info["optimized"].shape == (64, d) and info["top_idxs"].shape == (64,)
+    assert np.array_equal(info["top_idxs"].astype(np.int64), oopt.jnp_argsort(info["acq_vals"])[-64:])
+    best_random = info["acq_vals"].max()
+    chosen_val = info["opt_vals"].max() if info["chosen"] < 64 else best_random
+    assert chosen_val >= best_random, "proposal must be at least as good as the best random candidate (Q12 contract)"
+    assert np.all(info["opt_vals"] >= info["top_vals"] - 1e-5 * np.abs(info["top_vals"]) - 1e-7)
+    assert all(0.0 <= new[k][0] <= 1.0 for k in dom)
+
+
+@pytest.mark.parametrize("n", [1024, 4096, 8192])
+def test_config5_nlml_and_fit_step_large_n(n):
+    """C5: RBF marginal likelihood + Cholesky at n = 1024 / 4096 / 8192, d = 8, against the fp64 oracle; one AdamW
+    step moves every raw hyper-parameter by ~lr in the direction the oracle gradient says."""
+    d = 8
+    X, Y = _config_problem(d, n, seed=5)
+    Y = (Y + 0.01 * np.random.default_rng(0).standard_normal(n)).astype(np.float32)
+    raw = np.concatenate([[-4.0], [0.2], np.random.default_rng(7).uniform(-1, 1, d)]).astype(np.float32)
+    P = ogp.GPParams(raw[0], raw[1], raw[2:])
+    post = engine.Posterior(X, Y, raw.copy(), want_tc=False)
+    nl, loss, gl, gn = post.nlml_grad()
+    nl64 = ogp.marginal_likelihood(P, X, Y, np.ones(n), dtype=np.float64)
+    nl32 = ogp.marginal_likelihood(P, X, Y, np.ones(n), dtype=np.float32)
+    assert_close(nl, nl64, nl32, what=f"nlml n={n}")
+    assert np.all(np.isfinite(gl))
+    if n <= 4096:
+        g64 = ogp.loss_grad(P, X, Y, np.ones(n), dtype=np.float64)
+        ref = np.concatenate([[g64.noise], [g64.amplitude], g64.lengthscale])
+        assert np.all(np.abs(gl - ref) <= 2e-3 * np.linalg.norm(ref) + 1e-4), (gl, ref)
+        post.fit_hypers(steps=1)
+        step = post.raw_host() - raw
+        assert np.all(np.sign(step) == -np.sign(ref)) and np.all(np.abs(np.abs(step) - 1e-3) < 2e-5)
