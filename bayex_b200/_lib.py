@@ -19,7 +19,7 @@ if not os.path.exists(LIB_PATH):
 lib = C.CDLL(LIB_PATH)
 
 ACQ_IDS = {"EI": 0, "PI": 1, "UCB": 2, "LCB": 3}
-ENGINE_AUTO, ENGINE_SIMT, ENGINE_TCGEN05, ENGINE_TCGEN05_PAIR = 0, 1, 2, 3
+ENGINE_AUTO, ENGINE_SIMT, ENGINE_TCGEN05, ENGINE_TCGEN05_PAIR, ENGINE_TCGEN05_F16 = 0, 1, 2, 3, 4
 MAX_D, MAX_K, TILE = 64, 1024, 128
 
 
@@ -30,7 +30,7 @@ class DimT(C.Structure):
 class FactorT(C.Structure):
     _fields_ = [("n", C.c_int32), ("np", C.c_int32), ("d", C.c_int32), ("d4", C.c_int32),
                 ("d_U", C.c_void_p), ("d_T", C.c_void_p), ("d_Thi", C.c_void_p), ("d_Tlo", C.c_void_p),
-                ("d_alpha", C.c_void_p), ("d_scale", C.c_void_p), ("d_hyp", C.c_void_p)]
+                ("d_T16hi", C.c_void_p), ("d_T16lo", C.c_void_p), ("d_alpha", C.c_void_p), ("d_scale", C.c_void_p), ("d_hyp", C.c_void_p)]
 
 
 _vp, _i32, _u64, _f32, _sz = C.c_void_p, C.c_int32, C.c_uint64, C.c_float, C.c_size_t
@@ -47,7 +47,7 @@ SIGNATURES = {
     "bx_fit_workspace_bytes": (_sz, [_i32, _i32]),
     "bx_nlml_grad": (_i32, [_vp, _vp, _i32, _i32, _vp, _vp, _vp, _sz, _vp]),
     "bx_fit_adamw": (_i32, [_vp, _vp, _i32, _i32, _vp, _f32, _i32, _vp, _vp, _sz, _i32, _vp]),
-    "bx_factor_build": (_i32, [_vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "bx_factor_build": (_i32, [_vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "bx_score_points": (_i32, [C.POINTER(FactorT), _vp, _u64, _i32, _f32, _f32, _vp, _vp, _vp, _vp, _u64, _vp]),
     "bx_score_generated": (_i32, [C.POINTER(FactorT), _key, C.POINTER(DimT), _u64, _u64, _i32, _f32, _f32, _vp, _vp,
                                   _i32, _vp]),

@@ -34,7 +34,7 @@ constexpr float kSqrtLog2e = 1.2011224087864498f;  // sqrt(log2 e): coordinates 
 constexpr float kJitter = 1e-6f;                   // gp.py:46
 
 // hyp[] slots of bx_factor_t::d_hyp
-enum { HYP_AMP = 0, HYP_NOISE = 1, HYP_YMEAN = 2, HYP_LOG2AMP = 3, HYP_NLML = 4, HYP_LOGDET = 5, HYP_QUAD = 6, HYP_STATUS = 7 };
+enum { HYP_AMP = 0, HYP_NOISE = 1, HYP_YMEAN = 2, HYP_LOG2AMP = 3, HYP_NLML = 4, HYP_LOGDET = 5, HYP_QUAD = 6, HYP_STATUS = 7, HYP_T16SCALE = 8 };
 
 __host__ __device__ inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
 

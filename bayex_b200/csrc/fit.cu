@@ -1,5 +1,6 @@
 // GP fit path on the device: Gram build, Cholesky, T = L^-1, alpha, NLML, analytic gradient, clip + AdamW.
 // Replaces gp.py:41-57 (fit half of gaussian_process), gp.py:78-87 (neg_log_likelihood), gp.py:90-110 (posterior_fit).
+#include <cuda_fp16.h>
 #include <stdlib.h>
 
 #include "internal.h"
@@ -102,17 +103,39 @@ __global__ void __launch_bounds__(256) nlml_kernel(const float* __restrict__ v, 
   }
 }
 
-// Padded diagonal of T <- 0 (so padded observations contribute nothing to V), optional TF32 head/tail split.
-__global__ void finalize_T_kernel(float* T, int n, int np, float* Thi, float* Tlo) {
+// Padded rows/columns of T <- 0 (so padded observations contribute nothing to V) and max|T| for the fp16 scale.
+__global__ void zero_pad_absmax_kernel(float* T, int n, int np, unsigned int* absmax_bits) {
   const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  float t = 0.f;
+  if (e < (size_t)np * np) {
+    const int i = (int)(e / np), j = (int)(e % np);
+    t = T[e];
+    if (i >= n || j >= n) { t = 0.f; T[e] = 0.f; }
+  }
+  unsigned int b = __float_as_uint(fabsf(t));  // non-negative floats order like their bit patterns
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) b = max(b, __shfl_xor_sync(0xffffffffu, b, o));
+  if ((threadIdx.x & 31) == 0 && b) atomicMax(absmax_bits, b);
+}
+// TF32 head/tail (T & 0xFFFFE000, T - head) and fp16 head/tail of T * 2^b, 2^b chosen so max|T| 2^b is in [2^13, 2^14].
+__global__ void split_T_kernel(const float* __restrict__ T, int np, float* Thi, float* Tlo, __half* H16, __half* L16,
+                               const unsigned int* absmax_bits, float* hyp) {
+  const float amax = __uint_as_float(*absmax_bits);
+  const float sc = (amax > 0.f) ? exp2f(floorf(log2f(16384.f / amax))) : 1.f;
+  const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e == 0) hyp[HYP_T16SCALE] = sc;
   if (e >= (size_t)np * np) return;
-  const int i = (int)(e / np), j = (int)(e % np);
-  float t = T[e];
-  if (i >= n || j >= n) { t = 0.f; T[e] = 0.f; }
+  const float t = T[e];
   if (Thi) {
     const float hi = __uint_as_float(__float_as_uint(t) & 0xFFFFE000u);  // 10-bit mantissa: exact in TF32
     Thi[e] = hi;
     Tlo[e] = t - hi;
+  }
+  if (H16) {
+    const float ts = t * sc;
+    const __half h = __float2half_rn(ts);
+    H16[e] = h;
+    L16[e] = __float2half_rn(ts - __half2float(h));
   }
 }
 
@@ -481,7 +504,7 @@ FitWs carve_fit_ws(void* base, int n, int d) {
   w.part = take((size_t)w.ntiles * (d + 2));
   w.gbuf = take(2 + 2 * (d + 2));
   w.adam = take(2 * (d + 2) + 1);
-  w.status = reinterpret_cast<int*>(take(1));
+  w.status = reinterpret_cast<int*>(take(2));  // [0] Cholesky status, [1] max|T| bits
   w.bytes = off;
   return w;
 }
@@ -618,18 +641,24 @@ extern "C" int32_t bx_fit_adamw(const float* d_X, const float* d_y, int32_t n, i
 }
 
 extern "C" int32_t bx_factor_build(const float* d_X, const float* d_y, int32_t n, int32_t d, const float* d_raw,
-                                   float* d_U, float* d_T, float* d_Thi, float* d_Tlo, float* d_alpha, float* d_scale,
-                                   float* d_hyp, void* d_ws, size_t ws_bytes, void* stream) {
+                                   float* d_U, float* d_T, float* d_Thi, float* d_Tlo, void* d_T16hi, void* d_T16lo,
+                                   float* d_alpha, float* d_scale, float* d_hyp, void* d_ws, size_t ws_bytes, void* stream) {
   int32_t rc = check_fit_args(d_X, d_y, n, d, d_raw, d_ws, ws_bytes);
   if (rc) return rc;
   BX_CHECK_ARG(d_U && d_T && d_alpha && d_scale && d_hyp, BX_E_ARG, "null factor output");
   BX_CHECK_ARG((d_Thi == nullptr) == (d_Tlo == nullptr), BX_E_ARG, "Thi and Tlo must be given together");
+  BX_CHECK_ARG((d_T16hi == nullptr) == (d_T16lo == nullptr), BX_E_ARG, "T16hi and T16lo must be given together");
   cudaStream_t s = (cudaStream_t)stream;
   FitWs w = carve_fit_ws(d_ws, n, d);
   rc = launch_factor(s, d_X, d_y, n, d, d_raw, w, d_T, d_U, d_alpha, d_scale, d_hyp);
   if (rc) return rc;
   const size_t tot = (size_t)w.np * w.np;
-  finalize_T_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(d_T, n, w.np, d_Thi, d_Tlo);
+  unsigned int* amax = reinterpret_cast<unsigned int*>(w.status) + 1;  // second word of the status slot
+  BX_CUDA(cudaMemsetAsync(amax, 0, sizeof(unsigned int), s));
+  zero_pad_absmax_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(d_T, n, w.np, amax);
+  BX_LAUNCH_CHECK();
+  split_T_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(d_T, w.np, d_Thi, d_Tlo, reinterpret_cast<__half*>(d_T16hi),
+                                                               reinterpret_cast<__half*>(d_T16lo), amax, d_hyp);
   BX_LAUNCH_CHECK();
   return 0;
 }

@@ -146,22 +146,30 @@ class Posterior:
         with on_stream(self.stream, self.dev):
             if self._bufs is None:
                 e = lambda *s: torch.empty(s, dtype=torch.float32, device=self.dev)
-                self._bufs = dict(U=e(np_, d4), T=e(np_, np_), alpha=e(np_), scale=e(d4), hyp=e(8),
-                                  Thi=e(np_, np_) if self.want_tc else None, Tlo=e(np_, np_) if self.want_tc else None)
+                self._bufs = self._alloc_bufs()
             b = self._bufs
             check(lib.bx_factor_build(_ptr(self.X), _ptr(self.y), self.n, self.d, _ptr(self.raw), _ptr(b["U"]),
-                                      _ptr(b["T"]), _ptr(b["Thi"]), _ptr(b["Tlo"]), _ptr(b["alpha"]), _ptr(b["scale"]),
-                                      _ptr(b["hyp"]), _ptr(ws), nbytes, C.c_void_p(self.stream.cuda_stream)),
+                                      _ptr(b["T"]), _ptr(b["Thi"]), _ptr(b["Tlo"]), _ptr(b["T16hi"]), _ptr(b["T16lo"]),
+                                      _ptr(b["alpha"]), _ptr(b["scale"]), _ptr(b["hyp"]), _ptr(ws), nbytes,
+                                      C.c_void_p(self.stream.cuda_stream)),
                   "bx_factor_build")
         self._set_factor()
         return self
 
+    def _alloc_bufs(self):
+        np_, d4 = self.np_, self.d4
+        e = lambda *s: torch.empty(s, dtype=torch.float32, device=self.dev)
+        h = lambda *s: torch.empty(s, dtype=torch.float16, device=self.dev)
+        tc = self.want_tc
+        return dict(U=e(np_, d4), T=e(np_, np_), alpha=e(np_), scale=e(d4), hyp=torch.zeros(16, dtype=torch.float32, device=self.dev),
+                    Thi=e(np_, np_) if tc else None, Tlo=e(np_, np_) if tc else None,
+                    T16hi=h(np_, np_) if tc else None, T16lo=h(np_, np_) if tc else None)
+
     def _set_factor(self):
         b = self._bufs
-        self.factor = _lib.FactorT(self.n, self.np_, self.d, self.d4, b["U"].data_ptr(), b["T"].data_ptr(),
-                                   0 if b["Thi"] is None else b["Thi"].data_ptr(),
-                                   0 if b["Tlo"] is None else b["Tlo"].data_ptr(), b["alpha"].data_ptr(),
-                                   b["scale"].data_ptr(), b["hyp"].data_ptr())
+        p = lambda t: 0 if t is None else t.data_ptr()
+        self.factor = _lib.FactorT(self.n, self.np_, self.d, self.d4, p(b["U"]), p(b["T"]), p(b["Thi"]), p(b["Tlo"]),
+                                   p(b["T16hi"]), p(b["T16lo"]), p(b["alpha"]), p(b["scale"]), p(b["hyp"]))
 
     def hyp(self) -> np.ndarray:
         self._need_factor()
@@ -180,12 +188,9 @@ class Posterior:
     def broadcast(self, src=0, group=None):
         import torch.distributed as dist
         if self._bufs is None:
-            e = lambda *s: torch.empty(s, dtype=torch.float32, device=self.dev)
-            self._bufs = dict(U=e(self.np_, self.d4), T=e(self.np_, self.np_), alpha=e(self.np_), scale=e(self.d4),
-                              hyp=e(8), Thi=e(self.np_, self.np_) if self.want_tc else None,
-                              Tlo=e(self.np_, self.np_) if self.want_tc else None)
+            self._bufs = self._alloc_bufs()
         self.stream.synchronize()
-        names = ["U", "alpha", "scale", "hyp", "T"] + (["Thi", "Tlo"] if self.want_tc else [])
+        names = ["U", "alpha", "scale", "hyp", "T"] + (["Thi", "Tlo", "T16hi", "T16lo"] if self.want_tc else [])
         for name in names:
             dist.broadcast(self._bufs[name], src=src, group=group)
         dist.broadcast(self.raw, src=src, group=group)

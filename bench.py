@@ -35,6 +35,11 @@ WORKLOADS = {
 }
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of the scoring kernel from the committed `ncu --set full` capture
+# (profiles/), keyed by (workload, candidates); None where no capture exists for that size.
+TRAFFIC_BYTES = {}
+
+
 def ackley(u):
     x = u * 65.536 - 32.768
     d = x.shape[1]
@@ -169,7 +174,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--candidates", type=int, default=None)
-    ap.add_argument("--engine", default="auto", choices=["auto", "simt", "tcgen05", "tcgen05_pair"])
+    ap.add_argument("--engine", default="auto", choices=["auto", "simt", "tcgen05", "tcgen05_pair", "tcgen05_f16"])
     ap.add_argument("--ref-sample", type=int, default=32768)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -196,7 +201,7 @@ def main():
     dom = {f"x{i}": bayex.domain.Real(0.0, 1.0) for i in range(d)}
     opt = bayex.Optimizer(dom, acq=acq, maximize=False)
     opt.engine = {"auto": _lib.ENGINE_AUTO, "simt": _lib.ENGINE_SIMT, "tcgen05": _lib.ENGINE_TCGEN05,
-                  "tcgen05_pair": _lib.ENGINE_TCGEN05_PAIR}[args.engine]
+                  "tcgen05_pair": _lib.ENGINE_TCGEN05_PAIR, "tcgen05_f16": _lib.ENGINE_TCGEN05_F16}[args.engine]
     t0 = time.perf_counter()
     state = opt.init(Y, P)  # 100-step hyper-parameter fit + factor (untimed set-up)
     torch.cuda.synchronize()
@@ -278,6 +283,23 @@ def main():
         fl = flops_per_candidate(n, d) * m_count
         achieved = fl / (kern_ms_avg * 1e-3) / 1e12
         n_starts = opt.N_STARTS
+        f16 = args.engine in ("auto", "tcgen05_f16")
+        if f16 and peaks.get("bf16_tflops_sustained"):
+            # kind::f16 MMAs; the launch is ~1 s long under the 1000 W cap, so the sustained cuBLAS figure is the denominator
+            peak, peak_src = float(peaks["bf16_tflops_sustained"]), (
+                "MEASURED_PEAKS.json bf16_tflops_sustained (dense 16-bit cuBLAS under the power cap; burst "
+                f"{peaks.get('bf16_tflops')} TF/s); the head/tail split issues 3 MMAs per algorithmic MAC, so the "
+                "attainable ceiling is 1/3 of it")
+        elif f16:
+            peak, peak_src = 1400.0, "fallback of B200_PROFILING.md (sustained 1.4 PFLOP/s bf16; MEASURED_PEAKS.json absent)"
+        else:
+            peak, peak_src = tf32_peak, ("dense TF32 cuBLAS 8192^3 measured in this run (MEASURED_PEAKS.json has 16-bit only); "
+                                         "the 3xTF32 split caps algorithmic flops at 1/3 of it")
+        roofline = {"bound": "tensor", "kernel": "score (generate -> K* -> T K* -> sum v^2 -> acquisition -> arg-max)",
+                    "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
+                    "frac_of_split_ceiling": 3 * achieved / peak if peak else None,
+                    "traffic": TRAFFIC_BYTES.get((args.workload, M)), "kernel_ms": kern_ms_avg,
+                    "algorithmic_flops_per_launch": fl, "peak_source": peak_src, "tf32_peak_this_run": tf32_peak}
         launches_per_step = 1 + 19 + 1 + 4 * (opt.REFINE_ROUNDS + 1) + 1
         line = {
             "metric": "acq candidate-evals/sec", "value": M * args.steps / t_res, "unit": "candidates/s", "n_gpus": world,
@@ -292,11 +314,7 @@ def main():
                     "h2d_bytes_per_step": int(X.nbytes + Y.nbytes + 4 * (d + 2) + 8),
                     "d2h_bytes_per_step": int(4 * (d + 2) + 16 + 4 * n_starts * d + 4 * d)},
             "gpu_launches": launches_per_step * args.steps,
-            "roofline": {"bound": "tensor", "kernel": "score (generate -> K* -> T K* -> sum v^2 -> acquisition -> arg-max)",
-                         "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s", "frac": achieved / tf32_peak if tf32_peak else None,
-                         "traffic": None, "kernel_ms": kern_ms_avg, "algorithmic_flops_per_launch": fl,
-                         "peak_source": "dense TF32 cuBLAS 8192^3 measured in this run (MEASURED_PEAKS.json has bf16 only: "
-                                        f"{peaks.get('bf16_tflops')} TF/s); the 3xTF32 split caps algorithmic flops at 1/3 of it"},
+            "roofline": roofline,
             "clocks": clock_summary,
             "proposal": {k: float(v[0]) for k, v in list(proposal.items())[:3]},
         }

@@ -44,7 +44,13 @@ extern "C" {
 /* acquisition ids - names follow bayex.acq (acq.py:8,53,90,124) */
 enum { BX_ACQ_EI = 0, BX_ACQ_PI = 1, BX_ACQ_UCB = 2, BX_ACQ_LCB = 3 };
 /* scoring engines */
-enum { BX_ENGINE_AUTO = 0, BX_ENGINE_SIMT = 1, BX_ENGINE_TCGEN05 = 2 /* one CTA per tile */, BX_ENGINE_TCGEN05_PAIR = 3 /* cta_group::2 */ };
+enum {
+  BX_ENGINE_AUTO = 0,
+  BX_ENGINE_SIMT = 1,
+  BX_ENGINE_TCGEN05 = 2,      /* 3xTF32, one CTA per tile */
+  BX_ENGINE_TCGEN05_PAIR = 3, /* 3xTF32, cta_group::2 */
+  BX_ENGINE_TCGEN05_F16 = 4   /* fp16 head/tail split (same 22-bit operands, half the tensor work) */
+};
 
 /* One dimension of the parameter space - mirrors bayex.domain.Real / Integer (domain.py:22-131). */
 typedef struct {
@@ -66,9 +72,11 @@ typedef struct {
   const float* d_T;   /* [np x np] row-major, T = L^-1 (lower triangular), K = L L^T */
   const float* d_Thi; /* [np x np] TF32-exact head of T (tcgen05 engine), may be NULL */
   const float* d_Tlo; /* [np x np] tail T - Thi, may be NULL */
+  const void* d_T16hi;  /* [np x np] fp16 head of T * 2^b (tcgen05 fp16 engine), may be NULL; 2^b is d_hyp[8] */
+  const void* d_T16lo;  /* [np x np] fp16 tail, may be NULL */
   const float* d_alpha; /* [np] K^-1 (y - ymean) */
   const float* d_scale; /* [d4] sqrt(log2 e) / lengthscale_k */
-  const float* d_hyp;   /* [8] amp, noise, ymean, log2(amp), nlml, logdet(L), quad, status */
+  const float* d_hyp;   /* [16] amp, noise, ymean, log2(amp), nlml, logdet(L), quad, status, T16 scale, (7 reserved) */
 } bx_factor_t;
 
 int32_t bx_version(void);
@@ -105,11 +113,11 @@ int32_t bx_fit_adamw(const float* d_X, const float* d_y, int32_t n, int32_t d, f
                      float* d_trace, void* d_ws, size_t ws_bytes, int32_t use_graph, void* stream);
 
 /* Posterior factor - replaces: gp.py:41-49 (softplus, centring, Gram, Cholesky, alpha) once per fit.
- * Outputs are the arrays referenced by bx_factor_t (caller allocates: U np*d4, T np*np, Thi/Tlo optional, alpha np,
- * scale d4, hyp 8). */
+ * Outputs are the arrays referenced by bx_factor_t (caller allocates: U np*d4, T np*np, Thi/Tlo and T16hi/T16lo
+ * optional, alpha np, scale d4, hyp 16). */
 int32_t bx_factor_build(const float* d_X, const float* d_y, int32_t n, int32_t d, const float* d_raw, float* d_U,
-                        float* d_T, float* d_Thi, float* d_Tlo, float* d_alpha, float* d_scale, float* d_hyp,
-                        void* d_ws, size_t ws_bytes, void* stream);
+                        float* d_T, float* d_Thi, float* d_Tlo, void* d_T16hi, void* d_T16lo, float* d_alpha,
+                        float* d_scale, float* d_hyp, void* d_ws, size_t ws_bytes, void* stream);
 
 /* Posterior + acquisition at explicit points - replaces: gp.py:59-71 predict, acq.py:45-50,84-87,120-121,155-156.
  * d_cand [M x d] raw (unscaled) points.  Any of d_mu / d_sigma / d_acq may be NULL.  d_best (optional) is a

@@ -462,8 +462,9 @@ def test_tcgen05_engine_matches_simt_engine_and_oracle(n, d, M, acq):
     v_s, b_s = post.score_generated(key, dims, 5, M, acq, param, ystar, engine=_lib.ENGINE_SIMT)
     v_t, b_t = post.score_generated(key, dims, 5, M, acq, param, ystar, engine=_lib.ENGINE_TCGEN05)
     v_p, b_p = post.score_generated(key, dims, 5, M, acq, param, ystar, engine=_lib.ENGINE_TCGEN05_PAIR)
-    s, t, pr = (v.cpu().numpy().astype(np.float64) for v in (v_s, v_t, v_p))
-    assert np.all(np.isfinite(t)) and np.all(np.isfinite(pr))
+    v_h, b_h = post.score_generated(key, dims, 5, M, acq, param, ystar, engine=_lib.ENGINE_TCGEN05_F16)
+    s, t, pr, hf = (v.cpu().numpy().astype(np.float64) for v in (v_s, v_t, v_p, v_h))
+    assert np.all(np.isfinite(t)) and np.all(np.isfinite(pr)) and np.all(np.isfinite(hf))
     cand = engine.threefry_fill(key, dims, d, 5, M).cpu().numpy()
     f64, f32 = ogp.Factor(P, X, Y, np.ones(n), np.float64), ogp.Factor(P, X, Y, np.ones(n), np.float32)
     mu64, sd64 = f64.predict(cand.astype(np.float64))
@@ -480,11 +481,11 @@ def test_tcgen05_engine_matches_simt_engine_and_oracle(n, d, M, acq):
             prop = np.maximum(prop, np.abs(oacq.acq_from_moments(acq, mu64 + smu * tmu, np.maximum(sd64 + ssd * tsd, 1e-12),
                                                                  Y.astype(np.float64), np.ones(n)) - a64))
     tol = np.maximum.reduce([RTOL * np.maximum(np.abs(a64), np.abs(a64).mean()), 4 * np.abs(a32 - a64), 2 * prop])
-    for name, got in (("simt", s), ("tcgen05", t), ("tcgen05_pair", pr)):
+    for name, got in (("simt", s), ("tcgen05", t), ("tcgen05_pair", pr), ("tcgen05_f16", hf)):
         err = np.abs(got - a64)
         assert np.all(err <= tol), f"{name}: {np.sum(err > tol)}/{M} outside tolerance, worst {err.max():.3e} at {np.argmax(err)}"
     assert np.abs(s - t).max() <= 2 * tol.max() and np.abs(s - pr).max() <= 2 * tol.max()
-    for vv, bb in ((v_t, b_t), (v_p, b_p)):
+    for vv, bb in ((v_t, b_t), (v_p, b_p), (v_h, b_h)):
         vt, it = _lib.unpack(engine.to_unsigned(int(bb.item())))
         assert it == 5 + oopt.jnp_argmax(vv.cpu().numpy()) and np.float32(vt) == vv.cpu().numpy()[it - 5]
 
