@@ -19,7 +19,7 @@ if not os.path.exists(LIB_PATH):
 lib = C.CDLL(LIB_PATH)
 
 ACQ_IDS = {"EI": 0, "PI": 1, "UCB": 2, "LCB": 3}
-ENGINE_AUTO, ENGINE_SIMT, ENGINE_TCGEN05, ENGINE_TCGEN05_PAIR, ENGINE_TCGEN05_F16 = 0, 1, 2, 3, 4
+ENGINE_AUTO, ENGINE_SIMT, ENGINE_TCGEN05, ENGINE_TCGEN05_PAIR, ENGINE_TCGEN05_F16, ENGINE_TCGEN05_F16_PAIR = 0, 1, 2, 3, 4, 5
 MAX_D, MAX_K, TILE = 64, 1024, 128
 
 

@@ -203,6 +203,8 @@ int32_t launch_score_tc2(cudaStream_t s, const ScoreArgs& a, const SamplerPack& 
 // implemented in score_tc16.cu (fp16 head/tail engine)
 int32_t launch_score_tc16(cudaStream_t s, const ScoreArgs& a, const SamplerPack& sp);
 bool score_tc16_supported(const bx_factor_t& f);
+// implemented in score_tc16p.cu (fp16 head/tail, CTA pair, register-tiled producers): the production engine
+int32_t launch_score_tc16p(cudaStream_t s, const ScoreArgs& a, const SamplerPack& sp);
 
 }  // namespace bx
 
@@ -276,17 +278,17 @@ extern "C" int32_t bx_score_generated(const bx_factor_t* f, const uint32_t key[2
   ScoreArgs a{};
   a.f = *f; a.cand = nullptr; a.m_begin = m_begin; a.m_count = m_count; a.acq_id = acq_id; a.acq_param = acq_param;
   a.ystar = ystar; a.acq = d_acq; a.best = reinterpret_cast<unsigned long long*>(d_best); a.index_base = m_begin;
-  // AUTO: the fp16 head/tail engine carries the same 22 operand bits as 3xTF32 at half the tensor work (measured 1.25x faster
-  // on C3); the TF32 engines remain selectable (full fp32 exponent range of T), SIMT covers d > 32.
+  // AUTO: the fp16 head/tail engines carry the same 22 operand bits as 3xTF32 at half the tensor work; the CTA-pair version
+  // is the fastest (profiles/README.md).  The TF32 engines remain selectable (full fp32 exponent range of T); SIMT covers d > 32.
   if (engine == BX_ENGINE_AUTO)
-    engine = score_tc16_supported(*f) ? BX_ENGINE_TCGEN05_F16 : (score_tc_supported(*f) ? BX_ENGINE_TCGEN05 : BX_ENGINE_SIMT);
+    engine = score_tc16_supported(*f) ? BX_ENGINE_TCGEN05_F16_PAIR : (score_tc_supported(*f) ? BX_ENGINE_TCGEN05 : BX_ENGINE_SIMT);
   if (engine == BX_ENGINE_TCGEN05 || engine == BX_ENGINE_TCGEN05_PAIR) {
     BX_CHECK_ARG(score_tc_supported(*f), BX_E_UNSUPPORTED, "tcgen05 engines need the Thi/Tlo split of the factor and d <= 32");
     return engine == BX_ENGINE_TCGEN05 ? launch_score_tc((cudaStream_t)stream, a, sp) : launch_score_tc2((cudaStream_t)stream, a, sp);
   }
-  if (engine == BX_ENGINE_TCGEN05_F16) {
-    BX_CHECK_ARG(score_tc16_supported(*f), BX_E_UNSUPPORTED, "fp16 tcgen05 engine needs the T16hi/T16lo split of the factor and d <= 32");
-    return launch_score_tc16((cudaStream_t)stream, a, sp);
+  if (engine == BX_ENGINE_TCGEN05_F16 || engine == BX_ENGINE_TCGEN05_F16_PAIR) {
+    BX_CHECK_ARG(score_tc16_supported(*f), BX_E_UNSUPPORTED, "fp16 tcgen05 engines need the T16hi/T16lo split of the factor and d <= 32");
+    return engine == BX_ENGINE_TCGEN05_F16 ? launch_score_tc16((cudaStream_t)stream, a, sp) : launch_score_tc16p((cudaStream_t)stream, a, sp);
   }
   BX_CHECK_ARG(engine == BX_ENGINE_SIMT, BX_E_ARG, "unknown engine %d", engine);
   return launch_score_simt((cudaStream_t)stream, a, &sp, true);

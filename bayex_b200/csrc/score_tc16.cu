@@ -15,17 +15,11 @@ namespace tc16 {
 
 using namespace bx::tc;
 
-constexpr int BKH = 64;                    // observations per K-block
 constexpr int BN = 256, NACC = 2, SA = 2, SB = 2;
 constexpr int KPR = BN / BKH;
 constexpr int BTILE_BYTES = BN * BKH * 2;  // 32 KiB
 constexpr int NTHREADS = 448, PROD0 = 6 * 32, NPROD = 256;
 
-__device__ __forceinline__ float kstar_scale(float amp) { return exp2f(floorf(log2f(16384.f / amp))); }
-
-__host__ __device__ constexpr uint32_t make_idesc_f16(int n, int m = TM) {  // kind::f16, A/B = F16 (0), D = F32, K-major
-  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
-}
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
@@ -33,20 +27,6 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
-}
-// 8 scaled values -> fp16 head and tail, one 16-byte chunk each
-__device__ __forceinline__ void split_store_f16(uint32_t hi_tile, uint32_t lo_tile, int row, int q, const float (&v)[8]) {
-  uint32_t hw[4], lw[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const __half h0 = __float2half_rn(v[2 * i]), h1 = __float2half_rn(v[2 * i + 1]);
-    const __half l0 = __float2half_rn(v[2 * i] - __half2float(h0)), l1 = __float2half_rn(v[2 * i + 1] - __half2float(h1));
-    hw[i] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
-    lw[i] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
-  }
-  const uint32_t off = swz(row, q);
-  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(hi_tile + off), "r"(hw[0]), "r"(hw[1]), "r"(hw[2]), "r"(hw[3]) : "memory");
-  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(lo_tile + off), "r"(lw[0]), "r"(lw[1]), "r"(lw[2]), "r"(lw[3]) : "memory");
 }
 
 struct __align__(16) Smem {
@@ -305,24 +285,6 @@ score_tc16_kernel(const __grid_constant__ ScoreArgs a, const __grid_constant__ S
 }
 
 
-typedef CUresult (*EncodeTiledFn16)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static int32_t make_map16(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols) {
-  EncodeTiledFn16 fn = reinterpret_cast<EncodeTiledFn16>(encode_fn());
-  BX_CHECK_ARG(fn, BX_E_UNSUPPORTED, "cuTensorMapEncodeTiled not available from the driver");
-  const cuuint64_t dims[2] = {cols, rows};
-  const cuuint64_t strides[1] = {cols * 2};
-  const cuuint32_t box[2] = {(cuuint32_t)BKH, (cuuint32_t)BN};
-  const cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  BX_CHECK_ARG(r == CUDA_SUCCESS, BX_E_UNSUPPORTED, "cuTensorMapEncodeTiled(fp16) failed with CUresult %d", (int)r);
-  return 0;
-}
-
 template <int D4>
 static int32_t launch_d4(cudaStream_t s, const ScoreArgs& a, const SamplerPack& sp, const CUtensorMap& mh, const CUtensorMap& ml) {
   const size_t smem = sizeof(Smem) + sizeof(float) * 2 * (BKH * D4 + BKH);
@@ -345,9 +307,9 @@ int32_t launch_score_tc16(cudaStream_t s, const ScoreArgs& a_in, const SamplerPa
   ScoreArgs a = a_in;
   if (const char* e = getenv("BX_TC_ABLATE")) a.debug = atoi(e);
   CUtensorMap mh, ml;
-  int32_t rc = tc16::make_map16(&mh, a.f.d_T16hi, a.f.np, a.f.np);
+  int32_t rc = tc::make_map_f16(&mh, a.f.d_T16hi, a.f.np, a.f.np, tc16::BN);
   if (rc) return rc;
-  rc = tc16::make_map16(&ml, a.f.d_T16lo, a.f.np, a.f.np);
+  rc = tc::make_map_f16(&ml, a.f.d_T16lo, a.f.np, a.f.np, tc16::BN);
   if (rc) return rc;
   switch (a.f.d4) {
     case 4: return tc16::launch_d4<4>(s, a, sp, mh, ml);

@@ -1,0 +1,470 @@
+// tcgen05 scoring engine, fp16 head/tail split + CTA pair (cta_group::2): the production engine for large candidate sets.
+//
+// Replaces, for M generated candidates: domain.py:74,130,159-161 (Threefry draws) -> gp.py:60-64 (K*) -> gp.py:66-67 (mean)
+// -> gp.py:68-70 (V = L^-1 K*, diag variance, std) -> acq.py closed forms -> optimizer.py:205 (arg-max).
+//
+// What the ncu capture of the 1-CTA fp16 engine (profiles/r1_score_tc16_ncu_full.csv) said, and what this engine changes:
+//   * the shared-memory data pipe was 88 % busy: 45 % broadcast LDS.128 of observation rows by the K* producers
+//     (2.3 wavefronts each, one candidate per thread), 32 % tensor-core operand reads, 7 % STS.
+//       -> producers register-tile RC candidates per thread, so every observation row read feeds RC entries
+//          (LDS per generated entry / RC);
+//       -> cta_group::2: each CTA keeps only half (128 rows) of every T tile, the pair's tensor cores share it
+//          (operand reads per MMA 12 KB -> 8 KB per SM, T traffic L2 -> smem halved);
+//   * the FP32 pipe was 48 % busy (FADD2/FFMA2 occupy it for two cycles: packing saves issue slots, not lanes) and is the
+//     next wall; the per-entry epilogue was trimmed (one cvt.rn.f16x2 per pair, amp * 2^a folded into one multiply).
+//   * observation rows are staged by bulk-async copies (TMA, mbarrier complete_tx) instead of LDG -> STS -> bar.sync.
+//   * registers are re-partitioned with setmaxnreg: 2 producer warpgroups get 176, the epilogue 96, the control warps 56.
+//
+// Warp roles (512 threads): 0 TMA (T tiles) | 1 MMA issuer (leader CTA) | 2 TMA (observation rows) | 3 idle |
+//                           4-7 epilogue (TMEM lane quarter = warp & 3) | 8-15 K* producers.
+// Cross-CTA protocol (leader = cluster rank 0), as in score_tc2.cu:
+//   full_a[s]   (leader, count 16)  <- producer warps of both CTAs
+//   empty_a[s]  (both, count 1)     <- tcgen05.commit.multicast from the leader
+//   full_b[s]   (leader, count 2)   <- leader arrive.expect_tx + remote arrive; both CTAs' TMA loads complete_tx there
+//   empty_b[s], tmem_full[a] (both) <- tcgen05.commit.multicast;  tmem_empty[a] (leader, count 8) <- epilogue warps
+//   full_u[s] / empty_u[s] (CTA-local) <- bulk copy complete_tx / 8 producer warps
+#include "tc_common.cuh"
+
+namespace bx {
+namespace tc16p {
+
+using namespace bx::tc;
+
+constexpr int BN = 256;                    // T rows per accumulator = UMMA N
+constexpr int HN = BN / 2;                 // rows of every T tile held by one CTA
+constexpr int NACC = 2, SA = 2, SB = 4, NU = 3;
+constexpr int KPR = BN / BKH;              // K-blocks per row block
+constexpr int ATILE = TM * BKH * 2;        // 16 KiB: 128 candidates x 64 halves
+constexpr int BTILE = HN * BKH * 2;        // 16 KiB: 128 T rows x 64 halves
+constexpr int NTHREADS = 512, PROD0 = 8 * 32, NPROD = 256;
+constexpr int MAXOP = 8;                   // most observation parts (producer threads per candidate group)
+
+struct __align__(16) Smem {
+  char a_hi[SA][ATILE], a_lo[SA][ATILE];
+  char b_hi[SB][BTILE], b_lo[SB][BTILE];
+  float mean_s[MAXOP][TM];
+  unsigned long long full_a[SA], empty_a[SA], full_b[SB], empty_b[SB], full_u[NU], empty_u[NU], tmem_full[NACC],
+      tmem_empty[NACC], mean_full, mean_empty;
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ uint32_t cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {  // the same barrier in CTA rank 0
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, 0;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(bar)
+      : "memory");
+}
+template <int SLEEP_NS = 0>
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0, spins = 0;
+  long long t0 = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) return;
+    if (SLEEP_NS > 0) __nanosleep(SLEEP_NS);
+    if ((++spins & 0xFFFu) == 0) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000ll) {
+        printf("bayex_b200: cluster mbarrier timeout (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
+        __trap();
+      }
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar, int x, int y) {
+  // complete_tx lands on the leader CTA's barrier: clear the peer bit of the shared::cluster address
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"((uint64_t)map), "r"(bar & 0xFEFFFFFFu), "r"(x), "r"(y)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"((uint64_t)src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {  // arrives on `bar` in both CTAs
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3)
+               : "memory");
+}
+template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+__device__ __forceinline__ float4 lds128f(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// RC = candidates per producer thread.  128 / RC candidate groups x (2 RC) observation parts = 256 producer threads;
+// a thread generates RC candidates x (32 / RC) observations of every K-block.
+template <int D4, int RC>
+__global__ void __launch_bounds__(NTHREADS, 1)
+score_tc16p_kernel(const __grid_constant__ ScoreArgs a, const __grid_constant__ SamplerPack sp,
+                   const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  Smem& S = *reinterpret_cast<Smem*>(smem_raw);
+  constexpr int US = BKH * D4 + BKH;  // floats per staged K-block: 64 observation rows + 64 alpha
+  const uint32_t us_addr = smem_u32(smem_raw) + (uint32_t)sizeof(Smem);  // [NU][US]
+  if ((smem_u32(smem_raw) & 1023u) != 0u) __trap();
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = cluster_rank();
+  const bool leader = (rank == 0);
+  const int np = a.f.np;
+  const int nRB = (np + BN - 1) / BN;
+  const int nJtot = np / BKH;
+  const int nSB = (nRB + NACC - 1) / NACC;
+  const uint64_t ntiles = (a.m_count + TM - 1) / TM;
+  const uint64_t npairs = (ntiles + 1) / 2;  // pair-tiles of 256 candidates
+  const uint64_t pair0 = blockIdx.x >> 1, pstride = gridDim.x >> 1;
+
+  if (tid == 0) {
+    for (int i = 0; i < SA; ++i) { mbar_init(smem_u32(&S.full_a[i]), 2 * (NPROD / 32)); mbar_init(smem_u32(&S.empty_a[i]), 1); }
+    for (int i = 0; i < SB; ++i) { mbar_init(smem_u32(&S.full_b[i]), 2); mbar_init(smem_u32(&S.empty_b[i]), 1); }
+    for (int i = 0; i < NU; ++i) { mbar_init(smem_u32(&S.full_u[i]), 1); mbar_init(smem_u32(&S.empty_u[i]), NPROD / 32); }
+    for (int i = 0; i < NACC; ++i) { mbar_init(smem_u32(&S.tmem_full[i]), 1); mbar_init(smem_u32(&S.tmem_empty[i]), 8); }
+    mbar_init(smem_u32(&S.mean_full), NPROD / 32);
+    mbar_init(smem_u32(&S.mean_empty), 4);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_pair(smem_u32(&S.tmem_base), 512);
+  tc_fence_before();
+  cluster_sync_all();  // barriers of both CTAs initialised before anyone arrives remotely
+  tc_fence_after();
+  const uint32_t tmem = S.tmem_base;
+
+  if (warp < 4) {
+    reg_dec<56>();
+    if (warp == 0 && lane == 0) {
+      // ===== TMA: this CTA's 128-row half of every T tile (head + tail) =====
+      uint32_t it = 0;
+      for (uint64_t pt = pair0; pt < npairs; pt += pstride) {
+        for (int sb = 0; sb < nSB; ++sb) {
+          const int rb0 = sb * NACC, rb1 = min(rb0 + NACC, nRB);
+          for (int J = 0; J < min(KPR * rb1, nJtot); ++J) {
+            for (int rb = max(rb0, J / KPR); rb < rb1; ++rb, ++it) {
+              const uint32_t st = it % SB, ph = (it / SB) & 1;
+              mbar_wait<64>(smem_u32(&S.empty_b[st]), ph ^ 1);
+              const uint32_t bar = smem_u32(&S.full_b[st]);
+              if (leader) mbar_expect_tx(bar, 4 * BTILE);  // both halves, head + tail
+              else mbar_arrive_leader(bar);
+              tma_load_2d_pair(smem_u32(S.b_hi[st]), &map_hi, bar, J * BKH, rb * BN + (int)rank * HN);
+              tma_load_2d_pair(smem_u32(S.b_lo[st]), &map_lo, bar, J * BKH, rb * BN + (int)rank * HN);
+            }
+          }
+        }
+      }
+    } else if (warp == 1 && leader && lane == 0) {
+      // ===== MMA issuer (leader CTA only) =====
+      const uint32_t idesc = make_idesc_f16(BN, 2 * TM);
+      uint32_t ita = 0, itb = 0, acc_ph = 0;  // bit a of acc_ph = phase of accumulator a
+      for (uint64_t pt = pair0; pt < npairs; pt += pstride) {
+        for (int sb = 0; sb < nSB; ++sb) {
+          const int rb0 = sb * NACC, rb1 = min(rb0 + NACC, nRB);
+          for (int J = 0; J < min(KPR * rb1, nJtot); ++J, ++ita) {
+            const uint32_t sa = ita % SA, pa = (ita / SA) & 1;
+            mbar_wait_cluster(smem_u32(&S.full_a[sa]), pa);
+            tc_fence_after();
+            const uint64_t ah = make_desc(smem_u32(S.a_hi[sa])), al = make_desc(smem_u32(S.a_lo[sa]));
+            for (int rb = max(rb0, J / KPR); rb < rb1; ++rb, ++itb) {
+              const int acc = rb - rb0;
+              if (J == 0) {  // first write of this accumulator in this super-block: the epilogues must have drained it
+                mbar_wait_cluster(smem_u32(&S.tmem_empty[acc]), ((acc_ph >> acc) & 1) ^ 1);
+                tc_fence_after();
+              }
+              const uint32_t st = itb % SB, pb = (itb / SB) & 1;
+              mbar_wait(smem_u32(&S.full_b[st]), pb);
+              tc_fence_after();
+              const uint64_t bh = make_desc(smem_u32(S.b_hi[st])), bl = make_desc(smem_u32(S.b_lo[st]));
+              const uint32_t d = tmem + (uint32_t)(acc * BN);
+              if (!(a.debug & 2))
+#pragma unroll
+              for (int ks = 0; ks < BKH / 16; ++ks) {  // UMMA K = 16 halves = 32 bytes inside the swizzle atom
+                const uint64_t o = (uint64_t)(ks * 2);
+                umma_f16_pair(d, ah + o, bh + o, idesc, (J | ks) != 0);
+                umma_f16_pair(d, al + o, bh + o, idesc, 1u);
+                umma_f16_pair(d, ah + o, bl + o, idesc, 1u);
+              }
+              umma_commit_pair(smem_u32(&S.empty_b[st]));
+              if (J == min(KPR * rb + KPR, nJtot) - 1) {  // last K-block below the diagonal: this row block of V is complete
+                umma_commit_pair(smem_u32(&S.tmem_full[acc]));
+                acc_ph ^= 1u << acc;
+              }
+            }
+            umma_commit_pair(smem_u32(&S.empty_a[sa]));
+          }
+        }
+      }
+    } else if (warp == 2 && lane == 0) {
+      // ===== TMA: observation rows (scaled coordinates) + alpha of every K-block, NU-deep ring =====
+      uint32_t itu = 0;
+      for (uint64_t pt = pair0; pt < npairs; pt += pstride) {
+        for (int sb = 0; sb < nSB; ++sb) {
+          const int nJ = min(KPR * min(sb * NACC + NACC, nRB), nJtot);
+          for (int J = 0; J < nJ; ++J, ++itu) {
+            const uint32_t su = itu % NU, ph = (itu / NU) & 1;
+            mbar_wait<64>(smem_u32(&S.empty_u[su]), ph ^ 1);
+            const uint32_t bar = smem_u32(&S.full_u[su]), dst = us_addr + su * (uint32_t)(US * 4);
+            mbar_expect_tx(bar, (uint32_t)(US * 4));
+            bulk_load_1d(dst, a.f.d_U + (size_t)J * BKH * D4, (uint32_t)(BKH * D4 * 4), bar);
+            bulk_load_1d(dst + (uint32_t)(BKH * D4 * 4), a.f.d_alpha + (size_t)J * BKH, (uint32_t)(BKH * 4), bar);
+          }
+        }
+      }
+    }
+  } else if (warp < 8) {
+    reg_dec<96>();
+    // ===== epilogue (both CTAs, own 128 candidates): TMEM -> sum of squares -> std -> acquisition -> arg-max =====
+    constexpr int NOP = 2 * RC;
+    const int q = warp & 3, cl = q * 32 + lane;
+    const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
+    const float amp = a.f.d_hyp[HYP_AMP], ymean = a.f.d_hyp[HYP_YMEAN];
+    const float ksc = kstar_scale(amp);
+    const float unscale = 1.f / (a.f.d_hyp[HYP_T16SCALE] * ksc);  // operands were scaled by powers of two
+    const float unscale2 = unscale * unscale, mean_unscale = 1.f / ksc;
+    uint32_t acc_ph = 0, tiles_done = 0;
+    unsigned long long best = 0ull;
+    for (uint64_t pt = pair0; pt < npairs; pt += pstride, ++tiles_done) {
+      const uint64_t tile = 2 * pt + rank;
+      float ss = 0.f;
+      for (int sb = 0; sb < nSB; ++sb) {
+        const int rb0 = sb * NACC, rb1 = min(rb0 + NACC, nRB);
+        for (int acc = 0; acc < rb1 - rb0; ++acc) {
+          mbar_wait<128>(smem_u32(&S.tmem_full[acc]), (acc_ph >> acc) & 1);
+          acc_ph ^= 1u << acc;
+          tc_fence_after();
+#pragma unroll
+          for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t r[32];
+            tmem_ld32(lane_addr + (uint32_t)(acc * BN + c0), r);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const float v = __uint_as_float(r[i]);
+              ss = fmaf(v, v, ss);
+            }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (leader) mbar_arrive(smem_u32(&S.tmem_empty[acc]));
+            else mbar_arrive_leader(smem_u32(&S.tmem_empty[acc]));
+          }
+        }
+      }
+      mbar_wait<128>(smem_u32(&S.mean_full), tiles_done & 1);
+      float msum = 0.f;
+#pragma unroll
+      for (int o = 0; o < NOP; ++o) msum += S.mean_s[o][cl];
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&S.mean_empty));
+      const float mu = msum * mean_unscale + ymean;  // gp.py:67
+      const uint64_t row = tile * TM + cl;
+      if (row < a.m_count) {
+        const float var = amp - ss * unscale2;       // gp.py:69 (diagonal only)
+        const float sd = sqrtf(fmaxf(var, 1e-10f));  // gp.py:70
+        const float av = acquisition(a.acq_id, mu, sd, a.ystar, a.acq_param);
+        if (a.mu) a.mu[row] = mu;
+        if (a.sigma) a.sigma[row] = sd;
+        if (a.acq) a.acq[row] = av;
+        const unsigned long long key = pack_best(av, (uint32_t)(a.index_base + row));
+        best = key > best ? key : best;
+      }
+    }
+    if (a.best) {
+      best = warp_max_u64(best);
+      if (lane == 0 && best) atomicMax(a.best, best);
+    }
+  } else {
+    reg_inc<176>();
+    // ===== K* producers (both CTAs): RC candidates x OPT observations per thread and K-block =====
+    constexpr int NCG = TM / RC;         // candidate groups
+    constexpr int OPT = BKH / (2 * RC);  // observations per thread per K-block (32 / RC)
+    constexpr int OB = 8 / RC;           // observations in flight: RC * OB * 2 = 16 independent FMA chains
+    const int pth = tid - PROD0, cg = pth % NCG, op = pth / NCG;  // op is warp-uniform
+    const float amp = a.f.d_hyp[HYP_AMP];
+    const float ampk = amp * kstar_scale(amp);  // exact (power-of-two scale): entries land near 2^14
+    uint32_t ita = 0, itu = 0, tiles_done = 0;
+    for (uint64_t pt = pair0; pt < npairs; pt += pstride, ++tiles_done) {
+      const uint64_t tile = 2 * pt + rank;
+      uint64_t ncr[RC][D4 / 2];  // (-c_k, -c_{k+1}) packed: the squared distance runs on add.f32x2 / fma.f32x2
+#pragma unroll
+      for (int j = 0; j < RC; ++j) {
+        const uint64_t gidx = a.m_begin + tile * TM + cg + j * NCG;
+#pragma unroll
+        for (int k = 0; k < D4; k += 2) {
+          const float c0 = (k < a.f.d) ? sample_coord(sp.dim[k], gidx) * a.f.d_scale[k] : 0.f;
+          const float c1 = (k + 1 < a.f.d) ? sample_coord(sp.dim[k + 1], gidx) * a.f.d_scale[k + 1] : 0.f;
+          ncr[j][k / 2] = pack2(-c0, -c1);
+        }
+      }
+      float mpart[RC];
+#pragma unroll
+      for (int j = 0; j < RC; ++j) mpart[j] = 0.f;
+      for (int sb = 0; sb < nSB; ++sb) {
+        const bool last_sb = (sb == nSB - 1);
+        const int nJ = min(KPR * min(sb * NACC + NACC, nRB), nJtot);
+        for (int J = 0; J < nJ; ++J, ++ita, ++itu) {
+          const uint32_t su = itu % NU, pu = (itu / NU) & 1;
+          const uint32_t u = us_addr + su * (uint32_t)(US * 4) + (uint32_t)(op * OPT * D4 * 4);  // this thread's rows
+          const uint32_t al_addr = us_addr + su * (uint32_t)(US * 4) + (uint32_t)((BKH * D4 + op * OPT) * 4);
+          mbar_wait(smem_u32(&S.full_u[su]), pu);
+          const uint32_t sa = ita % SA, pa = (ita / SA) & 1;
+          mbar_wait(smem_u32(&S.empty_a[sa]), pa ^ 1);
+          const uint32_t a_hi = smem_u32(S.a_hi[sa]), a_lo = smem_u32(S.a_lo[sa]);
+          if (!(a.debug & 1))
+#pragma unroll
+          for (int g = 0; g < OPT / 8; ++g) {  // 8 observations -> one 16-byte chunk (8 halves) of RC rows of the A tile
+            float kv[RC][8];
+#pragma unroll
+            for (int b = 0; b < 8 / OB; ++b) {
+              uint64_t s01[RC][OB], s23[RC][OB];
+#pragma unroll
+              for (int j = 0; j < RC; ++j)
+#pragma unroll
+                for (int i = 0; i < OB; ++i) s01[j][i] = s23[j][i] = 0ull;
+#pragma unroll
+              for (int k4 = 0; k4 < D4; k4 += 4) {
+#pragma unroll
+                for (int i = 0; i < OB; ++i) {
+                  uint64_t u01, u23;
+                  lds_2x64(u + (uint32_t)(((g * 8 + b * OB + i) * D4 + k4) * 4), u01, u23);
+#pragma unroll
+                  for (int j = 0; j < RC; ++j) {
+                    const uint64_t d01 = add2(u01, ncr[j][k4 / 2]), d23 = add2(u23, ncr[j][k4 / 2 + 1]);
+                    s01[j][i] = fma2(d01, d01, s01[j][i]);
+                    s23[j][i] = fma2(d23, d23, s23[j][i]);
+                  }
+                }
+              }
+#pragma unroll
+              for (int j = 0; j < RC; ++j)
+#pragma unroll
+                for (int i = 0; i < OB; ++i) {
+                  float sx, sy;
+                  unpack2(add2(s01[j][i], s23[j][i]), sx, sy);
+                  kv[j][b * OB + i] = ampk * ex2_approx(-sx - sy);  // gp.py:64, times 2^a
+                }
+            }
+            if (last_sb) {  // gp.py:66-67: the last super-block visits every K-block, so the mean rides along there
+              const float4 a0 = lds128f(al_addr + (uint32_t)(g * 32)), a1 = lds128f(al_addr + (uint32_t)(g * 32 + 16));
+              const float al[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+              for (int j = 0; j < RC; ++j)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) mpart[j] = fmaf(al[i], kv[j][i], mpart[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < RC; ++j) split_store_f16(a_hi, a_lo, cg + j * NCG, op * (OPT / 8) + g, kv[j]);
+          }
+          fence_proxy_async();  // generic-proxy stores -> visible to the (leader's) tensor core
+          __syncwarp();
+          if (lane == 0) {
+            if (leader) mbar_arrive(smem_u32(&S.full_a[sa]));
+            else mbar_arrive_leader(smem_u32(&S.full_a[sa]));
+            mbar_arrive(smem_u32(&S.empty_u[su]));
+          }
+        }
+      }
+      mbar_wait(smem_u32(&S.mean_empty), (tiles_done & 1) ^ 1);
+#pragma unroll
+      for (int j = 0; j < RC; ++j) S.mean_s[op][cg + j * NCG] = mpart[j];
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&S.mean_full));
+    }
+  }
+  __syncwarp();
+  tc_fence_before();
+  cluster_sync_all();  // no CTA may exit (or free TMEM) while its peer can still touch its smem / barriers
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem, 512);
+  }
+}
+
+template <int D4, int RC>
+static int32_t launch_d4(cudaStream_t s, const ScoreArgs& a, const SamplerPack& sp, const CUtensorMap& mh, const CUtensorMap& ml) {
+  const size_t smem = sizeof(Smem) + sizeof(float) * NU * (BKH * D4 + BKH);
+  BX_CUDA(cudaFuncSetAttribute(score_tc16p_kernel<D4, RC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int dev = 0, sms = 0;
+  BX_CUDA(cudaGetDevice(&dev));
+  BX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const uint64_t ntiles = (a.m_count + TM - 1) / TM, npairs = (ntiles + 1) / 2;
+  const uint64_t max_pairs = (uint64_t)(sms / 2);
+  const unsigned grid = 2u * (unsigned)(npairs < max_pairs ? npairs : max_pairs);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(NTHREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  BX_CUDA(cudaLaunchKernelEx(&cfg, score_tc16p_kernel<D4, RC>, a, sp, mh, ml));
+  return 0;
+}
+
+}  // namespace tc16p
+
+int32_t launch_score_tc16p(cudaStream_t s, const ScoreArgs& a_in, const SamplerPack& sp) {
+  ScoreArgs a = a_in;
+  if (const char* e = getenv("BX_TC_ABLATE")) a.debug = atoi(e);
+  CUtensorMap mh, ml;
+  int32_t rc = tc::make_map_f16(&mh, a.f.d_T16hi, a.f.np, a.f.np, tc16p::HN);
+  if (rc) return rc;
+  rc = tc::make_map_f16(&ml, a.f.d_T16lo, a.f.np, a.f.np, tc16p::HN);
+  if (rc) return rc;
+  // RC = 4 candidates per producer thread while their coordinates fit the 176-register budget (d <= 20), else 2
+  switch (a.f.d4) {
+    case 4: return tc16p::launch_d4<4, 4>(s, a, sp, mh, ml);
+    case 8: return tc16p::launch_d4<8, 4>(s, a, sp, mh, ml);
+    case 12: return tc16p::launch_d4<12, 4>(s, a, sp, mh, ml);
+    case 16: return tc16p::launch_d4<16, 4>(s, a, sp, mh, ml);
+    case 20: return tc16p::launch_d4<20, 4>(s, a, sp, mh, ml);
+    case 24: return tc16p::launch_d4<24, 2>(s, a, sp, mh, ml);
+    case 28: return tc16p::launch_d4<28, 2>(s, a, sp, mh, ml);
+    case 32: return tc16p::launch_d4<32, 2>(s, a, sp, mh, ml);
+  }
+  set_error("tcgen05 engines support d <= 32 (d4=%d)", a.f.d4);
+  return BX_E_UNSUPPORTED;
+}
+
+}  // namespace bx

@@ -154,6 +154,40 @@ __device__ __forceinline__ void split_store(uint32_t hi_tile, uint32_t lo_tile, 
   sts128(lo_tile + off, l);
 }
 
+// ---- fp16 head/tail split (kind::f16 engines) ------------------------------------------------------------------
+// x = hi + lo with hi = fp16(x), lo = fp16(x - hi): 22 significand bits like the TF32 split, at twice the MMA rate.
+// fp16's narrow exponent is handled with two power-of-two scales: K* * 2^a (largest entry near 2^14, from the
+// amplitude) and T * 2^b (from max|T|, stored in hyp[HYP_T16SCALE] when the factor is built).
+constexpr int BKH = 64;  // observations per K-block of the fp16 engines: 64 halves = 128 B = one SWIZZLE_128B row
+__device__ __forceinline__ float kstar_scale(float amp) { return exp2f(floorf(log2f(16384.f / amp))); }
+
+__host__ __device__ constexpr uint32_t make_idesc_f16(int n, int m = TM) {  // kind::f16, A/B = F16 (0), D = F32, K-major
+  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+__device__ __forceinline__ uint32_t pack_f16x2(float lo_elem, float hi_elem) {  // one cvt.rn.f16x2.f32
+  uint32_t r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_elem), "f"(lo_elem));
+  return r;
+}
+__device__ __forceinline__ void unpack_f16x2(uint32_t h, float& lo_elem, float& hi_elem) {
+  asm("{\n\t.reg .b16 a, b;\n\tmov.b32 {a, b}, %2;\n\tcvt.f32.f16 %0, a;\n\tcvt.f32.f16 %1, b;\n\t}"
+      : "=f"(lo_elem), "=f"(hi_elem) : "r"(h));
+}
+// 8 scaled values -> fp16 head and tail, one 16-byte chunk each (chunk q of row `row` of a SWIZZLE_128B tile)
+__device__ __forceinline__ void split_store_f16(uint32_t hi_tile, uint32_t lo_tile, int row, int q, const float (&v)[8]) {
+  uint32_t hw[4], lw[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    hw[i] = pack_f16x2(v[2 * i], v[2 * i + 1]);
+    float h0, h1;
+    unpack_f16x2(hw[i], h0, h1);
+    lw[i] = pack_f16x2(v[2 * i] - h0, v[2 * i + 1] - h1);
+  }
+  const uint32_t off = (uint32_t)(row * 128 + ((q ^ (row & 7)) << 4));
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(hi_tile + off), "r"(hw[0]), "r"(hw[1]), "r"(hw[2]), "r"(hw[3]) : "memory");
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(lo_tile + off), "r"(lw[0]), "r"(lw[1]), "r"(lw[2]), "r"(lw[3]) : "memory");
+}
+
 // ---- host side ------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -185,6 +219,20 @@ inline int32_t make_map(CUtensorMap* m, const float* base, uint64_t rows, uint64
   return 0;
 }
 
+// fp16 row-major [rows x cols] matrix, box = box_rows x 64 columns (128 B), SWIZZLE_128B
+inline int32_t make_map_f16(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  BX_CHECK_ARG(fn, BX_E_UNSUPPORTED, "cuTensorMapEncodeTiled not available from the driver");
+  const cuuint64_t dims[2] = {cols, rows};
+  const cuuint64_t strides[1] = {cols * 2};
+  const cuuint32_t box[2] = {(cuuint32_t)BKH, box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  BX_CHECK_ARG(r == CUDA_SUCCESS, BX_E_UNSUPPORTED, "cuTensorMapEncodeTiled(fp16) failed with CUresult %d", (int)r);
+  return 0;
+}
 
 }  // namespace tc
 }  // namespace bx

@@ -49,7 +49,8 @@ enum {
   BX_ENGINE_SIMT = 1,
   BX_ENGINE_TCGEN05 = 2,      /* 3xTF32, one CTA per tile */
   BX_ENGINE_TCGEN05_PAIR = 3, /* 3xTF32, cta_group::2 */
-  BX_ENGINE_TCGEN05_F16 = 4   /* fp16 head/tail split (same 22-bit operands, half the tensor work) */
+  BX_ENGINE_TCGEN05_F16 = 4,  /* fp16 head/tail split (same 22-bit operands, half the tensor work) */
+  BX_ENGINE_TCGEN05_F16_PAIR = 5 /* fp16 head/tail split, cta_group::2, register-tiled K* producers (AUTO picks this) */
 };
 
 /* One dimension of the parameter space - mirrors bayex.domain.Real / Integer (domain.py:22-131). */
