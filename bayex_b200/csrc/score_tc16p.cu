@@ -32,7 +32,10 @@ using namespace bx::tc;
 
 constexpr int BN = 256;                    // T rows per accumulator = UMMA N
 constexpr int HN = BN / 2;                 // rows of every T tile held by one CTA
-constexpr int NACC = 2, SA = 2, SB = 4, NU = 3;
+// Ring depths.  A stage of K* is refilled only after the MMAs that read it have completed, so with P = producer time and
+// Tm = MMA time per K-block (both ~3000 clk) a 2-deep ring runs at (P + Tm + latencies) / 2 per K-block; 3 stages reach
+// max(P, Tm).  T tiles: 3 stages = 1.5 K-blocks of TMA look-ahead.
+constexpr int NACC = 2, SA = 3, SB = 3, NU = 3;
 constexpr int KPR = BN / BKH;              // K-blocks per row block
 constexpr int ATILE = TM * BKH * 2;        // 16 KiB: 128 candidates x 64 halves
 constexpr int BTILE = HN * BKH * 2;        // 16 KiB: 128 T rows x 64 halves
@@ -62,6 +65,17 @@ __device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {  // the same 
       "{\n\t.reg .b32 ra;\n\t"
       "mapa.shared::cluster.u32 ra, %0, 0;\n\t"
       "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(bar)
+      : "memory");
+}
+// Same, with the default (.release.cta) semantics: no MEMBAR.ALL.GPU in front of the arrive (ncu: 8 % of the rank-1
+// producers' samples sat on that fence).  Used where the data being published was written to this CTA's own shared
+// memory and already made visible to the async proxy by fence.proxy.async - the consumer is this SM's tensor core.
+__device__ __forceinline__ void mbar_arrive_leader_relaxed(uint32_t bar) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, 0;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
       ::"r"(bar)
       : "memory");
 }
@@ -179,7 +193,7 @@ score_tc16p_kernel(const __grid_constant__ ScoreArgs a, const __grid_constant__ 
           for (int J = 0; J < min(KPR * rb1, nJtot); ++J) {
             for (int rb = max(rb0, J / KPR); rb < rb1; ++rb, ++it) {
               const uint32_t st = it % SB, ph = (it / SB) & 1;
-              mbar_wait<64>(smem_u32(&S.empty_b[st]), ph ^ 1);
+              mbar_wait<256>(smem_u32(&S.empty_b[st]), ph ^ 1);
               const uint32_t bar = smem_u32(&S.full_b[st]);
               if (leader) mbar_expect_tx(bar, 4 * BTILE);  // both halves, head + tail
               else mbar_arrive_leader(bar);
@@ -198,7 +212,7 @@ score_tc16p_kernel(const __grid_constant__ ScoreArgs a, const __grid_constant__ 
           const int rb0 = sb * NACC, rb1 = min(rb0 + NACC, nRB);
           for (int J = 0; J < min(KPR * rb1, nJtot); ++J, ++ita) {
             const uint32_t sa = ita % SA, pa = (ita / SA) & 1;
-            mbar_wait_cluster(smem_u32(&S.full_a[sa]), pa);
+            mbar_wait_cluster<32>(smem_u32(&S.full_a[sa]), pa);  // back-off: the hot spin took 27 % of this SMSP's issue slots
             tc_fence_after();
             const uint64_t ah = make_desc(smem_u32(S.a_hi[sa])), al = make_desc(smem_u32(S.a_lo[sa]));
             for (int rb = max(rb0, J / KPR); rb < rb1; ++rb, ++itb) {
@@ -208,7 +222,7 @@ score_tc16p_kernel(const __grid_constant__ ScoreArgs a, const __grid_constant__ 
                 tc_fence_after();
               }
               const uint32_t st = itb % SB, pb = (itb / SB) & 1;
-              mbar_wait(smem_u32(&S.full_b[st]), pb);
+              mbar_wait<32>(smem_u32(&S.full_b[st]), pb);
               tc_fence_after();
               const uint64_t bh = make_desc(smem_u32(S.b_hi[st])), bl = make_desc(smem_u32(S.b_lo[st]));
               const uint32_t d = tmem + (uint32_t)(acc * BN);
@@ -238,7 +252,7 @@ score_tc16p_kernel(const __grid_constant__ ScoreArgs a, const __grid_constant__ 
           const int nJ = min(KPR * min(sb * NACC + NACC, nRB), nJtot);
           for (int J = 0; J < nJ; ++J, ++itu) {
             const uint32_t su = itu % NU, ph = (itu / NU) & 1;
-            mbar_wait<64>(smem_u32(&S.empty_u[su]), ph ^ 1);
+            mbar_wait<256>(smem_u32(&S.empty_u[su]), ph ^ 1);
             const uint32_t bar = smem_u32(&S.full_u[su]), dst = us_addr + su * (uint32_t)(US * 4);
             mbar_expect_tx(bar, (uint32_t)(US * 4));
             bulk_load_1d(dst, a.f.d_U + (size_t)J * BKH * D4, (uint32_t)(BKH * D4 * 4), bar);
@@ -395,7 +409,7 @@ score_tc16p_kernel(const __grid_constant__ ScoreArgs a, const __grid_constant__ 
           __syncwarp();
           if (lane == 0) {
             if (leader) mbar_arrive(smem_u32(&S.full_a[sa]));
-            else mbar_arrive_leader(smem_u32(&S.full_a[sa]));
+            else mbar_arrive_leader_relaxed(smem_u32(&S.full_a[sa]));
             mbar_arrive(smem_u32(&S.empty_u[su]));
           }
         }
