@@ -5,6 +5,7 @@
 """
 from . import acq, domain, gp, random  # noqa: F401
 from .optimizer import Optimizer, OptimizerState  # noqa: F401
+from .state_io import load_state, save_state  # noqa: F401
 
 __version__ = "0.2.2+b200.1"
 

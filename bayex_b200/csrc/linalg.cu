@@ -2,6 +2,7 @@
 // triangular inverse, triangular mat-vecs.  Tensor cores are deliberately not used here (north star: only the
 // candidate contraction may use them).
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "internal.h"
 
@@ -123,7 +124,167 @@ __global__ void __launch_bounds__(256) gemm64_kernel(GemmArgs g) {
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// 128x128x16 SIMT GEMM for the large products of the fit path (K^-1 = T^T T, the triangular-inverse tree, the
+// Cholesky panel / trailing updates).  256 threads, 8x8 register tile per thread (two 4x4 blocks per dimension, 64
+// apart, so every shared-memory read is one LDS.128), double-buffered shared tiles, register-staged global loads
+// of the next k-step in flight under the FMAs.  Extents are multiples of 64: edge tiles are guarded per float4.
+// Same K-range restrictions (triangular operands) and tree-batched mode as gemm64_kernel.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int HT = 128, HK = 16, HP = HT + 4;
+
+template <bool TA, bool TB>
+__global__ void __launch_bounds__(256, 2) gemm128_kernel(GemmArgs g) {
+  __shared__ __align__(16) float As[2][HK][HP];
+  __shared__ __align__(16) float Bs[2][HK][HP];
+  const float* A = g.A;
+  const float* B = g.B;
+  float* C = g.C;
+  int M = g.M, N = g.N, K = g.K, kmode = g.kmode;
+  float alpha = g.alpha;
+  if (g.tree_nb > 0) {
+    int lo, mid, hi;
+    tree_node(g.tree_nb, g.tree_level, blockIdx.z, lo, mid, hi);
+    if (hi - lo < 2) return;
+    if (g.tree_pass == 1) {  // TMP[mid:hi, lo:mid] = L[mid:hi, lo:mid] * T[lo:mid, lo:mid]
+      A += (size_t)mid * NB * g.lda + (size_t)lo * NB;
+      B += (size_t)lo * NB * g.ldb + (size_t)lo * NB;
+      C += (size_t)mid * NB * g.ldc + (size_t)lo * NB;
+      M = (hi - mid) * NB; N = K = (mid - lo) * NB; kmode = KM_B_LOWER; alpha = 1.f;
+    } else {                 // T[mid:hi, lo:mid] = -T[mid:hi, mid:hi] * TMP[mid:hi, lo:mid]
+      A += (size_t)mid * NB * g.lda + (size_t)mid * NB;
+      B += (size_t)mid * NB * g.ldb + (size_t)lo * NB;
+      C += (size_t)mid * NB * g.ldc + (size_t)lo * NB;
+      M = K = (hi - mid) * NB; N = (mid - lo) * NB; kmode = KM_A_LOWER; alpha = -1.f;
+    }
+  }
+  const int i0 = blockIdx.y * HT, j0 = blockIdx.x * HT;
+  if (i0 >= M || j0 >= N) return;
+  if (g.lower_only && j0 > i0) return;
+  int k_lo = 0, k_hi = K;
+  if (kmode == KM_A_LOWER) k_hi = min(K, i0 + HT);
+  else if (kmode == KM_B_LOWER) k_lo = j0;
+  else if (kmode == KM_TN_BOTH) k_lo = max(i0, j0);
+  else if (kmode == KM_TN_A) k_lo = i0;
+
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  float acc[8][8];
+#pragma unroll
+  for (int r = 0; r < 8; ++r)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[r][c] = 0.f;
+
+  // global -> register staging: 512 float4 per operand tile, two per thread
+  // row-major-in-k operands ([rows x K], "transpose on store"): f -> row f/4, k-quad f%4
+  // k-major operands ([K x cols], direct store):               f -> k f/32, col-quad f%32
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  auto load_a = [&](int k0, int q) -> float4 {
+    const int f = tid + q * 256;
+    if (TA) {
+      const int kk = f >> 5, c4 = (f & 31) * 4;
+      return (i0 + c4 < M) ? *reinterpret_cast<const float4*>(A + (size_t)(k0 + kk) * g.lda + i0 + c4) : zero4;
+    } else {
+      const int r = f >> 2, c4 = (f & 3) * 4;
+      return (i0 + r < M) ? *reinterpret_cast<const float4*>(A + (size_t)(i0 + r) * g.lda + k0 + c4) : zero4;
+    }
+  };
+  auto load_b = [&](int k0, int q) -> float4 {
+    const int f = tid + q * 256;
+    if (!TB) {
+      const int kk = f >> 5, c4 = (f & 31) * 4;
+      return (j0 + c4 < N) ? *reinterpret_cast<const float4*>(B + (size_t)(k0 + kk) * g.ldb + j0 + c4) : zero4;
+    } else {
+      const int r = f >> 2, c4 = (f & 3) * 4;
+      return (j0 + r < N) ? *reinterpret_cast<const float4*>(B + (size_t)(j0 + r) * g.ldb + k0 + c4) : zero4;
+    }
+  };
+  auto store_a = [&](int buf, int q, const float4& v) {
+    const int f = tid + q * 256;
+    if (TA) {
+      *reinterpret_cast<float4*>(&As[buf][f >> 5][(f & 31) * 4]) = v;
+    } else {
+      const int r = f >> 2, c4 = (f & 3) * 4;
+      As[buf][c4 + 0][r] = v.x; As[buf][c4 + 1][r] = v.y; As[buf][c4 + 2][r] = v.z; As[buf][c4 + 3][r] = v.w;
+    }
+  };
+  auto store_b = [&](int buf, int q, const float4& v) {
+    const int f = tid + q * 256;
+    if (!TB) {
+      *reinterpret_cast<float4*>(&Bs[buf][f >> 5][(f & 31) * 4]) = v;
+    } else {
+      const int r = f >> 2, c4 = (f & 3) * 4;
+      Bs[buf][c4 + 0][r] = v.x; Bs[buf][c4 + 1][r] = v.y; Bs[buf][c4 + 2][r] = v.z; Bs[buf][c4 + 3][r] = v.w;
+    }
+  };
+
+  if (k_lo < k_hi) {
+    float4 ra[2], rb[2];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) { ra[q] = load_a(k_lo, q); rb[q] = load_b(k_lo, q); }
+#pragma unroll
+    for (int q = 0; q < 2; ++q) { store_a(0, q, ra[q]); store_b(0, q, rb[q]); }
+    __syncthreads();
+    int buf = 0;
+    for (int k0 = k_lo; k0 < k_hi; k0 += HK) {
+      const bool more = (k0 + HK < k_hi);
+      if (more) {
+#pragma unroll
+        for (int q = 0; q < 2; ++q) { ra[q] = load_a(k0 + HK, q); rb[q] = load_b(k0 + HK, q); }
+      }
+#pragma unroll
+      for (int kk = 0; kk < HK; ++kk) {
+        const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 4]);
+        const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][kk][64 + ty * 4]);
+        const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 4]);
+        const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][kk][64 + tx * 4]);
+        const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+#pragma unroll
+          for (int c = 0; c < 8; ++c) acc[r][c] = fmaf(av[r], bv[c], acc[r][c]);
+      }
+      if (more) {
+#pragma unroll
+        for (int q = 0; q < 2; ++q) { store_a(buf ^ 1, q, ra[q]); store_b(buf ^ 1, q, rb[q]); }
+      }
+      __syncthreads();
+      buf ^= 1;
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    const int row = i0 + (r < 4 ? ty * 4 + r : 64 + ty * 4 + (r - 4));
+    if (row >= M) continue;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int col = j0 + h * 64 + tx * 4;
+      if (col >= N) continue;
+      float* cp = C + (size_t)row * g.ldc + col;
+      float4 o = make_float4(alpha * acc[r][h * 4 + 0], alpha * acc[r][h * 4 + 1], alpha * acc[r][h * 4 + 2], alpha * acc[r][h * 4 + 3]);
+      if (g.beta != 0.f) {
+        const float4 c = *reinterpret_cast<const float4*>(cp);
+        o.x = fmaf(g.beta, c.x, o.x); o.y = fmaf(g.beta, c.y, o.y); o.z = fmaf(g.beta, c.z, o.z); o.w = fmaf(g.beta, c.w, o.w);
+      }
+      *reinterpret_cast<float4*>(cp) = o;
+    }
+  }
+}
+
 int32_t gemm(cudaStream_t s, bool ta, bool tb, const GemmArgs& g, int grid_z) {
+  if (g.M <= 0 || g.N <= 0) return 0;
+  // large, squarish products go to the 128x128 kernel; skinny ones (panels of 64, the refinement's 64 starts) stay on 64x64
+  static const bool force64 = getenv("BX_GEMM64") != nullptr;
+  if (g.M >= HT && g.N >= HT && !force64) {
+    dim3 grid((g.N + HT - 1) / HT, (g.M + HT - 1) / HT, grid_z);
+    if (!ta && !tb) gemm128_kernel<false, false><<<grid, 256, 0, s>>>(g);
+    else if (ta && !tb) gemm128_kernel<true, false><<<grid, 256, 0, s>>>(g);
+    else if (!ta && tb) gemm128_kernel<false, true><<<grid, 256, 0, s>>>(g);
+    else gemm128_kernel<true, true><<<grid, 256, 0, s>>>(g);
+    BX_LAUNCH_CHECK();
+    return 0;
+  }
   dim3 grid(g.N / GT, g.M / GT, grid_z);
   if (grid.x == 0 || grid.y == 0) return 0;
   if (!ta && !tb) gemm64_kernel<false, false><<<grid, 256, 0, s>>>(g);
@@ -137,63 +298,82 @@ int32_t gemm(cudaStream_t s, bool ta, bool tb, const GemmArgs& g, int grid_z) {
 // ------------------------------------------------------------------------------------------------------------------
 // Diagonal-block factorisation: L_kk = chol(A_kk) in shared memory, plus L_kk^-1 and sum(log diag).
 // ------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) potrf_diag_kernel(float* A, int lda, int kb, float* Dinv, float* logdet_part,
-                                                         int* status) {
-  __shared__ float S[NB][NB + 1];
-  __shared__ float X[NB][NB + 1];
-  const int tid = threadIdx.x;
+// One thread per row, the row lives in registers (fully unrolled): per column ONE block barrier (the raw column and
+// the pivot are published together; the update uses a_ij a_cj / d_j instead of l_ij l_cj), then the inverse by forward
+// substitution with one column per thread.  ~5 us per 64x64 block instead of ~35 us for the shared-memory version:
+// this kernel is the serial chain of the blocked Cholesky (np / 64 launches per factorisation).
+constexpr int LP = NB + 4;  // padded row length of the shared copy of L (16-byte aligned rows)
+__global__ void __launch_bounds__(NB) potrf_diag_kernel(float* A, int lda, int kb, float* Dinv, float* logdet_part,
+                                                        int* status) {
+  __shared__ __align__(16) float Ls[NB][LP];
+  __shared__ __align__(16) float col[2][NB];
+  const int i = threadIdx.x;
   float* blk = A + (size_t)kb * NB * lda + (size_t)kb * NB;
-  for (int e = tid; e < NB * NB; e += 256) {
+  for (int e = i; e < NB * NB; e += NB) {  // coalesced load, then each thread picks up its row
     const int r = e >> 6, c = e & 63;
-    S[r][c] = (c <= r) ? blk[(size_t)r * lda + c] : 0.f;
-    X[r][c] = 0.f;
+    Ls[r][c] = blk[(size_t)r * lda + c];
   }
   __syncthreads();
+  float a[NB];
+#pragma unroll
+  for (int c = 0; c < NB; ++c) a[c] = Ls[i][c];
+  bool bad = false;
+#pragma unroll
   for (int j = 0; j < NB; ++j) {
-    if (tid == 0) {
-      const float dj = S[j][j];
-      if (!(dj > 0.f) || !(dj < CUDART_INF_F)) atomicOr(status, 1);
-      S[j][j] = sqrtf(dj);
-    }
+    col[j & 1][i] = a[j];  // rows >= j publish their (fully updated) entry of column j; row j's is the pivot
     __syncthreads();
-    const float inv = 1.f / S[j][j];
-    if (tid > j && tid < NB) S[tid][j] *= inv;
-    __syncthreads();
-    const int rem = NB - 1 - j;  // trailing square (j+1..63)^2, lower part only
-    for (int e = tid; e < rem * rem; e += 256) {
-      const int r = j + 1 + e / rem, c = j + 1 + e % rem;
-      if (c <= r) S[r][c] = fmaf(-S[r][j], S[c][j], S[r][c]);
-    }
-    __syncthreads();
-  }
-  // inverse by forward substitution, one column per thread
-  if (tid < NB) {
-    const int c = tid;
-    X[c][c] = 1.f / S[c][c];
-    for (int i = c + 1; i < NB; ++i) {
-      float acc = 0.f;
-      for (int j = c; j < i; ++j) acc = fmaf(S[i][j], X[j][c], acc);
-      X[i][c] = -acc / S[i][i];
+    const float dj = col[j & 1][j];
+    if (!(dj > 0.f) || !(dj < CUDART_INF_F)) bad = true;
+    const float f = a[j] / dj;  // l_ij / l_jj
+    if (i >= j) a[j] = (i == j) ? sqrtf(dj) : a[j] / sqrtf(dj);
+#pragma unroll
+    for (int c4 = (j + 1) & ~3; c4 < NB; c4 += 4) {
+      const float4 cv = *reinterpret_cast<const float4*>(&col[j & 1][c4]);
+      if (c4 + 0 > j) a[c4 + 0] = fmaf(-f, cv.x, a[c4 + 0]);
+      if (c4 + 1 > j) a[c4 + 1] = fmaf(-f, cv.y, a[c4 + 1]);
+      if (c4 + 2 > j) a[c4 + 2] = fmaf(-f, cv.z, a[c4 + 2]);
+      if (c4 + 3 > j) a[c4 + 3] = fmaf(-f, cv.w, a[c4 + 3]);
     }
   }
+  if (bad && i == 0) atomicOr(status, 1);
   __syncthreads();
-  float* dinv = Dinv + (size_t)kb * NB * NB;
-  for (int e = tid; e < NB * NB; e += 256) {
-    const int r = e >> 6, c = e & 63;
-    if (c <= r) blk[(size_t)r * lda + c] = S[r][c];
-    dinv[e] = X[r][c];
+#pragma unroll
+  for (int c = 0; c < NB; ++c) Ls[i][c] = (c <= i) ? a[c] : 0.f;
+  __syncthreads();
+  // X = L^-1, column i: x_r = -(sum_{j<r} l_rj x_j) / l_rr for r > i, x_i = 1 / l_ii, x_r = 0 for r < i
+  float x[NB];
+#pragma unroll
+  for (int r = 0; r < NB; ++r) {
+    float accv = 0.f;
+#pragma unroll
+    for (int j4 = 0; j4 < r; j4 += 4) {
+      const float4 lv = *reinterpret_cast<const float4*>(&Ls[r][j4]);
+      if (j4 + 0 < r) accv = fmaf(lv.x, x[j4 + 0], accv);
+      if (j4 + 1 < r) accv = fmaf(lv.y, x[j4 + 1], accv);
+      if (j4 + 2 < r) accv = fmaf(lv.z, x[j4 + 2], accv);
+      if (j4 + 3 < r) accv = fmaf(lv.w, x[j4 + 3], accv);
+    }
+    const float inv = 1.f / Ls[r][r];
+    x[r] = (r < i) ? 0.f : ((r == i) ? inv : -accv * inv);
   }
-  if (tid < 32) {
-    float l = logf(S[tid][tid]) + logf(S[tid + 32][tid + 32]);
+  float* dinv = Dinv + (size_t)kb * NB * NB;
+#pragma unroll
+  for (int r = 0; r < NB; ++r) dinv[r * NB + i] = x[r];
+  for (int e = i; e < NB * NB; e += NB) {
+    const int r = e >> 6, c = e & 63;
+    if (c <= r) blk[(size_t)r * lda + c] = Ls[r][c];
+  }
+  if (i < 32) {
+    float l = logf(Ls[i][i]) + logf(Ls[i + 32][i + 32]);
     l = warp_sum(l);
-    if (tid == 0) logdet_part[kb] = l;
+    if (i == 0) logdet_part[kb] = l;
   }
 }
 
 int32_t cholesky_inplace(cudaStream_t s, float* A, int np, int lda, float* Dinv, float* logdet_part, int* status) {
   const int nb = np / NB;
   for (int k = 0; k < nb; ++k) {
-    potrf_diag_kernel<<<1, 256, 0, s>>>(A, lda, k, Dinv, logdet_part, status);
+    potrf_diag_kernel<<<1, NB, 0, s>>>(A, lda, k, Dinv, logdet_part, status);
     BX_LAUNCH_CHECK();
     const int rem = nb - k - 1;
     if (rem == 0) break;

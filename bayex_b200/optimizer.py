@@ -42,7 +42,7 @@ class Optimizer:
     N_STARTS = 50        # optimizer.py:196
     REFINE_ROUNDS = 30   # role of max_iter=10 L-BFGS iterations x line-search evaluations (optimizer.py:199)
 
-    def __init__(self, domain: dict, acq: str = "EI", maximize: bool = False):
+    def __init__(self, domain: dict, acq: str = "EI", maximize: bool = False, *, acq_param: float = None):
         self.domain = domain
         self.sign = 1 if maximize else -1  # optimizer.py:95
         self.param_space = ParamSpace(domain)
@@ -51,7 +51,9 @@ class Optimizer:
         self.acq_name = acq
         self.acq = getattr(boacq, {"EI": "expected_improvement", "PI": "probability_improvement",
                                    "UCB": "upper_confidence_bounds", "LCB": "lower_confidence_bounds"}[acq])
-        self.acq_param = boacq.DEFAULT_PARAM[acq]  # Q13: the reference offers no override
+        # Q13: the reference offers no override of xi / kappa at this level; ``acq_param`` (keyword-only, SURVEY 8(f)
+        # rank 3) passes one through to the kernels - None keeps the reference defaults (acq.py:13,58,95,129)
+        self.acq_param = boacq.DEFAULT_PARAM[acq] if acq_param is None else float(acq_param)
         self.engine = _lib.ENGINE_AUTO
         self._dims = engine.dims_array(domain)
         self._cache = {}

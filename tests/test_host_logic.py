@@ -121,3 +121,37 @@ def test_merge_topk_equals_global_stable_argsort():
         parts_v.append(vals[loc]); parts_i.append(loc.astype(np.int32))
     v, i = bopt.merge_topk(np.concatenate(parts_v), np.concatenate(parts_i), 50)
     assert np.array_equal(i, want)
+
+
+def test_state_save_load_roundtrip(tmp_path):
+    """flat .npz format; dtypes (int32 Integer storage before the first fit) survive."""
+    from bayex_b200.gp import GPParams
+    st = bayex.OptimizerState(
+        params={"a": np.array([0.5, 1.5, 0, 0], np.float32), "k": np.array([3, -2, 0, 0], np.int32)},
+        ys=np.array([1.0, -2.0, 0, 0], np.float32), best_score=1.0, best_params={"a": np.float32(0.5), "k": np.int32(3)},
+        mask=np.array([True, True, False, False]),
+        gp_params=GPParams(np.float32(-7.9), np.float32(0.1), np.array([0.2, -0.3], np.float32)))
+    path = tmp_path / "state.npz"
+    bayex.save_state(path, st)
+    back = bayex.load_state(path)
+    assert list(back.params) == ["a", "k"] and back.params["k"].dtype == np.int32 and back.params["a"].dtype == np.float32
+    for k in st.params:
+        assert np.array_equal(back.params[k], st.params[k]) and back.best_params[k] == st.best_params[k]
+        assert back.best_params[k].dtype == st.best_params[k].dtype
+    assert np.array_equal(back.ys, st.ys) and np.array_equal(back.mask, st.mask) and back.mask.dtype == bool
+    assert back.best_score == st.best_score
+    for a, b in zip(back.gp_params, st.gp_params):
+        assert np.array_equal(np.asarray(a), np.asarray(b))
+    # the posterior cache key is a digest of exactly these arrays: a reloaded state must hit the same key
+    opt = bayex.Optimizer({"a": Real(0.0, 2.0), "k": Integer(-5, 5)}, acq="EI")
+    from bayex_b200 import engine
+    dig = lambda s: opt._digest(*opt._arrays(s.params, s.ys, s.mask), engine.raw_vector(s.gp_params, 2))
+    assert dig(st) == dig(back)
+
+
+def test_acq_param_passthrough_keeps_reference_defaults():
+    dom = {"x": Real(0.0, 1.0)}
+    assert bayex.Optimizer(dom, acq="EI").acq_param == np.float32(0.01) or bayex.Optimizer(dom, acq="EI").acq_param == 0.01
+    assert bayex.Optimizer(dom, acq="LCB").acq_param == 2.576
+    assert bayex.Optimizer(dom, acq="UCB", acq_param=1.5).acq_param == 1.5
+    assert bayex.Optimizer(dom, "PI", True).sign == 1  # positional order of the reference is untouched
