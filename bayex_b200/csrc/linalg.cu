@@ -298,82 +298,168 @@ int32_t gemm(cudaStream_t s, bool ta, bool tb, const GemmArgs& g, int grid_z) {
 // ------------------------------------------------------------------------------------------------------------------
 // Diagonal-block factorisation: L_kk = chol(A_kk) in shared memory, plus L_kk^-1 and sum(log diag).
 // ------------------------------------------------------------------------------------------------------------------
-// One thread per row, the row lives in registers (fully unrolled): per column ONE block barrier (the raw column and
-// the pivot are published together; the update uses a_ij a_cj / d_j instead of l_ij l_cj), then the inverse by forward
-// substitution with one column per thread.  ~5 us per 64x64 block instead of ~35 us for the shared-memory version:
-// this kernel is the serial chain of the blocked Cholesky (np / 64 launches per factorisation).
-constexpr int LP = NB + 4;  // padded row length of the shared copy of L (16-byte aligned rows)
-__global__ void __launch_bounds__(NB) potrf_diag_kernel(float* A, int lda, int kb, float* Dinv, float* logdet_part,
-                                                        int* status) {
-  __shared__ __align__(16) float Ls[NB][LP];
-  __shared__ __align__(16) float col[2][NB];
-  const int i = threadIdx.x;
+// This kernel is the serial chain of the blocked Cholesky (np / 64 launches per factorisation), so it is built for
+// latency.  The 64x64 block is handled as 2x2 blocks of 32; a 32x32 factorisation or triangular solve runs inside ONE
+// warp with a matrix row per lane in registers (fully unrolled, shuffles instead of barriers: ~90 clocks per column
+// on the critical path); the 32x32x32 products in between use all eight warps.  Seven block barriers in total.
+//   A00 = L00 L00^T | T00 = L00^-1, L10 = A10 L00^-T | A11 -= L10 L10^T | A11 = L11 L11^T | T11 = L11^-1,
+//   W = L10 T00 | T10 = -T11 W
+constexpr int LP = NB + 1;
+constexpr unsigned FULLW = 0xffffffffu;
+
+// lane i holds row i of a symmetric positive-definite 32x32 block (upper part zero); on return row i of its Cholesky factor
+__device__ __forceinline__ float chol32_warp(float (&a)[32], int lane, bool& bad) {
+  float diag = 1.f;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const float d = __shfl_sync(FULLW, a[j], j);
+    if (!(d > 0.f) || !(d < CUDART_INF_F)) bad = true;
+    float rs = rsqrtf(d);
+    rs = rs * fmaf(-0.5f * d, rs * rs, 1.5f);  // one Newton step: full fp32 accuracy without sqrt + divide in the chain
+    const float lij = (lane == j) ? d * rs : a[j] * rs;
+    a[j] = lij;
+    if (lane == j) diag = lij;
+#pragma unroll
+    for (int c = j + 1; c < 32; ++c) a[c] = fmaf(-lij, __shfl_sync(FULLW, lij, c), a[c]);
+  }
+  return diag;  // l_ii of this lane's row
+}
+// lane r holds row r of B; solves X L^T = B in place (L lower 32x32 in shared memory, row stride LP, rdiag = 1 / diag).
+// With B = identity this gives row r of L^-T = column r of L^-1.
+__device__ __forceinline__ void trsm32_warp(float (&b)[32], const float* L, const float* rdiag) {
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    b[j] *= rdiag[j];
+#pragma unroll
+    for (int c = j + 1; c < 32; ++c) b[c] = fmaf(-b[j], L[c * LP + j], b[c]);
+  }
+}
+
+__global__ void __launch_bounds__(256) potrf_diag_kernel(float* A, int lda, int kb, float* Dinv, float* logdet_part,
+                                                         int* status) {
+  __shared__ float S[NB][LP];   // A block -> L
+  __shared__ float X[NB][LP];   // L^-1
+  __shared__ float W[32][33];   // L10 T00
+  __shared__ float rdiag[NB];
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(FULLW, tid >> 5, 0);  // provably warp-uniform: the role branches below stay convergent
   float* blk = A + (size_t)kb * NB * lda + (size_t)kb * NB;
-  for (int e = i; e < NB * NB; e += NB) {  // coalesced load, then each thread picks up its row
+  for (int e = tid; e < NB * NB; e += 256) {
     const int r = e >> 6, c = e & 63;
-    Ls[r][c] = blk[(size_t)r * lda + c];
+    S[r][c] = (c <= r) ? blk[(size_t)r * lda + c] : 0.f;
+    X[r][c] = 0.f;
   }
   __syncthreads();
-  float a[NB];
-#pragma unroll
-  for (int c = 0; c < NB; ++c) a[c] = Ls[i][c];
   bool bad = false;
+  // 1. A00 = L00 L00^T
+  if (warp == 0) {
+    float a[32];
 #pragma unroll
-  for (int j = 0; j < NB; ++j) {
-    col[j & 1][i] = a[j];  // rows >= j publish their (fully updated) entry of column j; row j's is the pivot
-    __syncthreads();
-    const float dj = col[j & 1][j];
-    if (!(dj > 0.f) || !(dj < CUDART_INF_F)) bad = true;
-    const float f = a[j] / dj;  // l_ij / l_jj
-    if (i >= j) a[j] = (i == j) ? sqrtf(dj) : a[j] / sqrtf(dj);
+    for (int c = 0; c < 32; ++c) a[c] = S[lane][c];
+    const float dg = chol32_warp(a, lane, bad);
 #pragma unroll
-    for (int c4 = (j + 1) & ~3; c4 < NB; c4 += 4) {
-      const float4 cv = *reinterpret_cast<const float4*>(&col[j & 1][c4]);
-      if (c4 + 0 > j) a[c4 + 0] = fmaf(-f, cv.x, a[c4 + 0]);
-      if (c4 + 1 > j) a[c4 + 1] = fmaf(-f, cv.y, a[c4 + 1]);
-      if (c4 + 2 > j) a[c4 + 2] = fmaf(-f, cv.z, a[c4 + 2]);
-      if (c4 + 3 > j) a[c4 + 3] = fmaf(-f, cv.w, a[c4 + 3]);
+    for (int c = 0; c < 32; ++c) if (c <= lane) S[lane][c] = a[c];
+    rdiag[lane] = 1.f / dg;
+  }
+  __syncthreads();
+  // 2. T00 (warp 1) and L10 = A10 L00^-T (warp 2), independent
+  if (warp == 1) {
+    float x[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) x[c] = (c == lane) ? 1.f : 0.f;
+    trsm32_warp(x, &S[0][0], rdiag);
+#pragma unroll
+    for (int r = 0; r < 32; ++r) X[r][lane] = x[r];  // x[r] = T00[r][lane], zero for r < lane
+  } else if (warp == 2) {
+    float b[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) b[c] = S[32 + lane][c];
+    trsm32_warp(b, &S[0][0], rdiag);
+#pragma unroll
+    for (int c = 0; c < 32; ++c) S[32 + lane][c] = b[c];
+  }
+  __syncthreads();
+  // 3. A11 -= L10 L10^T : warp w takes columns 4w .. 4w+3, lane = row
+  {
+    float l[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) l[k] = S[32 + lane][k];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int c = warp * 4 + q;
+      float acc = 0.f;
+#pragma unroll
+      for (int k = 0; k < 32; ++k) acc = fmaf(l[k], S[32 + c][k], acc);
+      if (c <= lane) S[32 + lane][32 + c] -= acc;
     }
   }
-  if (bad && i == 0) atomicOr(status, 1);
   __syncthreads();
+  // 4. A11 = L11 L11^T
+  if (warp == 0) {
+    float a[32];
 #pragma unroll
-  for (int c = 0; c < NB; ++c) Ls[i][c] = (c <= i) ? a[c] : 0.f;
-  __syncthreads();
-  // X = L^-1, column i: x_r = -(sum_{j<r} l_rj x_j) / l_rr for r > i, x_i = 1 / l_ii, x_r = 0 for r < i
-  float x[NB];
+    for (int c = 0; c < 32; ++c) a[c] = S[32 + lane][32 + c];
+    const float dg = chol32_warp(a, lane, bad);
 #pragma unroll
-  for (int r = 0; r < NB; ++r) {
-    float accv = 0.f;
-#pragma unroll
-    for (int j4 = 0; j4 < r; j4 += 4) {
-      const float4 lv = *reinterpret_cast<const float4*>(&Ls[r][j4]);
-      if (j4 + 0 < r) accv = fmaf(lv.x, x[j4 + 0], accv);
-      if (j4 + 1 < r) accv = fmaf(lv.y, x[j4 + 1], accv);
-      if (j4 + 2 < r) accv = fmaf(lv.z, x[j4 + 2], accv);
-      if (j4 + 3 < r) accv = fmaf(lv.w, x[j4 + 3], accv);
-    }
-    const float inv = 1.f / Ls[r][r];
-    x[r] = (r < i) ? 0.f : ((r == i) ? inv : -accv * inv);
+    for (int c = 0; c < 32; ++c) if (c <= lane) S[32 + lane][32 + c] = a[c];
+    rdiag[32 + lane] = 1.f / dg;
+    if (bad && lane == 0) atomicOr(status, 1);
   }
+  __syncthreads();
+  // 5. T11 (warp 1) and W = L10 T00 (warps 4-7: 8 columns each)
+  if (warp == 1) {
+    float x[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) x[c] = (c == lane) ? 1.f : 0.f;
+    trsm32_warp(x, &S[32][32], rdiag + 32);
+#pragma unroll
+    for (int r = 0; r < 32; ++r) X[32 + r][32 + lane] = x[r];
+  } else if (warp >= 4) {
+    float l[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) l[k] = S[32 + lane][k];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int c = (warp - 4) * 8 + q;
+      float acc = 0.f;
+#pragma unroll
+      for (int k = 0; k < 32; ++k) acc = fmaf(l[k], X[k][c], acc);  // T00[k][c] = 0 for k < c
+      W[lane][c] = acc;
+    }
+  }
+  __syncthreads();
+  // 6. T10 = -T11 W
+  {
+    float t[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) t[k] = X[32 + lane][32 + k];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int c = warp * 4 + q;
+      float acc = 0.f;
+#pragma unroll
+      for (int k = 0; k < 32; ++k) acc = fmaf(t[k], W[k][c], acc);
+      X[32 + lane][c] = -acc;
+    }
+  }
+  __syncthreads();
   float* dinv = Dinv + (size_t)kb * NB * NB;
-#pragma unroll
-  for (int r = 0; r < NB; ++r) dinv[r * NB + i] = x[r];
-  for (int e = i; e < NB * NB; e += NB) {
+  for (int e = tid; e < NB * NB; e += 256) {
     const int r = e >> 6, c = e & 63;
-    if (c <= r) blk[(size_t)r * lda + c] = Ls[r][c];
+    if (c <= r) blk[(size_t)r * lda + c] = S[r][c];
+    dinv[e] = X[r][c];
   }
-  if (i < 32) {
-    float l = logf(Ls[i][i]) + logf(Ls[i + 32][i + 32]);
+  if (tid < 32) {
+    float l = logf(S[lane][lane]) + logf(S[lane + 32][lane + 32]);
     l = warp_sum(l);
-    if (i == 0) logdet_part[kb] = l;
+    if (tid == 0) logdet_part[kb] = l;
   }
 }
 
 int32_t cholesky_inplace(cudaStream_t s, float* A, int np, int lda, float* Dinv, float* logdet_part, int* status) {
   const int nb = np / NB;
   for (int k = 0; k < nb; ++k) {
-    potrf_diag_kernel<<<1, NB, 0, s>>>(A, lda, k, Dinv, logdet_part, status);
+    potrf_diag_kernel<<<1, 256, 0, s>>>(A, lda, k, Dinv, logdet_part, status);
     BX_LAUNCH_CHECK();
     const int rem = nb - k - 1;
     if (rem == 0) break;

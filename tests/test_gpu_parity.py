@@ -492,6 +492,45 @@ def test_tcgen05_engine_matches_simt_engine_and_oracle(n, d, M, acq):
         assert it == 5 + oopt.jnp_argmax(vv.cpu().numpy()) and np.float32(vt) == vv.cpu().numpy()[it - 5]
 
 
+@pytest.mark.parametrize("space,n,acq", [("mixed10", 2048, "PI"), ("mixed10", 130, "EI"), ("real6", 3, "UCB")])
+def test_production_engine_mixed_domain_ragged_shards(space, n, acq):
+    """AUTO (= fp16 CTA-pair tcgen05 engine) on BASELINE config 4's mixed Real/Integer domain: ragged candidate counts
+    (1, tile - 1, tile + 1, odd tile counts), arbitrary shard boundaries (bit-identical values whatever the split),
+    Integer coordinates exact, arg-max key = first maximum of the values."""
+    dom, odomn = both_spaces(space)
+    d = len(dom)
+    ospace = odom.ParamSpace(odomn)
+    Xd = ospace.to_array(ospace.sample_params(prng.key(3), (n,)))
+    Y = (-np.sum((Xd - Xd.mean(0)) ** 2, axis=1) / d).astype(np.float32)
+    raw = np.concatenate([[-5.0], [0.2], np.full(d, 0.4 if space == "real6" else 2.0)]).astype(np.float32)
+    key, dims = prng.key(9), engine.dims_array(dom)
+    post = engine.Posterior(Xd, Y, raw, want_tc=True).build()
+    param = bayex.acq.DEFAULT_PARAM[acq]
+    ystar = bayex.acq.ystar_for(acq, Y, np.ones(n))
+    M = 3 * 256 + 129
+    full, bfull = post.score_generated(key, dims, 0, M, acq, param, ystar)  # engine = AUTO
+    full = full.cpu().numpy()
+    ref, _ = post.score_generated(key, dims, 0, M, acq, param, ystar, engine=_lib.ENGINE_SIMT)
+    ref = ref.cpu().numpy().astype(np.float64)
+    assert np.all(np.isfinite(full))
+    scale = np.maximum(np.abs(ref), np.abs(ref).mean())
+    assert np.all(np.abs(full - ref) <= 5e-4 * scale + 1e-7), np.abs(full - ref).max()
+    v, i = _lib.unpack(engine.to_unsigned(int(bfull.item())))
+    assert i == oopt.jnp_argmax(full) and np.float32(v) == full[i]
+    for cuts in ([1], [127, 128, 129], [255, 257, 600], [M - 1]):
+        edges = [0] + cuts + [M]
+        parts, keys = [], []
+        for a, b in zip(edges[:-1], edges[1:]):
+            pv, pb = post.score_generated(key, dims, a, b - a, acq, param, ystar)
+            parts.append(pv.cpu().numpy())
+            keys.append(engine.to_unsigned(int(pb.item())))
+        assert np.array_equal(np.concatenate(parts), full), f"values depend on the shard boundaries {cuts}"
+        assert max(keys) == engine.to_unsigned(int(bfull.item()))
+    # candidates behind the values: Integer columns integral and in range, bit-equal to the oracle's draws
+    cand = engine.threefry_fill(key, dims, d, 0, M).cpu().numpy()
+    assert np.array_equal(cand, ospace.to_array(ospace.sample_params(key, (M,))))
+
+
 # ---- BASELINE.json configurations at full size: size-independent properties + oracle spot checks ------------------
 def _config_problem(d, n, seed=0):
     space = odom.ParamSpace({f"x{i}": odom.Real(0.0, 1.0) for i in range(d)})
