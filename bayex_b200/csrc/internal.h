@@ -26,6 +26,10 @@ struct GemmArgs {
   int lower_only;  // compute only tiles with i0 >= j0
   // tree-batched mode for the recursive triangular inverse (tree_nb > 0): blockIdx.z = node of `tree_level`
   int tree_nb, tree_level, tree_pass;
+  // deterministic split-K (64x64 kernel only, ksplit > 0, beta = 0): blockIdx.z = K chunk [z ksplit, (z+1) ksplit); chunk z
+  // writes its partial product to C + z * csplit (zeros where its K range is empty); the caller sums the chunks in order
+  int ksplit;
+  size_t csplit;
 };
 
 // C = alpha * op(A) * op(B) + beta * C on the SIMT fp32 pipes (row-major, 64x64x16 tiles).

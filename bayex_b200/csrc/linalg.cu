@@ -66,6 +66,11 @@ __global__ void __launch_bounds__(256) gemm64_kernel(GemmArgs g) {
   else if (kmode == KM_TN_BOTH) k_lo = max(i0, j0);
   else if (kmode == KM_TN_A) k_lo = i0;
 
+  if (g.ksplit > 0) {
+    k_lo = max(k_lo, (int)blockIdx.z * g.ksplit);
+    k_hi = min(k_hi, ((int)blockIdx.z + 1) * g.ksplit);
+    C += (size_t)blockIdx.z * g.csplit;
+  }
   const int tid = threadIdx.x, rg = tid & 15, cg = tid >> 4;
   float acc[4][4];
 #pragma unroll
@@ -276,7 +281,7 @@ int32_t gemm(cudaStream_t s, bool ta, bool tb, const GemmArgs& g, int grid_z) {
   if (g.M <= 0 || g.N <= 0) return 0;
   // large, squarish products go to the 128x128 kernel; skinny ones (panels of 64, the refinement's 64 starts) stay on 64x64
   static const bool force64 = getenv("BX_GEMM64") != nullptr;
-  if (g.M >= HT && g.N >= HT && !force64) {
+  if (g.M >= HT && g.N >= HT && !force64 && g.ksplit == 0) {
     dim3 grid((g.N + HT - 1) / HT, (g.M + HT - 1) / HT, grid_z);
     if (!ta && !tb) gemm128_kernel<false, false><<<grid, 256, 0, s>>>(g);
     else if (ta && !tb) gemm128_kernel<true, false><<<grid, 256, 0, s>>>(g);
