@@ -180,6 +180,12 @@ class Posterior:
         with on_stream(self.stream, self.dev):
             return self.raw.cpu().numpy()
 
+    def set_raw(self, raw):
+        """Replace the raw hypers in place (same observations, new starting point - restarts of the fit)."""
+        with on_stream(self.stream, self.dev):
+            self.raw.copy_(torch.from_numpy(np.ascontiguousarray(raw, dtype=np.float32)))
+        self.factor = None
+
     def _need_factor(self):
         if self.factor is None:
             self.build()

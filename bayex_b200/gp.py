@@ -97,3 +97,13 @@ def posterior_fit(y, x, mask, params, lr: float = 1e-3, trainsteps: int = 100):
 def params_from_raw(raw, d):
     raw = np.asarray(raw, dtype=np.float32)
     return GPParams(raw[0:1].reshape(1, 1).copy(), raw[1:2].reshape(1, 1).copy(), raw[2:2 + d].reshape(1, d).copy())
+
+
+def posterior_fit_restarts(y, x, mask, raws, lr=1e-3, trainsteps=100):
+    """``posterior_fit`` (gp.py:90-110) from several starting points - BASELINE config 5.  ``raws`` is (R, d + 2) raw
+    hypers ``[noise, amplitude, lengthscale...]``; restarts are sharded over the torch.distributed ranks.  Returns the
+    GPParams of the restart with the smallest ``neg_log_likelihood`` plus ``(best index, table)``."""
+    from . import fit_sweep
+    xv, yv = engine.compact(x, y, mask)
+    best, idx, table = fit_sweep.fit_restarts(xv, yv, raws, lr=lr, trainsteps=trainsteps)
+    return best, idx, table

@@ -74,3 +74,45 @@ def test_sharded_argmax_and_topk_match_single_process():
         v, i = _lib.unpack(packed)
         assert i == want_idx and np.float32(v) == vals[want_idx]
         assert top == want_top
+
+
+# ---- restart sweep (BASELINE config 5): round-robin sharding + all-gather of (loss, raw hypers) rows + arg-min ------
+def _sweep_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from bayex_b200 import fit_sweep
+    R, width = 7, 5
+    losses = np.array([3.0, np.nan, 1.5, 1.5, np.inf, 2.0, 9.0], np.float32)  # tie at 2/3 -> first wins; NaN/inf never
+    rows = {i: np.concatenate([[losses[i]], np.full(width - 1, 10.0 * i, np.float32)]) for i in fit_sweep.shard_restarts(R, rank, world)}
+    table = fit_sweep.gather_restart_rows(rows, R, width, dist)
+    q.put((rank, table.tolist(), fit_sweep.argmin_loss(table[:, 0])))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_restart_sweep_gather_and_argmin_world2():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_sweep_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=240) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    sys.path.insert(0, ROOT)
+    from bayex_b200 import fit_sweep
+    assert fit_sweep.shard_restarts(7, 0, 2) == [0, 2, 4, 6] and fit_sweep.shard_restarts(7, 1, 2) == [1, 3, 5]
+    assert sorted(fit_sweep.shard_restarts(32, r, 8)[0] for r in range(8)) == list(range(8))
+    assert all(len(fit_sweep.shard_restarts(32, r, 8)) == 4 for r in range(8))
+    tables = [np.array(t, np.float32) for _, t, _ in got]
+    assert np.array_equal(tables[0], tables[1], equal_nan=True)          # every rank ends with the same table
+    assert np.array_equal(tables[0][:, 1], 10.0 * np.arange(7))           # each row came from its owner
+    assert [b for _, _, b in got] == [2, 2]
+    single = fit_sweep.gather_restart_rows({i: tables[0][i] for i in range(7)}, 7, 5, None)
+    assert np.array_equal(single, tables[0], equal_nan=True)
+    import pytest
+    with pytest.raises(FloatingPointError):
+        fit_sweep.argmin_loss(np.array([np.nan, np.inf], np.float32))

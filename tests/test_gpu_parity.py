@@ -613,3 +613,24 @@ def test_config5_nlml_and_fit_step_large_n(n):
         post.fit_hypers(steps=1)
         step = post.raw_host() - raw
         assert np.all(np.sign(step) == -np.sign(ref)) and np.all(np.abs(np.abs(step) - 1e-3) < 2e-5)
+
+
+@pytest.mark.gpu
+def test_config5_restart_sweep_single_rank():
+    """BASELINE config 5 (restart sweep), one rank: every restart equals an independent posterior_fit from the same
+    start; the winner is the arg-min of the fitted losses; the oracle's loss at the winning hypers agrees."""
+    from bayex_b200 import fit_sweep
+    n, d, R = 300, 4, 5
+    X, Y = _config_problem(d, n, seed=5)
+    Y = (Y + 0.01 * np.random.default_rng(0).standard_normal(n)).astype(np.float32)
+    rng = np.random.default_rng(7)
+    raws = np.concatenate([rng.uniform(-8, -2, (R, 1)), rng.uniform(-1, 1, (R, 1 + d))], axis=1).astype(np.float32)
+    best, idx, table = bayex.gp.posterior_fit_restarts(Y, X, np.ones(n, bool), raws, trainsteps=30)
+    assert table.shape == (R, d + 3) and idx == fit_sweep.argmin_loss(table[:, 0])
+    for r in (0, R - 1):
+        P0 = bayex.gp.GPParams(raws[r, 0], raws[r, 1], raws[r, 2:])
+        Pr = bayex.gp.posterior_fit(Y, X, np.ones(n, bool), P0, trainsteps=30)
+        assert np.allclose(np.concatenate([np.ravel(v) for v in Pr]), table[r, 1:], rtol=0, atol=1e-6)
+    want = float(ogp.neg_log_likelihood(ogp.GPParams(*[np.ravel(v) if i == 2 else float(np.ravel(v)[0]) for i, v in enumerate(best)]),
+                                        X, Y, np.ones(n), dtype=np.float64))
+    assert abs(table[idx, 0] - want) <= 2e-4 * max(1.0, abs(want))
