@@ -305,38 +305,63 @@ int32_t gemm(cudaStream_t s, bool ta, bool tb, const GemmArgs& g, int grid_z) {
 // ------------------------------------------------------------------------------------------------------------------
 // This kernel is the serial chain of the blocked Cholesky (np / 64 launches per factorisation), so it is built for
 // latency.  The 64x64 block is handled as 2x2 blocks of 32; a 32x32 factorisation or triangular solve runs inside ONE
-// warp with a matrix row per lane in registers (fully unrolled, shuffles instead of barriers: ~90 clocks per column
-// on the critical path); the 32x32x32 products in between use all eight warps.  Seven block barriers in total.
+// warp with a matrix row per lane in registers (fully unrolled; per column one __syncwarp and broadcast shared-memory
+// reads instead of block barriers); the 32x32x32 products in between use all eight warps.  Seven block barriers.
+// clock64 stamps per phase (B200, 1.965 GHz): load 1.2k | chol32 5.5k | solves + rank-32 update 6k | chol32 5.5k |
+// solves + products 5.8k | store 1.6k = 25.6k clocks = 13 us (the first shared-memory version: 35 us).
 //   A00 = L00 L00^T | T00 = L00^-1, L10 = A10 L00^-T | A11 -= L10 L10^T | A11 = L11 L11^T | T11 = L11^-1,
 //   W = L10 T00 | T10 = -T11 W
 constexpr int LP = NB + 1;
 constexpr unsigned FULLW = 0xffffffffu;
 
-// lane i holds row i of a symmetric positive-definite 32x32 block (upper part zero); on return row i of its Cholesky factor
-__device__ __forceinline__ float chol32_warp(float (&a)[32], int lane, bool& bad) {
+// lane i holds row i of a symmetric positive-definite 32x32 block (upper part zero); on return row i of its Cholesky
+// factor; returns l_ii.  Per column the raw column (pivot included) is published to shared memory once and read back as
+// broadcast LDS.128 - a first version fetched every l_cj with its own warp shuffle (496 dependent-issue SHFLs per
+// factorisation) and measured ~390 clocks per column; the update uses a_ic -= a_ij a_cj / d_j so the loads do not
+// wait for the rsqrt chain.  cs = [2][32] floats of shared memory (double buffer: no barrier between columns beyond
+// the one __syncwarp).
+constexpr int LTP = 36;  // row stride of the transposed factor copies (16-byte aligned rows)
+__device__ __forceinline__ float chol32_warp(float (&a)[32], int lane, float* cs, float* LT, bool& bad) {
   float diag = 1.f;
 #pragma unroll
   for (int j = 0; j < 32; ++j) {
-    const float d = __shfl_sync(FULLW, a[j], j);
+    float* col = cs + (j & 1) * 32;
+    col[lane] = a[j];
+    __syncwarp();
+    float cv[32];
+#pragma unroll
+    for (int c4 = (j + 1) & ~3; c4 < 32; c4 += 4) {
+      const float4 v = *reinterpret_cast<const float4*>(col + c4);
+      cv[c4] = v.x; cv[c4 + 1] = v.y; cv[c4 + 2] = v.z; cv[c4 + 3] = v.w;
+    }
+    const float d = col[j];
     if (!(d > 0.f) || !(d < CUDART_INF_F)) bad = true;
     float rs = rsqrtf(d);
     rs = rs * fmaf(-0.5f * d, rs * rs, 1.5f);  // one Newton step: full fp32 accuracy without sqrt + divide in the chain
+    const float f = a[j] * (rs * rs);          // l_ij / l_jj
     const float lij = (lane == j) ? d * rs : a[j] * rs;
     a[j] = lij;
+    LT[j * LTP + lane] = lij;  // column j of L as a contiguous row: the triangular solves read it as broadcast LDS.128
     if (lane == j) diag = lij;
 #pragma unroll
-    for (int c = j + 1; c < 32; ++c) a[c] = fmaf(-lij, __shfl_sync(FULLW, lij, c), a[c]);
+    for (int c = j + 1; c < 32; ++c) a[c] = fmaf(-f, cv[c], a[c]);
   }
   return diag;  // l_ii of this lane's row
 }
-// lane r holds row r of B; solves X L^T = B in place (L lower 32x32 in shared memory, row stride LP, rdiag = 1 / diag).
-// With B = identity this gives row r of L^-T = column r of L^-1.
-__device__ __forceinline__ void trsm32_warp(float (&b)[32], const float* L, const float* rdiag) {
+// lane r holds row r of B; solves X L^T = B in place.  LT = L^T (row j = column j of L, stride LTP) in shared memory,
+// rdiag = 1 / diag(L).  With B = identity this gives row r of L^-T = column r of L^-1.
+__device__ __forceinline__ void trsm32_warp(float (&b)[32], const float* LT, const float* rdiag) {
 #pragma unroll
   for (int j = 0; j < 32; ++j) {
     b[j] *= rdiag[j];
 #pragma unroll
-    for (int c = j + 1; c < 32; ++c) b[c] = fmaf(-b[j], L[c * LP + j], b[c]);
+    for (int c4 = (j + 1) & ~3; c4 < 32; c4 += 4) {
+      const float4 v = *reinterpret_cast<const float4*>(LT + j * LTP + c4);
+      if (c4 + 0 > j) b[c4 + 0] = fmaf(-b[j], v.x, b[c4 + 0]);
+      if (c4 + 1 > j) b[c4 + 1] = fmaf(-b[j], v.y, b[c4 + 1]);
+      if (c4 + 2 > j) b[c4 + 2] = fmaf(-b[j], v.z, b[c4 + 2]);
+      if (c4 + 3 > j) b[c4 + 3] = fmaf(-b[j], v.w, b[c4 + 3]);
+    }
   }
 }
 
@@ -346,13 +371,25 @@ __global__ void __launch_bounds__(256) potrf_diag_kernel(float* A, int lda, int 
   __shared__ float X[NB][LP];   // L^-1
   __shared__ float W[32][33];   // L10 T00
   __shared__ float rdiag[NB];
+  __shared__ __align__(16) float colbuf[2][32];
+  __shared__ __align__(16) float LT0[32 * LTP], LT1[32 * LTP];  // L00^T, L11^T
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(FULLW, tid >> 5, 0);  // provably warp-uniform: the role branches below stay convergent
   float* blk = A + (size_t)kb * NB * lda + (size_t)kb * NB;
-  for (int e = tid; e < NB * NB; e += 256) {
-    const int r = e >> 6, c = e & 63;
-    S[r][c] = (c <= r) ? blk[(size_t)r * lda + c] : 0.f;
-    X[r][c] = 0.f;
+  {
+    float4 v[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {  // 1024 float4, all four loads of a thread in flight together
+      const int e4 = tid + q * 256, r = e4 >> 4, c = (e4 & 15) * 4;
+      v[q] = *reinterpret_cast<const float4*>(blk + (size_t)r * lda + c);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int e4 = tid + q * 256, r = e4 >> 4, c = (e4 & 15) * 4;
+      S[r][c] = (c <= r) ? v[q].x : 0.f; S[r][c + 1] = (c + 1 <= r) ? v[q].y : 0.f;
+      S[r][c + 2] = (c + 2 <= r) ? v[q].z : 0.f; S[r][c + 3] = (c + 3 <= r) ? v[q].w : 0.f;
+      X[r][c] = 0.f; X[r][c + 1] = 0.f; X[r][c + 2] = 0.f; X[r][c + 3] = 0.f;
+    }
   }
   __syncthreads();
   bool bad = false;
@@ -361,7 +398,7 @@ __global__ void __launch_bounds__(256) potrf_diag_kernel(float* A, int lda, int 
     float a[32];
 #pragma unroll
     for (int c = 0; c < 32; ++c) a[c] = S[lane][c];
-    const float dg = chol32_warp(a, lane, bad);
+    const float dg = chol32_warp(a, lane, &colbuf[0][0], LT0, bad);
 #pragma unroll
     for (int c = 0; c < 32; ++c) if (c <= lane) S[lane][c] = a[c];
     rdiag[lane] = 1.f / dg;
@@ -372,14 +409,14 @@ __global__ void __launch_bounds__(256) potrf_diag_kernel(float* A, int lda, int 
     float x[32];
 #pragma unroll
     for (int c = 0; c < 32; ++c) x[c] = (c == lane) ? 1.f : 0.f;
-    trsm32_warp(x, &S[0][0], rdiag);
+    trsm32_warp(x, LT0, rdiag);
 #pragma unroll
     for (int r = 0; r < 32; ++r) X[r][lane] = x[r];  // x[r] = T00[r][lane], zero for r < lane
   } else if (warp == 2) {
     float b[32];
 #pragma unroll
     for (int c = 0; c < 32; ++c) b[c] = S[32 + lane][c];
-    trsm32_warp(b, &S[0][0], rdiag);
+    trsm32_warp(b, LT0, rdiag);
 #pragma unroll
     for (int c = 0; c < 32; ++c) S[32 + lane][c] = b[c];
   }
@@ -404,7 +441,7 @@ __global__ void __launch_bounds__(256) potrf_diag_kernel(float* A, int lda, int 
     float a[32];
 #pragma unroll
     for (int c = 0; c < 32; ++c) a[c] = S[32 + lane][32 + c];
-    const float dg = chol32_warp(a, lane, bad);
+    const float dg = chol32_warp(a, lane, &colbuf[0][0], LT1, bad);
 #pragma unroll
     for (int c = 0; c < 32; ++c) if (c <= lane) S[32 + lane][32 + c] = a[c];
     rdiag[32 + lane] = 1.f / dg;
@@ -416,7 +453,7 @@ __global__ void __launch_bounds__(256) potrf_diag_kernel(float* A, int lda, int 
     float x[32];
 #pragma unroll
     for (int c = 0; c < 32; ++c) x[c] = (c == lane) ? 1.f : 0.f;
-    trsm32_warp(x, &S[32][32], rdiag + 32);
+    trsm32_warp(x, LT1, rdiag + 32);
 #pragma unroll
     for (int r = 0; r < 32; ++r) X[32 + r][32 + lane] = x[r];
   } else if (warp >= 4) {

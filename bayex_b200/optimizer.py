@@ -36,6 +36,38 @@ class OptimizerState(NamedTuple):
     gp_params: GPParams
 
 
+_ACQ_BY_FUNC = {"expected_improvement": "EI", "probability_improvement": "PI",
+                "upper_confidence_bounds": "UCB", "lower_confidence_bounds": "LCB"}
+
+
+def _optimize_suggestion(params, fun, max_iter: int = 10):
+    """optimizer.py:39-73: improve one suggestion ``params`` (d,) by ascending the acquisition ``fun``; iterates are
+    clipped to +-1e6 (optimizer.py:68) and returned un-transformed (quirk Q11).
+
+    ``fun`` is what the reference passes (optimizer.py:190-194): a ``functools.partial`` of one of the ``bayex.acq``
+    functions with ``xs, ys, mask, gp_params`` (and optionally ``xi`` / ``kappa``) bound.  The optax L-BFGS of the
+    reference (unpinned, mis-signed value_fn: Q12) is replaced by the device refinement ``bx_refine`` - a monotone
+    analytic-gradient ascent, 3 evaluations per reference iteration; the returned point never scores below ``params``."""
+    import functools
+    if not isinstance(fun, functools.partial) or getattr(fun.func, "__name__", "") not in _ACQ_BY_FUNC:
+        raise TypeError("fun must be functools.partial(bayex.acq.<acquisition>, xs=..., ys=..., mask=..., gp_params=...)")
+    name = _ACQ_BY_FUNC[fun.func.__name__]
+    kw = dict(fun.keywords)
+    for slot, arg in zip(("xs", "ys", "mask", "gp_params"), fun.args):
+        kw.setdefault(slot, arg)
+    xs, ys, mask = np.asarray(kw["xs"], dtype=np.float32), np.asarray(kw["ys"], dtype=np.float32), np.asarray(kw["mask"])
+    xs = xs[:, None] if xs.ndim == 1 else xs
+    param = float(kw.get("xi", kw.get("kappa", boacq.DEFAULT_PARAM[name])))
+    xv, yv = engine.compact(xs, ys, mask)
+    post = engine.Posterior(xv, yv, engine.raw_vector(kw["gp_params"], xv.shape[1]), want_tc=False)
+    x0 = np.asarray(params, dtype=np.float32).reshape(1, -1)
+    with engine.on_stream(post.stream, post.dev):
+        start = torch.from_numpy(x0).to(post.dev)
+    out, _ = post.refine(start, 3 * int(max_iter), name, param, boacq.ystar_for(name, ys, mask))
+    with engine.on_stream(post.stream, post.dev):
+        return out.cpu().numpy()[0]
+
+
 class Optimizer:
     """Bayesian optimiser: GP surrogate + EI / PI / UCB / LCB acquisition (optimizer.py:76-280)."""
 

@@ -634,3 +634,24 @@ def test_config5_restart_sweep_single_rank():
     want = float(ogp.neg_log_likelihood(ogp.GPParams(*[np.ravel(v) if i == 2 else float(np.ravel(v)[0]) for i, v in enumerate(best)]),
                                         X, Y, np.ones(n), dtype=np.float64))
     assert abs(table[idx, 0] - want) <= 2e-4 * max(1.0, abs(want))
+
+
+@pytest.mark.gpu
+def test_optimize_suggestion_reference_call_pattern():
+    """SURVEY row a18 (optimizer.py:39-73,190-199): the reference calls _optimize_suggestion(x, partial(acq, xs=, ys=, mask=,
+    gp_params=)); the replacement keeps that call and the value contract (never worse than the start, clipped)."""
+    import functools
+    from bayex_b200.optimizer import _optimize_suggestion
+    n, d = 120, 3
+    X, Y, raw, P = make_problem(n, d, seed=21)
+    gp_params = bayex.gp.GPParams(raw[0], raw[1], raw[2:])
+    mask = np.ones(n, bool)
+    for f, kw in ((bayex.acq.expected_improvement, {}), (bayex.acq.lower_confidence_bounds, {"kappa": 1.0})):
+        fun = functools.partial(f, xs=X, ys=Y, mask=mask, gp_params=gp_params, **kw)
+        x0 = np.array([0.3, 0.6, 0.1], np.float32)
+        x1 = _optimize_suggestion(x0, fun, max_iter=10)
+        assert x1.shape == (d,) and x1.dtype == np.float32 and np.all(np.abs(x1) <= 1e6)
+        v0, v1 = fun(x0[None])[0], fun(x1[None])[0]
+        assert v1 >= v0 - 1e-6 * max(1.0, abs(v0)), (v0, v1)
+    with pytest.raises(TypeError):
+        _optimize_suggestion(np.zeros(d, np.float32), lambda x: x)
