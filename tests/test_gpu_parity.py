@@ -655,3 +655,78 @@ def test_optimize_suggestion_reference_call_pattern():
         assert v1 >= v0 - 1e-6 * max(1.0, abs(v0)), (v0, v1)
     with pytest.raises(TypeError):
         _optimize_suggestion(np.zeros(d, np.float32), lambda x: x)
+
+
+# ---- edge cases of the path --------------------------------------------------------------------------------------
+@pytest.mark.gpu
+def test_single_observation_and_fewer_candidates_than_starts():
+    """n = 1 (padded to 10, optimizer.py:123), size < 50 (the top-k takes what exists), size = 1."""
+    dom = {"x": bayex.domain.Real(-1.0, 3.0), "k": bayex.domain.Integer(0, 4)}
+    opt = bayex.Optimizer(dom, acq="EI", maximize=True)
+    st = opt.init([0.7], {"x": [0.25], "k": [2]})
+    assert st.ys.shape == (10,) and int(st.mask.sum()) == 1 and st.params["k"].dtype == np.int32
+    for size in (1, 7, 49, 50, 51):
+        new, info = opt.sample(bayex.random.key(size), st, size=size, details=True)
+        assert info["acq_vals"].shape == (size,) and np.all(np.isfinite(info["acq_vals"]))
+        assert len(info["top_idxs"]) == min(50, size) and len(set(info["top_idxs"].tolist())) == min(50, size)
+        assert new["x"].shape == (1,) and -1.0 <= new["x"][0] <= 3.0 and new["k"][0] in (0.0, 1.0, 2.0, 3.0, 4.0)
+    st2 = opt.fit(st, 1.5, new)
+    assert int(st2.mask.sum()) == 2 and st2.best_score == 1.5 and st2.params["k"].dtype == np.float32  # Q14 promotion
+
+
+@pytest.mark.gpu
+def test_more_than_32_dimensions_take_the_simt_engine():
+    """d > 32 is outside the tcgen05 engines' template range: AUTO must fall back to the SIMT engine (same oracle bar),
+    an explicit tcgen05 request must fail loudly (BX_E_UNSUPPORTED), never silently change engine."""
+    n, d, M = 150, 40, 3000
+    X, Y, raw, P = make_problem(n, d, seed=4)
+    dom = {f"x{i}": bayex.domain.Real(0.0, 1.0) for i in range(d)}
+    dims = engine.dims_array(dom)
+    post = engine.Posterior(X, Y, raw, want_tc=True).build()
+    key = prng.key(2)
+    v, b = post.score_generated(key, dims, 0, M, "UCB", 0.01, 0.0)  # AUTO
+    cand = engine.threefry_fill(key, dims, d, 0, M).cpu().numpy()
+    f64 = ogp.Factor(P, X, Y, np.ones(n), np.float64)
+    mu64, sd64 = f64.predict(cand.astype(np.float64))
+    want = mu64 + 0.01 * sd64
+    got = v.cpu().numpy().astype(np.float64)
+    assert np.all(np.abs(got - want) <= 2e-4 * np.maximum(np.abs(want), np.abs(want).mean()) + 1e-6)
+    for eng in (_lib.ENGINE_TCGEN05, _lib.ENGINE_TCGEN05_F16, _lib.ENGINE_TCGEN05_F16_PAIR):
+        with pytest.raises(RuntimeError, match="d <= 32"):
+            post.score_generated(key, dims, 0, M, "UCB", 0.01, 0.0, engine=eng)
+
+
+@pytest.mark.gpu
+def test_failed_cholesky_gives_nan_like_the_reference():
+    """A non-finite observation makes K non-finite: the reference's cholesky returns NaN and everything downstream is
+    NaN, silently (SURVEY 8(b) error conventions).  Same here, plus the status flag; no exception, no hang."""
+    n, d = 200, 2
+    X, Y, raw, P = make_problem(n, d, seed=8)
+    X = X.copy()
+    X[17, 1] = np.nan
+    post = engine.Posterior(X, Y, raw, want_tc=True).build()
+    assert post.hyp()[7] != 0.0, "the bad pivot must be reported in the status slot"
+    out = post.score_points(np.array([[0.5, 0.5]], np.float32), acq="EI", param=0.01, ystar=1.0, want=("mu", "sigma", "acq"))
+    assert np.isnan(out["acq"].cpu().numpy()).all()
+    nl, loss, gl, gn = post.nlml_grad()
+    assert np.isnan(nl)
+    dims = engine.dims_array({"a": bayex.domain.Real(0.0, 1.0), "b": bayex.domain.Real(0.0, 1.0)})
+    v, b = post.score_generated(prng.key(0), dims, 0, 300, "UCB", 0.01, 0.0)  # production engine: NaN in, NaN out
+    assert np.isnan(v.cpu().numpy()).all()
+
+
+@pytest.mark.gpu
+def test_state_file_roundtrip_reproduces_the_proposal(tmp_path):
+    """save_state / load_state: a reloaded state rebuilds the same factor and proposes the same point."""
+    dom = {"a": bayex.domain.Real(0.0, 2.0), "k": bayex.domain.Integer(-5, 5)}
+    rng = np.random.default_rng(3)
+    P0 = {"a": rng.uniform(0, 2, 25).astype(np.float32), "k": rng.integers(-5, 6, 25)}
+    Y0 = ((P0["a"] - 1.2) ** 2 + 0.1 * P0["k"] ** 2).astype(np.float32)
+    opt = bayex.Optimizer(dom, acq="LCB")
+    st = opt.init(Y0, P0)
+    key = bayex.random.key(5)
+    want = opt.sample(key, st, size=4096)
+    bayex.save_state(tmp_path / "s.npz", st)
+    fresh = bayex.Optimizer(dom, acq="LCB")                        # cold cache: the factor is rebuilt from the file
+    got = fresh.sample(key, bayex.load_state(tmp_path / "s.npz"), size=4096)
+    assert all(np.array_equal(got[k], want[k]) for k in dom)
