@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libbayex_b200.so")
+LIB_PATH = os.environ.get("BAYEX_B200_LIB") or os.path.join(HERE, "libbayex_b200.so")  # override: tuning variants
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(
@@ -20,6 +20,7 @@ lib = C.CDLL(LIB_PATH)
 
 ACQ_IDS = {"EI": 0, "PI": 1, "UCB": 2, "LCB": 3}
 ENGINE_AUTO, ENGINE_SIMT, ENGINE_TCGEN05, ENGINE_TCGEN05_PAIR, ENGINE_TCGEN05_F16, ENGINE_TCGEN05_F16_PAIR = 0, 1, 2, 3, 4, 5
+ENGINE_TCGEN05_F16_SHARED = 6
 MAX_D, MAX_K, TILE = 64, 1024, 128
 
 

@@ -35,7 +35,16 @@ constexpr int HN = BN / 2;                 // rows of every T tile held by one C
 // Ring depths.  A stage of K* is refilled only after the MMAs that read it have completed, so with P = producer time and
 // Tm = MMA time per K-block (both ~3000 clk) a 2-deep ring runs at (P + Tm + latencies) / 2 per K-block; 3 stages reach
 // max(P, Tm).  T tiles: 3 stages = 1.5 K-blocks of TMA look-ahead.
-constexpr int NACC = 2, SA = 3, SB = 3, NU = 3;
+#ifndef BX_P_SA
+#define BX_P_SA 3
+#endif
+#ifndef BX_P_SB
+#define BX_P_SB 3
+#endif
+#ifndef BX_P_NU
+#define BX_P_NU 3
+#endif
+constexpr int NACC = 2, SA = BX_P_SA, SB = BX_P_SB, NU = BX_P_NU;
 constexpr int KPR = BN / BKH;              // K-blocks per row block
 constexpr int ATILE = TM * BKH * 2;        // 16 KiB: 128 candidates x 64 halves
 constexpr int BTILE = HN * BKH * 2;        // 16 KiB: 128 T rows x 64 halves

@@ -174,7 +174,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--candidates", type=int, default=None)
-    ap.add_argument("--engine", default="auto", choices=["auto", "simt", "tcgen05", "tcgen05_pair", "tcgen05_f16", "tcgen05_f16_pair"])
+    ap.add_argument("--engine", default="auto", choices=["auto", "simt", "tcgen05", "tcgen05_pair", "tcgen05_f16", "tcgen05_f16_pair", "tcgen05_f16_shared"])
     ap.add_argument("--ref-sample", type=int, default=32768)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -202,7 +202,7 @@ def main():
     opt = bayex.Optimizer(dom, acq=acq, maximize=False)
     opt.engine = {"auto": _lib.ENGINE_AUTO, "simt": _lib.ENGINE_SIMT, "tcgen05": _lib.ENGINE_TCGEN05,
                   "tcgen05_pair": _lib.ENGINE_TCGEN05_PAIR, "tcgen05_f16": _lib.ENGINE_TCGEN05_F16,
-                  "tcgen05_f16_pair": _lib.ENGINE_TCGEN05_F16_PAIR}[args.engine]
+                  "tcgen05_f16_pair": _lib.ENGINE_TCGEN05_F16_PAIR, "tcgen05_f16_shared": _lib.ENGINE_TCGEN05_F16_SHARED}[args.engine]
     t0 = time.perf_counter()
     state = opt.init(Y, P)  # 100-step hyper-parameter fit + factor (untimed set-up)
     torch.cuda.synchronize()
@@ -284,7 +284,7 @@ def main():
         fl = flops_per_candidate(n, d) * m_count
         achieved = fl / (kern_ms_avg * 1e-3) / 1e12
         n_starts = opt.N_STARTS
-        f16 = args.engine in ("auto", "tcgen05_f16", "tcgen05_f16_pair")
+        f16 = args.engine in ("auto", "tcgen05_f16", "tcgen05_f16_pair", "tcgen05_f16_shared")
         if f16 and peaks.get("bf16_tflops_sustained"):
             # kind::f16 MMAs; the launch is ~1 s long under the 1000 W cap, so the sustained cuBLAS figure is the denominator
             peak, peak_src = float(peaks["bf16_tflops_sustained"]), (

@@ -50,7 +50,8 @@ enum {
   BX_ENGINE_TCGEN05 = 2,      /* 3xTF32, one CTA per tile */
   BX_ENGINE_TCGEN05_PAIR = 3, /* 3xTF32, cta_group::2 */
   BX_ENGINE_TCGEN05_F16 = 4,  /* fp16 head/tail split (same 22-bit operands, half the tensor work) */
-  BX_ENGINE_TCGEN05_F16_PAIR = 5 /* fp16 head/tail split, cta_group::2, register-tiled K* producers (AUTO picks this) */
+  BX_ENGINE_TCGEN05_F16_PAIR = 5, /* fp16 head/tail split, cta_group::2, register-tiled K* producers (AUTO picks this) */
+  BX_ENGINE_TCGEN05_F16_SHARED = 6 /* fp16 head/tail split, K* generation shared by a 2-CTA cluster through DSMEM */
 };
 
 /* One dimension of the parameter space - mirrors bayex.domain.Real / Integer (domain.py:22-131). */

@@ -465,8 +465,9 @@ def test_tcgen05_engine_matches_simt_engine_and_oracle(n, d, M, acq):
     v_p, b_p = post.score_generated(key, dims, 5, M, acq, param, ystar, engine=_lib.ENGINE_TCGEN05_PAIR)
     v_h, b_h = post.score_generated(key, dims, 5, M, acq, param, ystar, engine=_lib.ENGINE_TCGEN05_F16)
     v_q, b_q = post.score_generated(key, dims, 5, M, acq, param, ystar, engine=_lib.ENGINE_TCGEN05_F16_PAIR)
-    s, t, pr, hf, hp = (v.cpu().numpy().astype(np.float64) for v in (v_s, v_t, v_p, v_h, v_q))
-    assert np.all(np.isfinite(t)) and np.all(np.isfinite(pr)) and np.all(np.isfinite(hf)) and np.all(np.isfinite(hp))
+    v_r, b_r = post.score_generated(key, dims, 5, M, acq, param, ystar, engine=_lib.ENGINE_TCGEN05_F16_SHARED)
+    s, t, pr, hf, hp, hs = (v.cpu().numpy().astype(np.float64) for v in (v_s, v_t, v_p, v_h, v_q, v_r))
+    assert np.all(np.isfinite(t)) and np.all(np.isfinite(pr)) and np.all(np.isfinite(hf)) and np.all(np.isfinite(hp)) and np.all(np.isfinite(hs))
     cand = engine.threefry_fill(key, dims, d, 5, M).cpu().numpy()
     f64, f32 = ogp.Factor(P, X, Y, np.ones(n), np.float64), ogp.Factor(P, X, Y, np.ones(n), np.float32)
     mu64, sd64 = f64.predict(cand.astype(np.float64))
@@ -483,11 +484,11 @@ def test_tcgen05_engine_matches_simt_engine_and_oracle(n, d, M, acq):
             prop = np.maximum(prop, np.abs(oacq.acq_from_moments(acq, mu64 + smu * tmu, np.maximum(sd64 + ssd * tsd, 1e-12),
                                                                  Y.astype(np.float64), np.ones(n)) - a64))
     tol = np.maximum.reduce([RTOL * np.maximum(np.abs(a64), np.abs(a64).mean()), 4 * np.abs(a32 - a64), 2 * prop])
-    for name, got in (("simt", s), ("tcgen05", t), ("tcgen05_pair", pr), ("tcgen05_f16", hf), ("tcgen05_f16_pair", hp)):
+    for name, got in (("simt", s), ("tcgen05", t), ("tcgen05_pair", pr), ("tcgen05_f16", hf), ("tcgen05_f16_pair", hp), ("tcgen05_f16_shared", hs)):
         err = np.abs(got - a64)
         assert np.all(err <= tol), f"{name}: {np.sum(err > tol)}/{M} outside tolerance, worst {err.max():.3e} at {np.argmax(err)}"
     assert np.abs(s - t).max() <= 2 * tol.max() and np.abs(s - pr).max() <= 2 * tol.max()
-    for vv, bb in ((v_t, b_t), (v_p, b_p), (v_h, b_h), (v_q, b_q)):
+    for vv, bb in ((v_t, b_t), (v_p, b_p), (v_h, b_h), (v_q, b_q), (v_r, b_r)):
         vt, it = _lib.unpack(engine.to_unsigned(int(bb.item())))
         assert it == 5 + oopt.jnp_argmax(vv.cpu().numpy()) and np.float32(vt) == vv.cpu().numpy()[it - 5]
 
