@@ -226,10 +226,13 @@ extern "C" int32_t bx_refine(const bx_factor_t* f, float* d_x, int32_t S, int32_
     g.A = f->d_T; g.lda = f->np; g.B = w.Kst; g.ldb = w.S64; g.C = w.Vp; g.ldc = w.S64;
     g.M = f->np; g.N = w.S64; g.K = f->np; g.alpha = 1.f; g.beta = 0.f; g.kmode = KM_A_LOWER;
     g.ksplit = w.ksplit; g.csplit = pstride;
+    if (w.nsplit == 1) g.C = w.V;  // a single chunk is the product itself: no reduction launch (n <= 512)
     rc = gemm(s, false, false, g, w.nsplit);
     if (rc) return rc;
-    refine_reduce_kernel<<<(unsigned)((pstride + 255) / 256), 256, 0, s>>>(w.Vp, w.nsplit, pstride, w.V);
-    BX_LAUNCH_CHECK();
+    if (w.nsplit > 1) {
+      refine_reduce_kernel<<<(unsigned)((pstride + 255) / 256), 256, 0, s>>>(w.Vp, w.nsplit, pstride, w.V);
+      BX_LAUNCH_CHECK();
+    }
     GemmArgs h{};  // W = T^T * V, K-chunk partials (summed by the update kernel)
     h.A = f->d_T; h.lda = f->np; h.B = w.V; h.ldb = w.S64; h.C = w.Wp; h.ldc = w.S64;
     h.M = f->np; h.N = w.S64; h.K = f->np; h.alpha = 1.f; h.beta = 0.f; h.kmode = KM_TN_A;

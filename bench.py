@@ -301,7 +301,9 @@ def main():
                     "frac_of_split_ceiling": 3 * achieved / peak if peak else None,
                     "traffic": TRAFFIC_BYTES.get((args.workload, M)), "kernel_ms": kern_ms_avg,
                     "algorithmic_flops_per_launch": fl, "peak_source": peak_src, "tf32_peak_this_run": tf32_peak}
-        launches_per_step = 1 + 19 + 1 + 4 * (opt.REFINE_ROUNDS + 1) + 1
+        # scoring 1 + top-k 19 (init, 8 x hist, 8 x select, gather, sort) + start gather 1 + refinement 5 per round (K*, V chunks,
+        # reduce, W chunks, update); the conditional re-gather of a winning random candidate is not counted
+        launches_per_step = 1 + 19 + 1 + 5 * (opt.REFINE_ROUNDS + 1)
         line = {
             "metric": "acq candidate-evals/sec", "value": M * args.steps / t_res, "unit": "candidates/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_res / args.steps, "higher_is_better": True,
