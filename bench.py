@@ -53,11 +53,21 @@ def flops_per_candidate(n, d):
 
 
 def make_observations(d, n, oracle_domain):
+    """Synthetic observations for the CPU arm (--impl reference): sample_params(key(0), (n,)) drawn by the oracle."""
     from oracle import prng
     space = oracle_domain.ParamSpace({f"x{i}": oracle_domain.Real(0.0, 1.0) for i in range(d)})
     P = space.sample_params(prng.key(0), (n,))
     X = space.to_array(P)
     return P, X, ackley(X)
+
+
+def make_observations_device(d, n, bayex, engine):
+    """The same draw for the GPU arm, produced by the product's own Threefry kernel (bit-identical to the oracle's:
+    tests/test_gpu_parity.py::test_threefry_candidates_bit_exact) - the GPU arm never touches oracle/ outside the
+    cpu_baseline leg."""
+    dom = {f"x{i}": bayex.domain.Real(0.0, 1.0) for i in range(d)}
+    X = engine.threefry_fill(bayex.random.key(0), engine.dims_array(dom), d, 0, n).cpu().numpy()
+    return {f"x{i}": X[:, i].copy() for i in range(d)}, X, ackley(X)
 
 
 class ClockSampler(threading.Thread):
@@ -194,10 +204,9 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     import bayex_b200 as bayex
-    from bayex_b200 import _lib
-    from oracle import domain as odom  # only to draw the synthetic observations identically to the CPU arm
+    from bayex_b200 import _lib, engine as bengine
 
-    P, X, Y = make_observations(d, n, odom)
+    P, X, Y = make_observations_device(d, n, bayex, bengine)
     dom = {f"x{i}": bayex.domain.Real(0.0, 1.0) for i in range(d)}
     opt = bayex.Optimizer(dom, acq=acq, maximize=False)
     opt.engine = {"auto": _lib.ENGINE_AUTO, "simt": _lib.ENGINE_SIMT, "tcgen05": _lib.ENGINE_TCGEN05,
