@@ -1,6 +1,7 @@
 // Dense fp32 linear algebra for the fit path (gp.py:46-49 and its gradient): SIMT GEMM, blocked Cholesky, recursive
 // triangular inverse, triangular mat-vecs.  Tensor cores are deliberately not used here (north star: only the
 // candidate contraction may use them).
+#include <math.h>
 #include <stdarg.h>
 #include <stdlib.h>
 
@@ -139,8 +140,13 @@ __global__ void __launch_bounds__(256) gemm64_kernel(GemmArgs g) {
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int HT = 128, HK = 16, HP = HT + 4;
 
-template <bool TA, bool TB>
-__global__ void __launch_bounds__(256, 2) gemm128_kernel(GemmArgs g) {
+// NT = 256: 8x8 outputs per thread, two CTAs per SM (many-tile launches).  NT = 512: 4x8 outputs per thread, one CTA of
+// 16 warps per SM - a lone 8-warp CTA reaches only ~50 % of the SM's FMA rate, and in single-wave launches (n <= 4096:
+// the inverse tree, T^T T) the launch lasts as long as its heaviest tile.
+template <bool TA, bool TB, int NT>
+__global__ void __launch_bounds__(NT, 512 / NT) gemm128_kernel(GemmArgs g) {
+  constexpr int RT = 2048 / NT;       // rows per thread: 8 or 4
+  constexpr int LQ = 512 / NT;        // float4 loads per thread and operand tile
   __shared__ __align__(16) float As[2][HK][HP];
   __shared__ __align__(16) float Bs[2][HK][HP];
   const float* A = g.A;
@@ -177,9 +183,9 @@ __global__ void __launch_bounds__(256, 2) gemm128_kernel(GemmArgs g) {
   else if (kmode == KM_TN_A) k_lo = i0;
 
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-  float acc[8][8];
+  float acc[RT][8];
 #pragma unroll
-  for (int r = 0; r < 8; ++r)
+  for (int r = 0; r < RT; ++r)
 #pragma unroll
     for (int c = 0; c < 8; ++c) acc[r][c] = 0.f;
 
@@ -188,7 +194,7 @@ __global__ void __launch_bounds__(256, 2) gemm128_kernel(GemmArgs g) {
   // k-major operands ([K x cols], direct store):               f -> k f/32, col-quad f%32
   const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
   auto load_a = [&](int k0, int q) -> float4 {
-    const int f = tid + q * 256;
+    const int f = tid + q * NT;
     if (TA) {
       const int kk = f >> 5, c4 = (f & 31) * 4;
       return (i0 + c4 < M) ? *reinterpret_cast<const float4*>(A + (size_t)(k0 + kk) * g.lda + i0 + c4) : zero4;
@@ -198,7 +204,7 @@ __global__ void __launch_bounds__(256, 2) gemm128_kernel(GemmArgs g) {
     }
   };
   auto load_b = [&](int k0, int q) -> float4 {
-    const int f = tid + q * 256;
+    const int f = tid + q * NT;
     if (!TB) {
       const int kk = f >> 5, c4 = (f & 31) * 4;
       return (j0 + c4 < N) ? *reinterpret_cast<const float4*>(B + (size_t)(k0 + kk) * g.ldb + j0 + c4) : zero4;
@@ -208,7 +214,7 @@ __global__ void __launch_bounds__(256, 2) gemm128_kernel(GemmArgs g) {
     }
   };
   auto store_a = [&](int buf, int q, const float4& v) {
-    const int f = tid + q * 256;
+    const int f = tid + q * NT;
     if (TA) {
       *reinterpret_cast<float4*>(&As[buf][f >> 5][(f & 31) * 4]) = v;
     } else {
@@ -217,7 +223,7 @@ __global__ void __launch_bounds__(256, 2) gemm128_kernel(GemmArgs g) {
     }
   };
   auto store_b = [&](int buf, int q, const float4& v) {
-    const int f = tid + q * 256;
+    const int f = tid + q * NT;
     if (!TB) {
       *reinterpret_cast<float4*>(&Bs[buf][f >> 5][(f & 31) * 4]) = v;
     } else {
@@ -227,42 +233,42 @@ __global__ void __launch_bounds__(256, 2) gemm128_kernel(GemmArgs g) {
   };
 
   if (k_lo < k_hi) {
-    float4 ra[2], rb[2];
+    float4 ra[LQ], rb[LQ];
 #pragma unroll
-    for (int q = 0; q < 2; ++q) { ra[q] = load_a(k_lo, q); rb[q] = load_b(k_lo, q); }
+    for (int q = 0; q < LQ; ++q) { ra[q] = load_a(k_lo, q); rb[q] = load_b(k_lo, q); }
 #pragma unroll
-    for (int q = 0; q < 2; ++q) { store_a(0, q, ra[q]); store_b(0, q, rb[q]); }
+    for (int q = 0; q < LQ; ++q) { store_a(0, q, ra[q]); store_b(0, q, rb[q]); }
     __syncthreads();
     int buf = 0;
     for (int k0 = k_lo; k0 < k_hi; k0 += HK) {
       const bool more = (k0 + HK < k_hi);
       if (more) {
 #pragma unroll
-        for (int q = 0; q < 2; ++q) { ra[q] = load_a(k0 + HK, q); rb[q] = load_b(k0 + HK, q); }
+        for (int q = 0; q < LQ; ++q) { ra[q] = load_a(k0 + HK, q); rb[q] = load_b(k0 + HK, q); }
       }
 #pragma unroll
       for (int kk = 0; kk < HK; ++kk) {
         const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 4]);
-        const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][kk][64 + ty * 4]);
+        const float4 a1 = (RT == 8) ? *reinterpret_cast<const float4*>(&As[buf][kk][64 + (ty & 15) * 4]) : a0;
         const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 4]);
         const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][kk][64 + tx * 4]);
         const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
         const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-        for (int r = 0; r < 8; ++r)
+        for (int r = 0; r < RT; ++r)
 #pragma unroll
           for (int c = 0; c < 8; ++c) acc[r][c] = fmaf(av[r], bv[c], acc[r][c]);
       }
       if (more) {
 #pragma unroll
-        for (int q = 0; q < 2; ++q) { store_a(buf ^ 1, q, ra[q]); store_b(buf ^ 1, q, rb[q]); }
+        for (int q = 0; q < LQ; ++q) { store_a(buf ^ 1, q, ra[q]); store_b(buf ^ 1, q, rb[q]); }
       }
       __syncthreads();
       buf ^= 1;
     }
   }
 #pragma unroll
-  for (int r = 0; r < 8; ++r) {
+  for (int r = 0; r < RT; ++r) {
     const int row = i0 + (r < 4 ? ty * 4 + r : 64 + ty * 4 + (r - 4));
     if (row >= M) continue;
 #pragma unroll
@@ -284,12 +290,32 @@ int32_t gemm(cudaStream_t s, bool ta, bool tb, const GemmArgs& g, int grid_z) {
   if (g.M <= 0 || g.N <= 0) return 0;
   // large, squarish products go to the 128x128 kernel; skinny ones (panels of 64, the refinement's 64 starts) stay on 64x64
   static const bool force64 = getenv("BX_GEMM64") != nullptr;
-  if (g.M >= HT && g.N >= HT && !force64 && g.ksplit == 0) {
+  // Tile-size choice by a two-term model in clocks: a launch takes the longer of its critical path (the tile with the
+  // longest K range: K/16 k-steps of ~2300 clocks for a 128x128 tile, ~600 for a 64x64 tile, both with 256 threads) and
+  // its total work at the kernel's measured throughput (~45 vs ~18 TFLOP/s).  Few-tile products (n <= 1024, the bottom of
+  // the inverse tree, late trailing updates) are latency-bound and finish sooner on 64x64 tiles.
+  const double kext = (g.tree_nb > 0) ? (double)g.M : (double)g.K;  // tree mode: extents are per node, ~M
+  double flops = 2.0 * (double)g.M * (double)g.N * kext * (double)grid_z;
+  if (g.lower_only) flops *= 0.5;
+  if (g.kmode != KM_FULL || g.tree_nb > 0) flops *= 0.5;
+  const double t128 = fmax(kext / 16.0 * 2300.0, flops * 4.2e-5), t64 = fmax(kext / 16.0 * 600.0, flops * 1.06e-4);
+  if (g.M >= HT && g.N >= HT && !force64 && g.ksplit == 0 && t128 < t64) {
     dim3 grid((g.N + HT - 1) / HT, (g.M + HT - 1) / HT, grid_z);
-    if (!ta && !tb) gemm128_kernel<false, false><<<grid, 256, 0, s>>>(g);
-    else if (ta && !tb) gemm128_kernel<true, false><<<grid, 256, 0, s>>>(g);
-    else if (!ta && tb) gemm128_kernel<false, true><<<grid, 256, 0, s>>>(g);
-    else gemm128_kernel<true, true><<<grid, 256, 0, s>>>(g);
+    // at most ~two tiles per SM: one 16-warp CTA per tile; otherwise two 8-warp CTAs per SM
+    static const int wide_max = [] { const char* e = getenv("BX_GEMM_WIDE_MAX"); return e ? atoi(e) : 296; }();
+    double tiles = (double)grid.x * grid.y * grid.z;
+    if (g.lower_only) tiles *= 0.5;
+    if (tiles <= (double)wide_max) {
+      if (!ta && !tb) gemm128_kernel<false, false, 512><<<grid, 512, 0, s>>>(g);
+      else if (ta && !tb) gemm128_kernel<true, false, 512><<<grid, 512, 0, s>>>(g);
+      else if (!ta && tb) gemm128_kernel<false, true, 512><<<grid, 512, 0, s>>>(g);
+      else gemm128_kernel<true, true, 512><<<grid, 512, 0, s>>>(g);
+    } else {
+      if (!ta && !tb) gemm128_kernel<false, false, 256><<<grid, 256, 0, s>>>(g);
+      else if (ta && !tb) gemm128_kernel<true, false, 256><<<grid, 256, 0, s>>>(g);
+      else if (!ta && tb) gemm128_kernel<false, true, 256><<<grid, 256, 0, s>>>(g);
+      else gemm128_kernel<true, true, 256><<<grid, 256, 0, s>>>(g);
+    }
     BX_LAUNCH_CHECK();
     return 0;
   }
