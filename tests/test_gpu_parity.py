@@ -451,7 +451,7 @@ def test_umma_selftest_3xtf32(K):
 
 @pytest.mark.parametrize("n,d,M,acq", [(200, 3, 1000, "UCB"), (512, 6, 37965, "EI"), (1000, 10, 5000, "LCB"),
                                        (2048, 20, 4096, "LCB"), (1300, 20, 3000, "PI"), (700, 27, 2500, "EI"),
-                                       (384, 32, 1111, "UCB"), (64, 1, 129, "PI")])
+                                       (384, 32, 1111, "UCB"), (64, 1, 129, "PI"), (8192, 8, 700, "EI")])
 def test_tcgen05_engine_matches_simt_engine_and_oracle(n, d, M, acq):
     X, Y, raw, P = make_problem(n, d, seed=n * 3 + d)
     dom = {f"x{i}": bayex.domain.Real(-0.1, 1.1) for i in range(d)}
