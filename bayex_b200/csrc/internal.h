@@ -13,6 +13,7 @@ enum KMode {
   KM_B_LOWER = 2,   // B lower triangular (NN): k >= j0
   KM_TN_BOTH = 3,   // A^T B with both lower triangular: k >= max(i0, j0)
   KM_TN_A = 4,      // A^T B with A lower triangular: k >= i0
+  KM_BT_LOWER = 5,  // A B^T with B (stored [N x K]) lower triangular: k < j0 + 64
 };
 
 struct GemmArgs {

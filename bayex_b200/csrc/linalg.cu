@@ -66,6 +66,7 @@ __global__ void __launch_bounds__(256) gemm64_kernel(GemmArgs g) {
   else if (kmode == KM_B_LOWER) k_lo = j0;
   else if (kmode == KM_TN_BOTH) k_lo = max(i0, j0);
   else if (kmode == KM_TN_A) k_lo = i0;
+  else if (kmode == KM_BT_LOWER) k_hi = min(K, j0 + GT);
 
   if (g.ksplit > 0) {
     k_lo = max(k_lo, (int)blockIdx.z * g.ksplit);
@@ -181,6 +182,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) gemm128_kernel(GemmArgs g) {
   else if (kmode == KM_B_LOWER) k_lo = j0;
   else if (kmode == KM_TN_BOTH) k_lo = max(i0, j0);
   else if (kmode == KM_TN_A) k_lo = i0;
+  else if (kmode == KM_BT_LOWER) k_hi = min(K, j0 + HT);
 
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   float acc[RT][8];
