@@ -34,7 +34,8 @@ constexpr int BN = 256;                    // T rows per accumulator = UMMA N
 constexpr int HN = BN / 2;                 // rows of every T tile held by one CTA
 // Ring depths.  A stage of K* is refilled only after the MMAs that read it have completed, so with P = producer time and
 // Tm = MMA time per K-block (both ~3000 clk) a 2-deep ring runs at (P + Tm + latencies) / 2 per K-block; 3 stages reach
-// max(P, Tm).  T tiles: 3 stages = 1.5 K-blocks of TMA look-ahead.
+// max(P, Tm).  T tiles: 3 stages = 1.5 K-blocks of TMA look-ahead.  Observation rows: 2 stages (profiles/
+// r1c_ring_depth_sweep.csv: all of 3/3/3, 4/2/3, 4/2/2, 3/2/3, 3/3/2 within 0.6 % - the kernel is energy-bound).
 #ifndef BX_P_SA
 #define BX_P_SA 3
 #endif
@@ -42,7 +43,7 @@ constexpr int HN = BN / 2;                 // rows of every T tile held by one C
 #define BX_P_SB 3
 #endif
 #ifndef BX_P_NU
-#define BX_P_NU 3
+#define BX_P_NU 2
 #endif
 #ifndef BX_P_WAIT_NS
 #define BX_P_WAIT_NS 64
@@ -166,6 +167,11 @@ score_tc16p_kernel(const __grid_constant__ ScoreArgs a, const __grid_constant__ 
   Smem& S = *reinterpret_cast<Smem*>(smem_raw);
   constexpr int US = BKH * D4 + BKH;  // floats per staged K-block: 64 observation rows + 64 alpha
   const uint32_t us_addr = smem_u32(smem_raw) + (uint32_t)sizeof(Smem);  // [NU][US]
+  // scaled candidate coordinates of the current tile [TM][D4], drawn ONCE per tile by the 256 producer threads together:
+  // a producer thread needs the RC x D4 coordinates of its candidates, and the 2 RC threads that share a candidate group
+  // used to draw them redundantly - at n = 512 those Threefry calls were half of the producers' instructions
+  constexpr bool SHARE_COORDS = (D4 <= 28);  // D4 = 32 does not leave room for the buffer
+  const uint32_t cs_addr = us_addr + (uint32_t)(NU * US * 4);
   if ((smem_u32(smem_raw) & 1023u) != 0u) __trap();
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -348,14 +354,32 @@ score_tc16p_kernel(const __grid_constant__ ScoreArgs a, const __grid_constant__ 
     for (uint64_t pt = pair0; pt < npairs; pt += pstride, ++tiles_done) {
       const uint64_t tile = 2 * pt + rank;
       uint64_t ncr[RC][D4 / 2];  // (-c_k, -c_{k+1}) packed: the squared distance runs on add.f32x2 / fma.f32x2
+      if constexpr (SHARE_COORDS) {
+        for (int e = pth; e < TM * D4; e += NPROD) {
+          const int c = e / D4, k = e % D4;
+          const float v = (k < a.f.d) ? sample_coord(sp.dim[k], a.m_begin + tile * TM + c) * a.f.d_scale[k] : 0.f;
+          sts32(cs_addr + 4u * (uint32_t)e, -v);
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");  // producers only; the K loop below keeps tiles apart
 #pragma unroll
-      for (int j = 0; j < RC; ++j) {
-        const uint64_t gidx = a.m_begin + tile * TM + cg + j * NCG;
+        for (int j = 0; j < RC; ++j)
 #pragma unroll
-        for (int k = 0; k < D4; k += 2) {
-          const float c0 = (k < a.f.d) ? sample_coord(sp.dim[k], gidx) * a.f.d_scale[k] : 0.f;
-          const float c1 = (k + 1 < a.f.d) ? sample_coord(sp.dim[k + 1], gidx) * a.f.d_scale[k + 1] : 0.f;
-          ncr[j][k / 2] = pack2(-c0, -c1);
+          for (int k = 0; k < D4; k += 4) {
+            uint64_t c01, c23;
+            lds_2x64(cs_addr + (uint32_t)(((cg + j * NCG) * D4 + k) * 4), c01, c23);
+            ncr[j][k / 2] = c01;
+            ncr[j][k / 2 + 1] = c23;
+          }
+      } else {
+#pragma unroll
+        for (int j = 0; j < RC; ++j) {
+          const uint64_t gidx = a.m_begin + tile * TM + cg + j * NCG;
+#pragma unroll
+          for (int k = 0; k < D4; k += 2) {
+            const float c0 = (k < a.f.d) ? sample_coord(sp.dim[k], gidx) * a.f.d_scale[k] : 0.f;
+            const float c1 = (k + 1 < a.f.d) ? sample_coord(sp.dim[k + 1], gidx) * a.f.d_scale[k + 1] : 0.f;
+            ncr[j][k / 2] = pack2(-c0, -c1);
+          }
         }
       }
       float mpart[RC];
@@ -446,7 +470,7 @@ score_tc16p_kernel(const __grid_constant__ ScoreArgs a, const __grid_constant__ 
 
 template <int D4, int RC>
 static int32_t launch_d4(cudaStream_t s, const ScoreArgs& a, const SamplerPack& sp, const CUtensorMap& mh, const CUtensorMap& ml) {
-  const size_t smem = sizeof(Smem) + sizeof(float) * NU * (BKH * D4 + BKH);
+  const size_t smem = sizeof(Smem) + sizeof(float) * NU * (BKH * D4 + BKH) + (D4 <= 28 ? sizeof(float) * TM * D4 : 0);
   BX_CUDA(cudaFuncSetAttribute(score_tc16p_kernel<D4, RC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int dev = 0, sms = 0;
   BX_CUDA(cudaGetDevice(&dev));
