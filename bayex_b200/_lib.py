@@ -22,6 +22,7 @@ ACQ_IDS = {"EI": 0, "PI": 1, "UCB": 2, "LCB": 3}
 ENGINE_AUTO, ENGINE_SIMT, ENGINE_TCGEN05, ENGINE_TCGEN05_PAIR, ENGINE_TCGEN05_F16, ENGINE_TCGEN05_F16_PAIR = 0, 1, 2, 3, 4, 5
 ENGINE_TCGEN05_F16_SHARED = 6
 MAX_D, MAX_K, TILE = 64, 1024, 128
+POINTS_TC_MIN = 65536  # BX_POINTS_TC_MIN
 
 
 class DimT(C.Structure):

@@ -8,7 +8,7 @@ from __future__ import annotations
 import numpy as np
 import torch
 
-from . import engine
+from . import _lib, engine
 from .gp import GPParams  # noqa: F401  (re-exported like the reference: acq.py:5)
 
 
@@ -25,9 +25,11 @@ def ystar_for(acq: str, ys, mask) -> float:
 
 def _score(acq, x_pred, xs, ys, mask, gp_params, param):
     xv, yv = engine.compact(xs, ys, mask)
-    post = engine.Posterior(xv, yv, engine.raw_vector(gp_params, xv.shape[1]), want_tc=False)
     xt = np.asarray(x_pred, dtype=np.float32)
     xt = xt[:, None] if xt.ndim == 1 else xt
+    # large point sets run on the tcgen05 engine (bx_score_points switches at BX_POINTS_TC_MIN), which needs the fp16
+    # copies of the factor; small ones stay on the fp32 SIMT engine and skip building them
+    post = engine.Posterior(xv, yv, engine.raw_vector(gp_params, xv.shape[1]), want_tc=len(xt) >= _lib.POINTS_TC_MIN)
     out = post.score_points(xt, acq=acq, param=param, ystar=ystar_for(acq, ys, mask), want=("acq",))
     with engine.on_stream(post.stream, post.dev):
         return out["acq"].cpu().numpy()

@@ -263,6 +263,10 @@ extern "C" int32_t bx_score_points(const bx_factor_t* f, const float* d_cand, ui
   ScoreArgs a{};
   a.f = *f; a.cand = d_cand; a.m_begin = 0; a.m_count = M; a.acq_id = acq_id; a.acq_param = acq_param; a.ystar = ystar;
   a.mu = d_mu; a.sigma = d_sigma; a.acq = d_acq; a.best = reinterpret_cast<unsigned long long*>(d_best); a.index_base = index_base;
+  // large explicit point sets (gp.predict / acq.* with M >= 2^16) take the production tcgen05 engine when the factor
+  // carries its fp16 copies: same fused pipeline, coordinates read from d_cand instead of drawn (SIMT: 16 TFLOP/s)
+  static const SamplerPack no_sampler{};
+  if (M >= BX_POINTS_TC_MIN && score_tc16_supported(*f)) return launch_score_tc16p((cudaStream_t)stream, a, no_sampler);
   return launch_score_simt((cudaStream_t)stream, a, nullptr, false);
 }
 

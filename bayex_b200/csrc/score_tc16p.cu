@@ -156,6 +156,13 @@ __device__ __forceinline__ float4 lds128f(uint32_t addr) {
   return v;
 }
 
+// Raw coordinate k of candidate `row` (position in this launch): generated from the Threefry key (optimizer.py:183-184) or
+// read from the caller's explicit points (gp.predict / acq.* on large point sets); rows past the end read as 0.
+__device__ __forceinline__ float cand_coord(const ScoreArgs& a, const SamplerPack& sp, uint64_t row, int k) {
+  if (a.cand) return row < a.m_count ? __ldg(a.cand + row * (uint64_t)a.f.d + k) : 0.f;
+  return sample_coord(sp.dim[k], a.m_begin + row);
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // RC = candidates per producer thread.  128 / RC candidate groups x (2 RC) observation parts = 256 producer threads;
 // a thread generates RC candidates x (32 / RC) observations of every K-block.
@@ -357,7 +364,7 @@ score_tc16p_kernel(const __grid_constant__ ScoreArgs a, const __grid_constant__ 
       if constexpr (SHARE_COORDS) {
         for (int e = pth; e < TM * D4; e += NPROD) {
           const int c = e / D4, k = e % D4;
-          const float v = (k < a.f.d) ? sample_coord(sp.dim[k], a.m_begin + tile * TM + c) * a.f.d_scale[k] : 0.f;
+          const float v = (k < a.f.d) ? cand_coord(a, sp, tile * TM + c, k) * a.f.d_scale[k] : 0.f;
           sts32(cs_addr + 4u * (uint32_t)e, -v);
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");  // producers only; the K loop below keeps tiles apart
@@ -373,11 +380,11 @@ score_tc16p_kernel(const __grid_constant__ ScoreArgs a, const __grid_constant__ 
       } else {
 #pragma unroll
         for (int j = 0; j < RC; ++j) {
-          const uint64_t gidx = a.m_begin + tile * TM + cg + j * NCG;
+          const uint64_t grow = tile * TM + cg + j * NCG;
 #pragma unroll
           for (int k = 0; k < D4; k += 2) {
-            const float c0 = (k < a.f.d) ? sample_coord(sp.dim[k], gidx) * a.f.d_scale[k] : 0.f;
-            const float c1 = (k + 1 < a.f.d) ? sample_coord(sp.dim[k + 1], gidx) * a.f.d_scale[k + 1] : 0.f;
+            const float c0 = (k < a.f.d) ? cand_coord(a, sp, grow, k) * a.f.d_scale[k] : 0.f;
+            const float c1 = (k + 1 < a.f.d) ? cand_coord(a, sp, grow, k + 1) * a.f.d_scale[k + 1] : 0.f;
             ncr[j][k / 2] = pack2(-c0, -c1);
           }
         }

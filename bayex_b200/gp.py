@@ -13,7 +13,7 @@ from functools import partial
 import numpy as np
 import torch
 
-from . import engine
+from . import _lib, engine
 from ._lib import lib, check
 
 MASK_VARIANCE = 1e12  # gp.py:10 (kept for API parity; padded rows are compacted away before the kernels run)
@@ -59,12 +59,13 @@ def _posterior(params, x, y, mask, want_tc=False):
 
 def gaussian_process(params, x, y, mask, xt=None, compute_ml=False):
     """gp.py:30-71: NLML (``compute_ml=True``) or posterior (mean, std) at ``xt``."""
-    post = _posterior(params, x, y, mask)
     if compute_ml:
-        return np.float32(post.nlml_grad()[0])
+        return np.float32(_posterior(params, x, y, mask).nlml_grad()[0])
     assert xt is not None, "xt can't be None during prediction."  # gp.py:59
     xt = np.asarray(xt, dtype=np.float32)
     xt = xt[:, None] if xt.ndim == 1 else xt
+    # point sets of BX_POINTS_TC_MIN and more are scored by the tcgen05 engine, which needs the fp16 copies of the factor
+    post = _posterior(params, x, y, mask, want_tc=len(xt) >= _lib.POINTS_TC_MIN)
     out = post.score_points(xt, want=("mu", "sigma"))
     with engine.on_stream(post.stream, post.dev):
         return out["mu"].cpu().numpy(), out["sigma"].cpu().numpy()

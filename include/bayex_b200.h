@@ -121,6 +121,8 @@ int32_t bx_factor_build(const float* d_X, const float* d_y, int32_t n, int32_t d
                         float* d_T, float* d_Thi, float* d_Tlo, void* d_T16hi, void* d_T16lo, float* d_alpha,
                         float* d_scale, float* d_hyp, void* d_ws, size_t ws_bytes, void* stream);
 
+#define BX_POINTS_TC_MIN 65536 /* bx_score_points: point sets at least this large use the tcgen05 engine if the factor has its fp16 copies */
+
 /* Posterior + acquisition at explicit points - replaces: gp.py:59-71 predict, acq.py:45-50,84-87,120-121,155-156.
  * d_cand [M x d] raw (unscaled) points.  Any of d_mu / d_sigma / d_acq may be NULL.  d_best (optional) is a
  * uint64 packed arg-max accumulator (see bx_pack); index = index_base + row. */

@@ -738,3 +738,48 @@ def test_state_file_roundtrip_reproduces_the_proposal(tmp_path):
     fresh = bayex.Optimizer(dom, acq="LCB")                        # cold cache: the factor is rebuilt from the file
     got = fresh.sample(key, bayex.load_state(tmp_path / "s.npz"), size=4096)
     assert all(np.array_equal(got[k], want[k]) for k in dom)
+
+
+@pytest.mark.gpu
+def test_large_explicit_point_sets_take_the_tcgen05_engine():
+    """gp.predict / acq.* on >= BX_POINTS_TC_MIN explicit points (rows a10, a13-a16) run on the production tensor-core engine
+    with the coordinates read from the caller's array.  Bars: the mean at the fp32 bar; the variance to 5e-5 of the
+    amplitude (tcgen05.mma accumulates in fp32 with truncation, one per MMA - scripts/dev/diag_umma_bias.py - which costs
+    ~1e-5 amp on a - sum v^2; the SIMT engine below the switch stays at the fp32 oracle's level); the acquisition through
+    the same propagated tolerance as every other engine test."""
+    n, d, M = 700, 5, _lib.POINTS_TC_MIN + 777
+    X, Y, raw, P = make_problem(n, d, seed=31)
+    gp_params = bayex.gp.GPParams(raw[0], raw[1], raw[2:])
+    mask = np.ones(n, bool)
+    rng = np.random.default_rng(5)
+    xt = rng.uniform(-0.1, 1.1, (M, d)).astype(np.float32)
+    xt[:4] = X[:4] + 1e-3
+    mu, sd = bayex.gp.predict(gp_params, X, Y, mask, xt)                                    # tcgen05 engine
+    k = _lib.POINTS_TC_MIN - 1
+    mu_s, sd_s = bayex.gp.predict(gp_params, X, Y, mask, xt[:k])                             # SIMT engine
+    assert mu.shape == sd.shape == (M,) and mu.dtype == np.float32 and np.all(np.isfinite(mu)) and np.all(np.isfinite(sd))
+    f64, f32 = ogp.Factor(P, X, Y, np.ones(n), np.float64), ogp.Factor(P, X, Y, np.ones(n), np.float32)
+    mu64, sd64 = f64.predict(xt.astype(np.float64))
+    mu32, sd32 = f32.predict(xt)
+    amp = float(np.logaddexp(np.float64(raw[1]), 0.0))
+    tmu = np.maximum(RTOL * np.maximum(np.abs(mu64), np.abs(mu64).mean()), 4 * np.abs(mu32 - mu64))
+    tmu = np.maximum(tmu, 2 * np.abs(mu32 - mu64).max())
+    assert np.all(np.abs(mu - mu64) <= tmu), np.abs(mu - mu64).max()
+    assert np.all(np.abs(mu_s - mu64[:k]) <= tmu[:k])
+    var_err = np.abs(sd.astype(np.float64) ** 2 - sd64 ** 2) / amp
+    var_err_s = np.abs(sd_s.astype(np.float64) ** 2 - sd64[:k] ** 2) / amp
+    var_err_32 = np.abs(sd32.astype(np.float64) ** 2 - sd64 ** 2) / amp
+    assert var_err.max() <= 5e-5, var_err.max()
+    assert var_err_s.max() <= max(1e-5, 4 * var_err_32.max()), (var_err_s.max(), var_err_32.max())
+    ei = bayex.acq.expected_improvement(xt, X, Y, mask, gp_params)
+    a64 = oacq.acq_from_moments("EI", mu64, sd64, Y.astype(np.float64), np.ones(n))
+    a32 = oacq.acq_from_moments("EI", mu32, sd32, Y, np.ones(n))
+    tsd = np.maximum(RTOL * sd64, 4 * np.abs(sd32.astype(np.float64) - sd64))
+    prop = np.zeros_like(a64)
+    for smu in (-1, 1):
+        for ssd in (-1, 1):
+            prop = np.maximum(prop, np.abs(oacq.acq_from_moments("EI", mu64 + smu * tmu, np.maximum(sd64 + ssd * tsd, 1e-12),
+                                                                 Y.astype(np.float64), np.ones(n)) - a64))
+    tol = np.maximum.reduce([RTOL * np.maximum(np.abs(a64), np.abs(a64).mean()), 4 * np.abs(a32 - a64), 2 * prop,
+                             np.full_like(a64, 2 * np.abs(a32 - a64).max())])
+    assert ei.shape == (M,) and np.all(np.abs(ei - a64) <= tol), np.abs(ei - a64).max()
