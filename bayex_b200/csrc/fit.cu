@@ -465,8 +465,9 @@ static size_t fit_small_smem(int n, int d) {
   const int d4 = round_up(d, 4), P = d + 2;
   return sizeof(float) * ((size_t)2 * n * (n + 1) + (size_t)n * d4 + 3 * n + 2 * P + d4 + 2 * P);
 }
-// measured on B200: 0.024 ms/step at n=23, 0.11 at n=64 (multi-kernel path: 0.22 ms/step up to n=128) -> cross-over ~ n=80
-constexpr int FS_DISPATCH_N = 80;
+// measured on B200: fused 0.027 ms/step at n=24, 0.065 at 48, 0.087 at 56, 0.110 at 64, 0.165 at 80; the multi-kernel
+// path (one 128-row tile, CUDA graph) takes 0.085 ms/step for every n <= 128 -> cross-over at n = 56
+constexpr int FS_DISPATCH_N = 56;
 static bool fit_small_ok(int n, int d) { return n <= FS_DISPATCH_N && fit_small_smem(n, d) <= 200 * 1024; }
 
 static int32_t launch_fit_small(cudaStream_t s, const float* d_X, const float* d_y, int n, int d, float* d_raw, float lr,
