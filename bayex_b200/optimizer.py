@@ -168,13 +168,20 @@ class Optimizer:
                               best_params=best_params, mask=mask, gp_params=params_from_raw(raw, d))
 
     def sample(self, key, state: OptimizerState, size: int = 10_000, *, n_starts: int = None, refine_rounds: int = None,
-               details: bool = False):
+               q: int = 1, details: bool = False):
         """optimizer.py:168-208: draw ``size`` candidates, score, refine the top 50, return the arg-max as a dict.
 
         With an initialised ``torch.distributed`` group the candidate axis is sharded across ranks (each GPU
         generates and scores its own index range), the proposal is picked with a packed max all-reduce and every
         rank returns the same dict.
+
+        ``q > 1`` (keyword-only, SURVEY 8(f) rank 3 - the reference proposes one point per call) returns the ``q`` best
+        distinct points of the same pool the single proposal is the arg-max of - the refined starts followed by the top
+        random candidates, ordered by acquisition value (refined points first among ties) - as arrays of shape ``(q,)``;
+        entry 0 is exactly the ``q = 1`` proposal.
         """
+        if q < 1:
+            raise ValueError("q must be at least 1")
         n_starts = self.N_STARTS if n_starts is None else n_starts
         refine_rounds = self.REFINE_ROUNDS if refine_rounds is None else refine_rounds
         key = brandom.as_key(key)
@@ -219,7 +226,11 @@ class Optimizer:
             with engine.on_stream(post.stream, post.dev):
                 point = post.gather(key, self._dims, idx).cpu().numpy()[0]
             chosen = len(opt_host) + j
-        best_params = self.param_space.to_dict(point[None])  # optimizer.py:207
+        if q > 1:
+            point = self._batch_points(post, key, point, opt_host, ov_host, tv, ti, q)
+        else:
+            point = point[None]
+        best_params = self.param_space.to_dict(point)  # optimizer.py:207
         best_params = {k: np.asarray(v, dtype=np.float32) for k, v in best_params.items()}
         if details:
             with engine.on_stream(post.stream, post.dev):
@@ -228,6 +239,25 @@ class Optimizer:
                             best_opt=_lib.unpack(b_opt), best_rnd=_lib.unpack(b_rnd), m_begin=m_begin, m_count=m_count)
             return best_params, info
         return best_params
+
+    def _batch_points(self, post, key, first, opt_host, ov_host, tv, ti, q):
+        """The q best distinct points of concat(refined starts, top random candidates) by acquisition value; row 0 = ``first``."""
+        with engine.on_stream(post.stream, post.dev):
+            rnd_pts = post.gather(key, self._dims, ti).cpu().numpy() if ti.numel() else np.zeros((0, len(self.domain)), np.float32)
+            rnd_vals = tv.cpu().numpy()
+        pts = np.concatenate([opt_host, rnd_pts], axis=0)
+        vals = np.concatenate([ov_host, rnd_vals]).astype(np.float32) + np.float32(0.0)
+        nan = np.isnan(vals)
+        order = np.lexsort((np.arange(len(vals)), -np.where(nan, np.float32(np.inf), vals)))  # value desc, position asc
+        rows, seen = [np.asarray(first, np.float32)], {np.asarray(first, np.float32).tobytes()}
+        for j in order:
+            if len(rows) == q:
+                break
+            b = pts[j].astype(np.float32).tobytes()
+            if b not in seen:
+                seen.add(b)
+                rows.append(pts[j].astype(np.float32))
+        return np.stack(rows, axis=0)
 
     def expand(self, opt_state: OptimizerState) -> OptimizerState:
         """optimizer.py:211-239: double the padded buffers when full."""

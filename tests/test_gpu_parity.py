@@ -783,3 +783,34 @@ def test_large_explicit_point_sets_take_the_tcgen05_engine():
     tol = np.maximum.reduce([RTOL * np.maximum(np.abs(a64), np.abs(a64).mean()), 4 * np.abs(a32 - a64), 2 * prop,
                              np.full_like(a64, 2 * np.abs(a32 - a64).max())])
     assert ei.shape == (M,) and np.all(np.abs(ei - a64) <= tol), np.abs(ei - a64).max()
+
+
+@pytest.mark.gpu
+def test_batched_proposals_q():
+    """sample(..., q=4): (q,) arrays, row 0 is the q = 1 proposal, rows are distinct, Integer columns integral, and no row
+    scores above row 0 (it is the arg-max of the same pool)."""
+    dom = {"a": bayex.domain.Real(0.0, 2.0), "k": bayex.domain.Integer(-5, 5)}
+    rng = np.random.default_rng(3)
+    P0 = {"a": rng.uniform(0, 2, 30).astype(np.float32), "k": rng.integers(-5, 6, 30)}
+    Y0 = ((P0["a"] - 1.2) ** 2 + 0.1 * P0["k"] ** 2).astype(np.float32)
+    opt = bayex.Optimizer(dom, acq="EI")
+    st = opt.init(Y0, P0)
+    key = bayex.random.key(11)
+    one = opt.sample(key, st, size=5000)
+    four = opt.sample(key, st, size=5000, q=4)
+    assert all(four[k].shape == (4,) and four[k].dtype == np.float32 for k in dom)
+    assert all(four[k][0] == one[k][0] for k in dom)
+    pts = np.stack([four["a"], four["k"]], axis=1)
+    assert len({p.tobytes() for p in pts}) == 4 and np.all(four["k"] == np.round(four["k"])) and np.all(np.abs(four["k"]) <= 5)
+    # value order on a Real-only domain (no rounding between the pool's values and the returned points, quirk Q11)
+    rdom = {"a": bayex.domain.Real(0.0, 2.0), "b": bayex.domain.Real(-1.0, 1.0)}
+    R0 = {"a": P0["a"], "b": rng.uniform(-1, 1, 30).astype(np.float32)}
+    ropt = bayex.Optimizer(rdom, acq="EI")
+    rst = ropt.init(((R0["a"] - 1.2) ** 2 + R0["b"] ** 2).astype(np.float32), R0)
+    three = ropt.sample(key, rst, size=5000, q=3)
+    rp = np.stack([three["a"], three["b"]], axis=1)
+    xs = ropt.param_space.to_array({k: rst.params[k] for k in rdom})
+    vals = bayex.acq.expected_improvement(rp, xs, -rst.ys, rst.mask, rst.gp_params)
+    assert vals[0] >= vals[1] * (1 - 1e-4) - 1e-9 and vals[1] >= vals[2] * (1 - 1e-4) - 1e-9, vals
+    with pytest.raises(ValueError):
+        opt.sample(key, st, size=100, q=0)
