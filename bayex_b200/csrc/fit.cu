@@ -285,7 +285,7 @@ __global__ void adamw_kernel(float* raw, const float* __restrict__ gbuf, int d, 
 // gradient contraction -> clip + AdamW, `steps` times.  This is the README / test-suite regime (n = 3 .. ~100), where
 // the multi-kernel path is pure launch latency.
 // ------------------------------------------------------------------------------------------------------------------
-constexpr int FS_MAXN = 128, FS_THREADS = 256;
+constexpr int FS_THREADS = 256;
 
 __device__ __forceinline__ float fs_block_sum(float v, float* red) {
   v = warp_sum(v);

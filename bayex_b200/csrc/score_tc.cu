@@ -1,4 +1,6 @@
-// tcgen05 scoring engine: the one dense contraction of the hot path on the 5th-gen tensor cores.
+// tcgen05 scoring engine, 3xTF32, one CTA per tile (BX_ENGINE_TCGEN05): the first tensor-core engine, kept as a cross-check
+// with different operand arithmetic (full fp32 exponent range of T).  Production: score_tc16p.cu.
+// The one dense contraction of the hot path on the 5th-gen tensor cores.
 //
 // Per tile of 128 candidates (UMMA M = 128, one TMEM lane per candidate):
 //     V[cand, row] = sum_obs K*[cand, obs] * T[row, obs]        (gp.py:68 as a GEMM against T = L^-1)

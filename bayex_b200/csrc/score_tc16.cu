@@ -1,4 +1,5 @@
-// tcgen05 scoring engine with an fp16 head/tail split ("3xFP16"): same pipeline as score_tc.cu, half the tensor work.
+// tcgen05 scoring engine with an fp16 head/tail split ("3xFP16"), one CTA per tile (BX_ENGINE_TCGEN05_F16): same pipeline
+// as score_tc.cu, half the tensor work.  Kept selectable; production: score_tc16p.cu.
 //
 // x = hi + lo with hi = fp16(x), lo = fp16(x - hi) carries 22 significand bits - the same as the TF32 head/tail split -
 // but kind::f16 MMAs run at twice the TF32 rate and the operands are half as wide, so tensor time, shared-memory operand

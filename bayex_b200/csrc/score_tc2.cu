@@ -1,4 +1,5 @@
-// tcgen05 scoring engine, CTA-pair version (cta_group::2): the production engine for large candidate sets.
+// tcgen05 scoring engine, 3xTF32, CTA-pair version (cta_group::2, BX_ENGINE_TCGEN05_PAIR): where the pair protocol was
+// developed; kept selectable.  Production: score_tc16p.cu (the same protocol with fp16 head/tail operands).
 //
 // Same algorithm as score_tc.cu (see there), but two CTAs of a cluster - the two SMs of one TPC - cooperate on one
 // UMMA M=256 x N=256 tile: each CTA owns 128 candidates (its own generated K* tile, its own 512 TMEM columns, its own
@@ -35,15 +36,6 @@ struct __align__(16) Smem {
   uint32_t tmem_base;
 };
 
-__device__ __forceinline__ uint32_t cluster_rank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
 // arrive on the leader's copy of `bar` (same smem offset in CTA rank 0)
 __device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {
   asm volatile(
@@ -52,30 +44,6 @@ __device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {
       "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
       ::"r"(bar)
       : "memory");
-}
-template <int SLEEP_NS = 0>
-__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
-  uint32_t done = 0, spins = 0;
-  long long t0 = 0;
-  while (true) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (done) return;
-    if (SLEEP_NS > 0) __nanosleep(SLEEP_NS);
-    if ((++spins & 0xFFFu) == 0) {
-      const long long now = clock64();
-      if (t0 == 0) t0 = now;
-      else if (now - t0 > 4000000000ll) {
-        printf("bayex_b200: cluster mbarrier timeout (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
-        __trap();
-      }
-    }
-  }
 }
 __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar, int x, int y) {
   // complete_tx lands on the leader CTA's barrier: clear the peer bit of the shared::cluster address

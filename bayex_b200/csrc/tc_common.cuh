@@ -154,6 +154,51 @@ __device__ __forceinline__ void split_store(uint32_t hi_tile, uint32_t lo_tile, 
   sts128(lo_tile + off, l);
 }
 
+// ---- thread-block cluster helpers (CTA-pair and shared-generation engines) --------------------------------------------
+__device__ __forceinline__ uint32_t cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// wait on a CTA-local barrier whose arrivals (or complete_tx bytes) may come from the peer CTA: cluster-scope acquire
+template <int SLEEP_NS = 0>
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0, spins = 0;
+  long long t0 = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) return;
+    if (SLEEP_NS > 0) __nanosleep(SLEEP_NS);
+    if ((++spins & 0xFFFu) == 0) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000ll) {
+        printf("bayex_b200: cluster mbarrier timeout (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
+        __trap();
+      }
+    }
+  }
+}
+// 1-D bulk-async copy global -> shared with mbarrier complete_tx (TMA without a tensor map)
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"((uint64_t)src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+// register re-partitioning between warpgroups (all four warps of a warpgroup execute the same one)
+template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+
 // ---- fp16 head/tail split (kind::f16 engines) ------------------------------------------------------------------
 // x = hi + lo with hi = fp16(x), lo = fp16(x - hi): 22 significand bits like the TF32 split, at twice the MMA rate.
 // fp16's narrow exponent is handled with two power-of-two scales: K* * 2^a (largest entry near 2^14, from the
