@@ -21,7 +21,7 @@ lib = C.CDLL(LIB_PATH)
 ACQ_IDS = {"EI": 0, "PI": 1, "UCB": 2, "LCB": 3}
 ENGINE_AUTO, ENGINE_SIMT, ENGINE_TCGEN05, ENGINE_TCGEN05_PAIR, ENGINE_TCGEN05_F16, ENGINE_TCGEN05_F16_PAIR = 0, 1, 2, 3, 4, 5
 ENGINE_TCGEN05_F16_SHARED = 6
-MAX_D, MAX_K, TILE = 64, 1024, 128
+MAX_D, MAX_K, TILE, FIT_BATCH_MAX = 64, 1024, 128, 32
 POINTS_TC_MIN = 65536  # BX_POINTS_TC_MIN
 
 
@@ -49,6 +49,7 @@ SIGNATURES = {
     "bx_fit_workspace_bytes": (_sz, [_i32, _i32]),
     "bx_nlml_grad": (_i32, [_vp, _vp, _i32, _i32, _vp, _vp, _vp, _sz, _vp]),
     "bx_fit_adamw": (_i32, [_vp, _vp, _i32, _i32, _vp, _f32, _i32, _vp, _vp, _sz, _i32, _vp]),
+    "bx_fit_adamw_batch": (_i32, [_vp, _vp, _i32, _i32, _vp, _i32, _f32, _i32, _vp, _vp, _sz, _vp]),
     "bx_factor_build": (_i32, [_vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "bx_score_points": (_i32, [C.POINTER(FactorT), _vp, _u64, _i32, _f32, _f32, _vp, _vp, _vp, _vp, _u64, _vp]),
     "bx_score_generated": (_i32, [C.POINTER(FactorT), _key, C.POINTER(DimT), _u64, _u64, _i32, _f32, _f32, _vp, _vp,

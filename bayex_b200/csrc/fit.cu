@@ -3,6 +3,8 @@
 #include <cuda_fp16.h>
 #include <stdlib.h>
 
+#include <vector>
+
 #include "internal.h"
 
 namespace bx {
@@ -528,7 +530,7 @@ int32_t launch_factor(cudaStream_t s, const float* d_X, const float* d_y, int n,
   const size_t gsm = 2 * 32 * (d4 + 1) * sizeof(float);
   gram_kernel<<<dim3(np / 32, np / 32), 256, gsm, s>>>(U, n, np, d4, hyp, T, np);
   BX_LAUNCH_CHECK();
-  int32_t rc = cholesky_inplace(s, T, np, np, w.Dinv, w.logdet_part, w.status);
+  int32_t rc = cholesky_inplace(s, T, np, np, w.Dinv, w.logdet_part, w.status, w.la);
   if (rc) return rc;
   rc = tri_inverse_inplace(s, T, np, np, w.Dinv, w.TMP);
   if (rc) return rc;
@@ -585,6 +587,8 @@ extern "C" int32_t bx_nlml_grad(const float* d_X, const float* d_y, int32_t n, i
   FitWs w = carve_fit_ws(d_ws, n, d);
   if (fit_small_ok(n, d) && !getenv("BX_NO_FIT_SMALL"))  // one-kernel evaluation (raw is left untouched: steps = 0)
     return launch_fit_small(s, d_X, d_y, n, d, const_cast<float*>(d_raw), 0.f, 0, nullptr, d_out, 1);
+  Lookahead la;
+  if (lookahead_wanted(w.np)) { if ((rc = la.init())) return rc; w.la = &la; }
   rc = launch_grad(s, d_X, d_y, n, d, d_raw, w);
   if (rc) return rc;
   BX_CUDA(cudaMemcpyAsync(d_out, w.gbuf, sizeof(float) * (2 + 2 * (d + 2)), cudaMemcpyDeviceToDevice, s));
@@ -603,6 +607,8 @@ extern "C" int32_t bx_fit_adamw(const float* d_X, const float* d_y, int32_t n, i
   if (fit_small_ok(n, d) && !getenv("BX_NO_FIT_SMALL"))  // whole loop in one launch
     return launch_fit_small(s, d_X, d_y, n, d, d_raw, lr, steps, d_trace, nullptr, 0);
   BX_CUDA(cudaMemsetAsync(w.adam, 0, sizeof(float) * (2 * (d + 2) + 1), s));  // fresh moments per call (gp.py:100)
+  Lookahead la;
+  if (lookahead_wanted(w.np)) { if ((rc = la.init())) return rc; w.la = &la; }
   if (use_graph && !d_trace) {
     // One step is captured once and replayed `steps` times: the loop never returns to the host.
     cudaGraph_t graph = nullptr;
@@ -641,6 +647,122 @@ extern "C" int32_t bx_fit_adamw(const float* d_X, const float* d_y, int32_t n, i
   return 0;
 }
 
+// Concurrent branches of one batched call: branch 0 is the caller's stream, branches 1.. are side streams that fork
+// from it and join it again through events (inside a stream capture they become parallel branches of the graph).
+// Created and destroyed with the call: the library keeps no persistent state.
+namespace {
+struct Branches {
+  std::vector<cudaStream_t> st;
+  std::vector<cudaEvent_t> done;
+  cudaEvent_t forked = nullptr;
+  cudaStream_t main = nullptr;
+  int32_t init(int R, cudaStream_t s) {
+    main = s;
+    st.assign(R, nullptr);
+    done.assign(R, nullptr);
+    st[0] = s;
+    BX_CUDA(cudaEventCreateWithFlags(&forked, cudaEventDisableTiming));
+    for (int r = 1; r < R; ++r) {
+      BX_CUDA(cudaStreamCreateWithFlags(&st[r], cudaStreamNonBlocking));
+      BX_CUDA(cudaEventCreateWithFlags(&done[r], cudaEventDisableTiming));
+    }
+    return 0;
+  }
+  int32_t fork() {
+    BX_CUDA(cudaEventRecord(forked, main));
+    for (size_t r = 1; r < st.size(); ++r) BX_CUDA(cudaStreamWaitEvent(st[r], forked, 0));
+    return 0;
+  }
+  int32_t join() {
+    for (size_t r = 1; r < st.size(); ++r) {
+      BX_CUDA(cudaEventRecord(done[r], st[r]));
+      BX_CUDA(cudaStreamWaitEvent(main, done[r], 0));
+    }
+    return 0;
+  }
+  ~Branches() {
+    for (size_t r = 1; r < st.size(); ++r) {
+      if (done[r]) cudaEventDestroy(done[r]);
+      if (st[r]) cudaStreamDestroy(st[r]);
+    }
+    if (forked) cudaEventDestroy(forked);
+  }
+};
+}  // namespace
+
+extern "C" int32_t bx_fit_adamw_batch(const float* d_X, const float* d_y, int32_t n, int32_t d, float* d_raws, int32_t R,
+                                      float lr, int32_t steps, float* d_out, void* d_ws, size_t ws_bytes, void* stream) {
+  BX_CHECK_ARG(d_X && d_y && d_raws && d_ws, BX_E_ARG, "null pointer argument");
+  BX_CHECK_ARG(n > 0 && d > 0, BX_E_ARG, "n and d must be positive (n=%d d=%d)", n, d);
+  BX_CHECK_ARG(d <= BX_MAX_D, BX_E_RANGE, "d=%d exceeds BX_MAX_D=%d", d, BX_MAX_D);
+  BX_CHECK_ARG(R >= 1 && R <= BX_FIT_BATCH_MAX, BX_E_RANGE, "R=%d outside [1, %d]", R, BX_FIT_BATCH_MAX);
+  BX_CHECK_ARG(steps >= 0, BX_E_ARG, "steps must be >= 0");
+  const size_t slot = bx_fit_workspace_bytes(n, d);
+  BX_CHECK_ARG(ws_bytes >= slot * (size_t)R, BX_E_WORKSPACE, "workspace too small: %zu < %zu", ws_bytes, slot * (size_t)R);
+  cudaStream_t s = (cudaStream_t)stream;
+  const int P = d + 2, W = 2 + 2 * P;
+  std::vector<FitWs> w(R);
+  for (int r = 0; r < R; ++r) w[r] = carve_fit_ws(reinterpret_cast<char*>(d_ws) + slot * r, n, d);
+  Branches br;
+  int32_t rc = br.init(R, s);
+  if (rc) return rc;
+
+  if (fit_small_ok(n, d) && !getenv("BX_NO_FIT_SMALL")) {  // one launch per restart and phase, all restarts side by side
+    if ((rc = br.fork())) return rc;
+    for (int r = 0; r < R && rc == 0; ++r) {
+      if (steps > 0) rc = launch_fit_small(br.st[r], d_X, d_y, n, d, d_raws + (size_t)r * P, lr, steps, nullptr, nullptr, 0);
+      if (rc == 0 && d_out)
+        rc = launch_fit_small(br.st[r], d_X, d_y, n, d, d_raws + (size_t)r * P, 0.f, 0, nullptr, d_out + (size_t)r * W, 1);
+    }
+    const int32_t jr = br.join();
+    cudaStreamSynchronize(s);  // the side streams are destroyed on return
+    return rc ? rc : jr;
+  }
+
+  if (steps > 0) {
+    for (int r = 0; r < R; ++r)
+      BX_CUDA(cudaMemsetAsync(w[r].adam, 0, sizeof(float) * (2 * P + 1), s));  // fresh moments per call (gp.py:100)
+    // One step of ALL restarts is captured as one graph with R parallel branches and replayed `steps` times.
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    BX_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+    rc = br.fork();
+    for (int r = 0; r < R && rc == 0; ++r) {
+      rc = launch_grad(br.st[r], d_X, d_y, n, d, d_raws + (size_t)r * P, w[r]);
+      if (rc == 0) {
+        adamw_kernel<<<1, 32, 0, br.st[r]>>>(d_raws + (size_t)r * P, w[r].gbuf, d, lr, w[r].adam, nullptr, 0);
+        cudaError_t le = cudaGetLastError();
+        if (le != cudaSuccess) { set_error("adamw launch failed: %s", cudaGetErrorString(le)); rc = (int32_t)le; }
+      }
+    }
+    const int32_t jr = br.join();
+    cudaError_t ce = cudaStreamEndCapture(s, &graph);
+    if (rc == 0) rc = jr;
+    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+    BX_CUDA(ce);
+    cudaError_t e = cudaGraphInstantiate(&exec, graph, 0);
+    for (int i = 0; i < steps && e == cudaSuccess; ++i) e = cudaGraphLaunch(exec, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);  // the exec object must outlive its queued launches
+    if (exec) cudaGraphExecDestroy(exec);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) { set_error("batched fit graph failed: %s", cudaGetErrorString(e)); return (int32_t)e; }
+  }
+  if (d_out) {  // NLML, loss and gradients at the fitted hypers, again side by side
+    if ((rc = br.fork())) return rc;
+    for (int r = 0; r < R && rc == 0; ++r) {
+      rc = launch_grad(br.st[r], d_X, d_y, n, d, d_raws + (size_t)r * P, w[r]);
+      if (rc == 0) {
+        cudaError_t ce = cudaMemcpyAsync(d_out + (size_t)r * W, w[r].gbuf, sizeof(float) * W, cudaMemcpyDeviceToDevice, br.st[r]);
+        if (ce != cudaSuccess) { set_error("cudaMemcpyAsync failed: %s", cudaGetErrorString(ce)); rc = (int32_t)ce; }
+      }
+    }
+    const int32_t jr = br.join();
+    cudaStreamSynchronize(s);
+    if (rc == 0) rc = jr;
+  }
+  return rc;
+}
+
 extern "C" int32_t bx_factor_build(const float* d_X, const float* d_y, int32_t n, int32_t d, const float* d_raw,
                                    float* d_U, float* d_T, float* d_Thi, float* d_Tlo, void* d_T16hi, void* d_T16lo,
                                    float* d_alpha, float* d_scale, float* d_hyp, void* d_ws, size_t ws_bytes, void* stream) {
@@ -651,6 +773,8 @@ extern "C" int32_t bx_factor_build(const float* d_X, const float* d_y, int32_t n
   BX_CHECK_ARG((d_T16hi == nullptr) == (d_T16lo == nullptr), BX_E_ARG, "T16hi and T16lo must be given together");
   cudaStream_t s = (cudaStream_t)stream;
   FitWs w = carve_fit_ws(d_ws, n, d);
+  Lookahead la;
+  if (lookahead_wanted(w.np)) { if ((rc = la.init())) return rc; w.la = &la; }
   rc = launch_factor(s, d_X, d_y, n, d, d_raw, w, d_T, d_U, d_alpha, d_scale, d_hyp);
   if (rc) return rc;
   const size_t tot = (size_t)w.np * w.np;

@@ -38,7 +38,18 @@ int32_t gemm(cudaStream_t s, bool ta, bool tb, const GemmArgs& g, int grid_z = 1
 
 // In-place lower Cholesky of the np x np matrix A (row-major, lda); also the inverses of the 64x64 diagonal blocks
 // (Dinv [np/64][64][64]) and per-block sum(log diag) (logdet_part [np/64]).  status[0] |= 1 on a bad pivot.
-int32_t cholesky_inplace(cudaStream_t s, float* A, int np, int lda, float* Dinv, float* logdet_part, int* status);
+// `la` (optional): look-ahead.  The serial chain of a panel (potrf, panel solves, the update of the NEXT panel's columns)
+// runs on la->chain, a high-priority helper stream forked from and joined to `s`, while `s` itself carries the rest of
+// every trailing update - the chain of panel p+1 overlaps the bulk update of panel p.
+struct Lookahead {
+  cudaStream_t chain = nullptr;
+  cudaEvent_t ev_chain = nullptr, ev_bulk = nullptr;
+  int32_t init();  // created per call and destroyed on return (work still queued keeps the resources alive): no library state
+  ~Lookahead();
+};
+bool lookahead_wanted(int np);
+int32_t cholesky_inplace(cudaStream_t s, float* A, int np, int lda, float* Dinv, float* logdet_part, int* status,
+                         const Lookahead* la = nullptr);
 // In place L -> T = L^-1 (upper triangle zeroed), using Dinv from cholesky_inplace and a np x np scratch matrix.
 int32_t tri_inverse_inplace(cudaStream_t s, float* A, int np, int lda, const float* Dinv, float* TMP);
 // out = T * x (lower) and out = T^T * x
@@ -51,6 +62,7 @@ struct FitWs {
   int* status;
   int np, d4, nb, ntiles;
   size_t bytes;
+  const Lookahead* la;  // optional, set by the entry point (never by carve_fit_ws)
 };
 FitWs carve_fit_ws(void* base, int n, int d);
 

@@ -529,17 +529,46 @@ __global__ void __launch_bounds__(256) potrf_diag_kernel(float* A, int lda, int 
   }
 }
 
-int32_t cholesky_inplace(cudaStream_t s, float* A, int np, int lda, float* Dinv, float* logdet_part, int* status) {
+int32_t Lookahead::init() {
+  int least = 0, greatest = 0;
+  BX_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+  BX_CUDA(cudaStreamCreateWithPriority(&chain, cudaStreamNonBlocking, greatest));
+  BX_CUDA(cudaEventCreateWithFlags(&ev_chain, cudaEventDisableTiming));
+  BX_CUDA(cudaEventCreateWithFlags(&ev_bulk, cudaEventDisableTiming));
+  return 0;
+}
+Lookahead::~Lookahead() {
+  if (ev_chain) cudaEventDestroy(ev_chain);
+  if (ev_bulk) cudaEventDestroy(ev_bulk);
+  if (chain) cudaStreamDestroy(chain);
+}
+// Below ~2048 rows the trailing updates are a few tiles: nothing to overlap the chain with.
+bool lookahead_wanted(int np) {
+  static const int min_np = [] { const char* e = getenv("BX_CHOL_LOOKAHEAD_MIN"); return e ? atoi(e) : 2048; }();
+  return min_np > 0 && np >= min_np;
+}
+
+int32_t cholesky_inplace(cudaStream_t s, float* A, int np, int lda, float* Dinv, float* logdet_part, int* status,
+                         const Lookahead* la) {
   // Two-level right-looking blocking: 64-wide steps (potrf of the diagonal block, panel solve) are applied only inside a
   // panel of PW blocks; the trailing matrix is updated once per panel with K = 64 PW (a rank-64 update per step moves
   // the whole trailing matrix through the SMs for 64 FMAs per element: 27 TFLOP/s measured at n = 8192).
+  // With look-ahead the trailing update of panel p is split: the columns of panel p+1 are updated on the chain stream
+  // `c` right away, the rest on `s`; the bulk update of panel p-1 and the next-panel update of panel p both modify the
+  // columns of panel p+1, so the chain waits for the former (ev_bulk) before the latter.
   static const int PW = [] { const char* e = getenv("BX_CHOL_PW"); const int v = e ? atoi(e) : 2; return v < 1 ? 1 : v; }();
   const int nb = np / NB;
+  cudaStream_t c = la ? la->chain : s;
+  bool bulk_pending = false;
+  if (la) {
+    BX_CUDA(cudaEventRecord(la->ev_bulk, s));
+    BX_CUDA(cudaStreamWaitEvent(c, la->ev_bulk, 0));
+  }
   for (int k0 = 0; k0 < nb; k0 += PW) {
     const int pw = min(PW, nb - k0);
     for (int t = 0; t < pw; ++t) {
       const int k = k0 + t;
-      potrf_diag_kernel<<<1, 256, 0, s>>>(A, lda, k, Dinv, logdet_part, status);
+      potrf_diag_kernel<<<1, 256, 0, c>>>(A, lda, k, Dinv, logdet_part, status);
       BX_LAUNCH_CHECK();
       const int rem = nb - k - 1;
       if (rem == 0) break;
@@ -547,25 +576,52 @@ int32_t cholesky_inplace(cudaStream_t s, float* A, int np, int lda, float* Dinv,
       GemmArgs p{};  // panel <- panel * Dinv_k^T   (in place: each CTA owns its 64 rows x 64 cols)
       p.A = panel; p.lda = lda; p.B = Dinv + (size_t)k * NB * NB; p.ldb = NB; p.C = panel; p.ldc = lda;
       p.M = rem * NB; p.N = NB; p.K = NB; p.alpha = 1.f; p.beta = 0.f; p.kmode = KM_FULL;
-      int32_t rc = gemm(s, false, true, p);
+      int32_t rc = gemm(c, false, true, p);
       if (rc) return rc;
       const int inner = pw - 1 - t;  // block columns of this panel still to be factorised
       if (inner > 0) {
         GemmArgs u{};  // A[k+1:, k+1 : k0+pw] -= L[k+1:, k] * L[k+1 : k0+pw, k]^T
         u.A = panel; u.lda = lda; u.B = panel; u.ldb = lda; u.C = A + (size_t)(k + 1) * NB * lda + (size_t)(k + 1) * NB; u.ldc = lda;
         u.M = rem * NB; u.N = inner * NB; u.K = NB; u.alpha = -1.f; u.beta = 1.f; u.kmode = KM_FULL; u.lower_only = 1;
-        rc = gemm(s, false, true, u);
+        rc = gemm(c, false, true, u);
         if (rc) return rc;
       }
     }
     const int rem = nb - k0 - pw;
     if (rem <= 0) break;
     float* wide = A + (size_t)(k0 + pw) * NB * lda + (size_t)k0 * NB;  // L[k0+pw:, k0 : k0+pw]
+    float* trail = A + (size_t)(k0 + pw) * NB * lda + (size_t)(k0 + pw) * NB;
     GemmArgs u{};  // trailing(lower tiles) -= wide * wide^T
-    u.A = wide; u.lda = lda; u.B = wide; u.ldb = lda; u.C = A + (size_t)(k0 + pw) * NB * lda + (size_t)(k0 + pw) * NB; u.ldc = lda;
+    u.A = wide; u.lda = lda; u.B = wide; u.ldb = lda; u.C = trail; u.ldc = lda;
     u.M = rem * NB; u.N = rem * NB; u.K = pw * NB; u.alpha = -1.f; u.beta = 1.f; u.kmode = KM_FULL; u.lower_only = 1;
-    int32_t rc = gemm(s, false, true, u);
+    if (!la) {
+      int32_t rc = gemm(s, false, true, u);
+      if (rc) return rc;
+      continue;
+    }
+    const int nxt = min(PW, rem);  // block columns of the next panel
+    if (rem > nxt) BX_CUDA(cudaEventRecord(la->ev_chain, c));  // panel p is final
+    if (bulk_pending) {
+      BX_CUDA(cudaStreamWaitEvent(c, la->ev_bulk, 0));
+      bulk_pending = false;
+    }
+    u.N = nxt * NB;
+    int32_t rc = gemm(c, false, true, u);
     if (rc) return rc;
+    if (rem > nxt) {
+      BX_CUDA(cudaStreamWaitEvent(s, la->ev_chain, 0));
+      const size_t skip = (size_t)nxt * NB;
+      u.A = wide + skip * lda; u.B = u.A; u.C = trail + skip * lda + skip;
+      u.M = u.N = (rem - nxt) * NB;
+      rc = gemm(s, false, true, u);
+      if (rc) return rc;
+      BX_CUDA(cudaEventRecord(la->ev_bulk, s));
+      bulk_pending = true;
+    }
+  }
+  if (la) {
+    BX_CUDA(cudaEventRecord(la->ev_chain, c));
+    BX_CUDA(cudaStreamWaitEvent(s, la->ev_chain, 0));
   }
   return 0;
 }

@@ -128,6 +128,22 @@ class Posterior:
         self.factor = None
         return tr
 
+    def fit_hypers_batch(self, raws, lr=1e-3, steps=100):
+        """``posterior_fit`` (gp.py:90-110) from every row of ``raws`` (R, d + 2) side by side on this GPU (one CUDA
+        graph with R parallel branches per step).  Returns ``(fitted raws (R, d + 2), rows (R, 2 + 2(d + 2)))`` as host
+        arrays; ``rows[r]`` is the ``nlml_grad`` record at the fitted hypers of restart r.  ``self.raw`` is untouched."""
+        raws = np.ascontiguousarray(raws, dtype=np.float32)
+        R, P = raws.shape
+        assert P == self.d + 2 and 1 <= R <= _lib.FIT_BATCH_MAX
+        nbytes = lib.bx_fit_workspace_bytes(self.n, self.d) * R
+        ws = _workspace(self.dev, nbytes)
+        with on_stream(self.stream, self.dev):
+            d_raws = torch.from_numpy(raws).to(self.dev)
+            out = torch.empty((R, 2 + 2 * P), dtype=torch.float32, device=self.dev)
+            check(lib.bx_fit_adamw_batch(_ptr(self.X), _ptr(self.y), self.n, self.d, _ptr(d_raws), R, lr, steps, _ptr(out),
+                                         _ptr(ws), nbytes, C.c_void_p(self.stream.cuda_stream)), "bx_fit_adamw_batch")
+            return d_raws.cpu().numpy(), out.cpu().numpy()
+
     def nlml_grad(self):
         """(nlml, loss, dloss/draw, dnlml/draw) at the current raw hypers (gp.py:74-87)."""
         ws, nbytes = self._ws()

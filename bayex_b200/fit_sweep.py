@@ -10,8 +10,11 @@ from __future__ import annotations
 import numpy as np
 import torch
 
-from . import engine
+from . import _lib, engine
 from .gp import params_from_raw
+
+
+CONCURRENT_RESTARTS = 4  # restarts fitted side by side per GPU (workspace: 2 np^2 floats each)
 
 
 def shard_restarts(n_restarts: int, rank: int, world: int):
@@ -48,29 +51,34 @@ def argmin_loss(losses: np.ndarray) -> int:
     return int(np.argmin(l))
 
 
-def fit_restarts(x, y, raws, lr: float = 1e-3, trainsteps: int = 100):
+def fit_restarts(x, y, raws, lr: float = 1e-3, trainsteps: int = 100, concurrent: int = None):
     """Run ``posterior_fit`` from every row of ``raws`` ((R, d + 2): [noise, amplitude, lengthscale...] raw values) on
     the compacted observations (x (n, d), y (n,)), sharded over the ``torch.distributed`` ranks if a group is
-    initialised.  Returns ``(best GPParams, best index, table)`` with ``table[r] = [loss_r, fitted raw_r...]``; the loss
-    is ``neg_log_likelihood`` (gp.py:78-87) at the fitted hypers."""
+    initialised.  A rank fits its restarts ``concurrent`` at a time side by side on its GPU (``bx_fit_adamw_batch``;
+    default ``CONCURRENT_RESTARTS``; 1 = one after the other) - the results do not depend on it.  Returns
+    ``(best GPParams, best index, table)`` with ``table[r] = [loss_r, fitted raw_r...]``; the loss is
+    ``neg_log_likelihood`` (gp.py:78-87) at the fitted hypers."""
     import torch.distributed as tdist
     raws = np.ascontiguousarray(raws, dtype=np.float32)
     R, P = raws.shape
     d = np.asarray(x).shape[1]
     assert P == d + 2, "raws must have d + 2 columns"
+    concurrent = CONCURRENT_RESTARTS if concurrent is None else int(concurrent)
+    if not 1 <= concurrent <= _lib.FIT_BATCH_MAX:
+        raise ValueError(f"concurrent must be in [1, {_lib.FIT_BATCH_MAX}]")
     dist = tdist if (tdist.is_available() and tdist.is_initialized() and tdist.get_world_size() > 1) else None
     rank = dist.get_rank() if dist else 0
     world = dist.get_world_size() if dist else 1
     rows = {}
     post = None
-    for r in shard_restarts(R, rank, world):
+    mine = shard_restarts(R, rank, world)
+    for c0 in range(0, len(mine), concurrent):
+        chunk = mine[c0:c0 + concurrent]
         if post is None:
-            post = engine.Posterior(x, y, raws[r], want_tc=False)
-        else:
-            post.set_raw(raws[r])
-        post.fit_hypers(lr=lr, steps=trainsteps)
-        _, loss, _, _ = post.nlml_grad()
-        rows[r] = np.concatenate([[loss], post.raw_host()])
+            post = engine.Posterior(x, y, raws[chunk[0]], want_tc=False)
+        fitted, recs = post.fit_hypers_batch(raws[chunk], lr=lr, steps=trainsteps)
+        for j, r in enumerate(chunk):
+            rows[r] = np.concatenate([[recs[j, 1]], fitted[j]])
     dev = post.dev if post is not None else engine.device()
     table = gather_restart_rows(rows, R, P + 1, dist, device=dev if dist else "cpu")
     best = argmin_loss(table[:, 0])

@@ -114,6 +114,17 @@ int32_t bx_nlml_grad(const float* d_X, const float* d_y, int32_t n, int32_t d, c
 int32_t bx_fit_adamw(const float* d_X, const float* d_y, int32_t n, int32_t d, float* d_raw, float lr, int32_t steps,
                      float* d_trace, void* d_ws, size_t ws_bytes, int32_t use_graph, void* stream);
 
+#define BX_FIT_BATCH_MAX 32 /* restarts fitted side by side by one bx_fit_adamw_batch call */
+
+/* posterior_fit from R starting points side by side - replaces: R independent gp.py:90-110 posterior_fit calls on the same
+ * observations (BASELINE config 5: the hyper-parameter restart sweep).  d_raws [R x (d+2)] is updated in place.  One
+ * step of all R restarts is one CUDA graph with R parallel branches (side streams forked from and joined to `stream`),
+ * so the serial potrf / panel-solve chain of one restart overlaps with the GEMMs of the others; every restart's
+ * arithmetic is the one bx_fit_adamw does, bit for bit.  d_out (optional) [R x (2 + 2(d+2))] receives the
+ * bx_nlml_grad row at the fitted hypers of every restart.  d_ws: R * bx_fit_workspace_bytes(n, d) bytes. */
+int32_t bx_fit_adamw_batch(const float* d_X, const float* d_y, int32_t n, int32_t d, float* d_raws, int32_t R, float lr,
+                           int32_t steps, float* d_out, void* d_ws, size_t ws_bytes, void* stream);
+
 /* Posterior factor - replaces: gp.py:41-49 (softplus, centring, Gram, Cholesky, alpha) once per fit.
  * Outputs are the arrays referenced by bx_factor_t (caller allocates: U np*d4, T np*np, Thi/Tlo and T16hi/T16lo
  * optional, alpha np, scale d4, hyp 16). */

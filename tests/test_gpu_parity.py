@@ -645,6 +645,23 @@ def test_config5_restart_sweep_single_rank():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("n", [40, 300])
+def test_restarts_side_by_side_equal_one_after_the_other(n):
+    """bx_fit_adamw_batch (R parallel graph branches; n = 40 takes the one-kernel fit) gives every restart the bits of its
+    own sequential fit, whatever the number of restarts in flight."""
+    from bayex_b200 import fit_sweep
+    d, R = 3, 7
+    X, Y = _config_problem(d, n, seed=9)
+    rng = np.random.default_rng(11)
+    raws = np.concatenate([rng.uniform(-8, -2, (R, 1)), rng.uniform(-1, 1, (R, 1 + d))], axis=1).astype(np.float32)
+    _, i1, t1 = fit_sweep.fit_restarts(X, Y, raws, trainsteps=20, concurrent=1)
+    for c in (3, 7):
+        _, ic, tc = fit_sweep.fit_restarts(X, Y, raws, trainsteps=20, concurrent=c)
+        assert ic == i1 and np.array_equal(tc, t1), (c, np.abs(tc - t1).max())
+    assert np.all(np.isfinite(t1)) and not np.allclose(t1[:, 1:], raws)
+
+
+@pytest.mark.gpu
 def test_optimize_suggestion_reference_call_pattern():
     """SURVEY row a18 (optimizer.py:39-73,190-199): the reference calls _optimize_suggestion(x, partial(acq, xs=, ys=, mask=,
     gp_params=)); the replacement keeps that call and the value contract (never worse than the start, clipped)."""
