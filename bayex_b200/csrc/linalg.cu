@@ -529,6 +529,243 @@ __global__ void __launch_bounds__(256) potrf_diag_kernel(float* A, int lda, int 
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Fused block column: diagonal factorisation + panel solve in ONE launch (the serial chain of the blocked Cholesky).
+// ------------------------------------------------------------------------------------------------------------------
+// grid = nb - k CTAs.  EVERY CTA factorises the diagonal block itself - redundant but parallel, it removes the launch
+// boundary between potrf and the panel solve - and CTA b >= 1 then solves its own 64x64 block of the panel,
+// X L_kk^T = B, by forward substitution (trsm32_warp, a row of B per lane): no inverse is formed on the chain.
+// The `t` previous block columns of the same panel are applied first (left-looking inside the panel), which also
+// removes the separate rank-64 update launch:  D -= sum_j P_j P_j^T,  B -= sum_j Q_j P_j^T  with P_j = L[k][k-t+j],
+// Q_j = L[k+b][k-t+j].  CTA 0 stores L_kk to Ldiag[k] (not in place: the other CTAs still read A_kk), sum(log diag)
+// and the pivot status; diag_inverse_kernel below turns Ldiag into the block inverses off the chain, for all blocks
+// at once.  Phases (clocks, estimated from the potrf_diag stamps): load 1.5k [+ 3k per previous column] | chol32 5.5k |
+// L10 and X0 solves 3k | rank-32 updates 1k | chol32 5.5k | X1 solve 3k | store 1k  =  ~20k (10 us) against
+// 25.6k + a 5.6 us GEMM launch before.
+constexpr int LQ = 68;  // shared-memory row stride of the 64x64 tiles: 16-byte aligned rows, LDS.128 along k
+constexpr int PS_TILE = NB * LQ;
+constexpr size_t PS_SMEM = sizeof(float) * (4 * PS_TILE + 2 * 32 * LTP + 64 + 64);
+
+// C[r][c] -= sum_k A[r][k] B[c][k]   (r < NR, c < NC, k < KK; shared memory, stride LQ; 256 threads, no barrier inside)
+template <int NR, int NC, int KK>
+__device__ __forceinline__ void mm_nt_sub(float* C, const float* A, const float* B, int tid) {
+  constexpr int RI = NR / 16, CJ = NC / 16;
+  const int tr = tid >> 4, tc = tid & 15;
+  float acc[RI][CJ];
+#pragma unroll
+  for (int i = 0; i < RI; ++i)
+#pragma unroll
+    for (int j = 0; j < CJ; ++j) acc[i][j] = 0.f;
+#pragma unroll 4
+  for (int k = 0; k < KK; k += 4) {
+    float4 a[RI], b[CJ];
+#pragma unroll
+    for (int i = 0; i < RI; ++i) a[i] = *reinterpret_cast<const float4*>(A + (tr + 16 * i) * LQ + k);
+#pragma unroll
+    for (int j = 0; j < CJ; ++j) b[j] = *reinterpret_cast<const float4*>(B + (tc + 16 * j) * LQ + k);
+#pragma unroll
+    for (int i = 0; i < RI; ++i)
+#pragma unroll
+      for (int j = 0; j < CJ; ++j)
+        acc[i][j] = fmaf(a[i].x, b[j].x, fmaf(a[i].y, b[j].y, fmaf(a[i].z, b[j].z, fmaf(a[i].w, b[j].w, acc[i][j]))));
+  }
+#pragma unroll
+  for (int i = 0; i < RI; ++i)
+#pragma unroll
+    for (int j = 0; j < CJ; ++j) C[(tr + 16 * i) * LQ + tc + 16 * j] -= acc[i][j];
+}
+
+__device__ __forceinline__ void load_tile64(float* dst, const float* src, int ld, int tid) {
+  float4 v[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {  // 1024 float4, all four loads of a thread in flight together
+    const int e4 = tid + q * 256, r = e4 >> 4, c = (e4 & 15) * 4;
+    v[q] = *reinterpret_cast<const float4*>(src + (size_t)r * ld + c);
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int e4 = tid + q * 256, r = e4 >> 4, c = (e4 & 15) * 4;
+    *reinterpret_cast<float4*>(dst + r * LQ + c) = v[q];
+  }
+}
+// lane's row (32 entries starting at column c0) of a stride-LQ tile <-> registers
+__device__ __forceinline__ void row_load32(float (&a)[32], const float* row) {
+#pragma unroll
+  for (int c = 0; c < 32; c += 4) {
+    const float4 v = *reinterpret_cast<const float4*>(row + c);
+    a[c] = v.x; a[c + 1] = v.y; a[c + 2] = v.z; a[c + 3] = v.w;
+  }
+}
+__device__ __forceinline__ void row_store32(float* row, const float (&a)[32]) {
+#pragma unroll
+  for (int c = 0; c < 32; c += 4) *reinterpret_cast<float4*>(row + c) = make_float4(a[c], a[c + 1], a[c + 2], a[c + 3]);
+}
+
+__global__ void __launch_bounds__(256) potrf_solve_kernel(float* A, int lda, int k, int t, float* Ldiag, float* logdet_part,
+                                                          int* status) {
+  extern __shared__ __align__(16) float ps_smem[];
+  float* S = ps_smem;             // D -> L_kk
+  float* Bm = S + PS_TILE;        // B -> X (this CTA's block of the panel)
+  float* Pm = Bm + PS_TILE;       // staging: P_j
+  float* Qm = Pm + PS_TILE;       // staging: Q_j
+  float* LT0 = Qm + PS_TILE;      // L00^T, L11^T (stride LTP)
+  float* LT1 = LT0 + 32 * LTP;
+  float* colbuf = LT1 + 32 * LTP;  // [2][32]
+  float* rdiag = colbuf + 64;      // [64]
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(FULLW, tid >> 5, 0);  // provably warp-uniform: the role branches below stay convergent
+  const int b = blockIdx.x;                          // 0: diagonal duty only; b >= 1: row block k + b of the panel
+  const float* Dg = A + (size_t)k * NB * lda + (size_t)k * NB;
+  float* Bg = A + (size_t)(k + b) * NB * lda + (size_t)k * NB;
+  load_tile64(S, Dg, lda, tid);
+  if (b) load_tile64(Bm, Bg, lda, tid);
+  for (int j = 0; j < t; ++j) {
+    const size_t col = (size_t)(k - t + j) * NB;
+    load_tile64(Pm, A + (size_t)k * NB * lda + col, lda, tid);
+    if (b) load_tile64(Qm, A + (size_t)(k + b) * NB * lda + col, lda, tid);
+    __syncthreads();
+    mm_nt_sub<64, 64, 64>(S, Pm, Pm, tid);
+    if (b) mm_nt_sub<64, 64, 64>(Bm, Qm, Pm, tid);
+    __syncthreads();
+  }
+  __syncthreads();
+  bool bad = false;
+  // 1. D00 = L00 L00^T
+  if (warp == 0) {
+    float a[32];
+    row_load32(a, S + lane * LQ);
+#pragma unroll
+    for (int c = 0; c < 32; ++c) if (c > lane) a[c] = 0.f;
+    const float dg = chol32_warp(a, lane, colbuf, LT0, bad);
+    row_store32(S + lane * LQ, a);
+    rdiag[lane] = 1.f / dg;
+  }
+  __syncthreads();
+  // 2. L10 = D10 L00^-T (warp 2) and X0 = B[:, 0:32] L00^-T (warps 3, 4), independent
+  if (warp == 2) {
+    float x[32];
+    row_load32(x, S + (32 + lane) * LQ);
+    trsm32_warp(x, LT0, rdiag);
+    row_store32(S + (32 + lane) * LQ, x);
+  } else if (b && (warp == 3 || warp == 4)) {
+    float x[32];
+    float* row = Bm + ((warp - 3) * 32 + lane) * LQ;
+    row_load32(x, row);
+    trsm32_warp(x, LT0, rdiag);
+    row_store32(row, x);
+  }
+  __syncthreads();
+  // 3. D11 -= L10 L10^T,  B[:, 32:64] -= X0 L10^T
+  mm_nt_sub<32, 32, 32>(S + 32 * LQ + 32, S + 32 * LQ, S + 32 * LQ, tid);
+  if (b) mm_nt_sub<64, 32, 32>(Bm + 32, Bm, S + 32 * LQ, tid);
+  __syncthreads();
+  // 4. D11 = L11 L11^T
+  if (warp == 0) {
+    float a[32];
+    row_load32(a, S + (32 + lane) * LQ + 32);
+#pragma unroll
+    for (int c = 0; c < 32; ++c) if (c > lane) a[c] = 0.f;
+    const float dg = chol32_warp(a, lane, colbuf, LT1, bad);
+    row_store32(S + (32 + lane) * LQ + 32, a);
+    rdiag[32 + lane] = 1.f / dg;
+    if (bad && lane == 0 && b == 0) atomicOr(status, 1);
+  }
+  __syncthreads();
+  // 5. X1 = B[:, 32:64] L11^-T
+  if (b) {
+    if (warp == 3 || warp == 4) {
+      float x[32];
+      float* row = Bm + ((warp - 3) * 32 + lane) * LQ + 32;
+      row_load32(x, row);
+      trsm32_warp(x, LT1, rdiag + 32);
+      row_store32(row, x);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int e4 = tid + q * 256, r = e4 >> 4, c = (e4 & 15) * 4;
+      *reinterpret_cast<float4*>(Bg + (size_t)r * lda + c) = *reinterpret_cast<const float4*>(Bm + r * LQ + c);
+    }
+  } else {
+    float* ld = Ldiag + (size_t)k * NB * NB;
+    for (int e = tid; e < NB * NB; e += 256) {
+      const int r = e >> 6, c = e & 63;
+      ld[e] = (c <= r) ? S[r * LQ + c] : 0.f;
+    }
+    if (tid < 32) {
+      float l = logf(S[lane * LQ + lane]) + logf(S[(lane + 32) * LQ + lane + 32]);
+      l = warp_sum(l);
+      if (tid == 0) logdet_part[k] = l;
+    }
+  }
+}
+
+// Block inverses off the chain: Dinv[k] holds L_kk on entry (from potrf_solve_kernel) and L_kk^-1 on return; L_kk is also
+// written in place into the diagonal block of A.  One CTA per block, all blocks in one launch.
+//   T00 = L00^-1, T11 = L11^-1 (one warp each), W = L10 T00, T10 = -T11 W.
+__global__ void __launch_bounds__(256) diag_inverse_kernel(float* A, int lda, float* Dinv) {
+  __shared__ float S[NB][LP];  // L
+  __shared__ float X[NB][LP];  // L^-1
+  __shared__ float W[32][33];
+  __shared__ float rdiag[NB];
+  __shared__ __align__(16) float LT0[32 * LTP], LT1[32 * LTP];
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(FULLW, tid >> 5, 0);
+  const int kb = blockIdx.x;
+  float* dinv = Dinv + (size_t)kb * NB * NB;
+  float* blk = A + (size_t)kb * NB * lda + (size_t)kb * NB;
+  for (int e = tid; e < NB * NB; e += 256) {
+    const int r = e >> 6, c = e & 63;
+    const float v = dinv[e];
+    S[r][c] = v;
+    X[r][c] = 0.f;
+    if (c <= r) blk[(size_t)r * lda + c] = v;
+    if (r < 32 && c < 32) LT0[c * LTP + r] = v;
+    if (r >= 32 && c >= 32) LT1[(c - 32) * LTP + (r - 32)] = v;
+    if (r == c) rdiag[r] = 1.f / v;
+  }
+  __syncthreads();
+  if (warp == 1 || warp == 2) {
+    const int h = warp - 1;  // 0: T00, 1: T11
+    float x[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) x[c] = (c == lane) ? 1.f : 0.f;
+    trsm32_warp(x, h ? LT1 : LT0, rdiag + 32 * h);
+#pragma unroll
+    for (int r = 0; r < 32; ++r) X[32 * h + r][32 * h + lane] = x[r];  // x[r] = T[r][lane], zero for r < lane
+  }
+  __syncthreads();
+  {  // W = L10 T00 : warp w takes columns 4w .. 4w+3, lane = row
+    float l[32];
+#pragma unroll
+    for (int kk = 0; kk < 32; ++kk) l[kk] = S[32 + lane][kk];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int c = warp * 4 + q;
+      float acc = 0.f;
+#pragma unroll
+      for (int kk = 0; kk < 32; ++kk) acc = fmaf(l[kk], X[kk][c], acc);  // T00[kk][c] = 0 for kk < c
+      W[lane][c] = acc;
+    }
+  }
+  __syncthreads();
+  {  // T10 = -T11 W
+    float tt[32];
+#pragma unroll
+    for (int kk = 0; kk < 32; ++kk) tt[kk] = X[32 + lane][32 + kk];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int c = warp * 4 + q;
+      float acc = 0.f;
+#pragma unroll
+      for (int kk = 0; kk < 32; ++kk) acc = fmaf(tt[kk], W[kk][c], acc);
+      X[32 + lane][c] = -acc;
+    }
+  }
+  __syncthreads();
+  for (int e = tid; e < NB * NB; e += 256) dinv[e] = X[e >> 6][e & 63];
+}
+
 int32_t Lookahead::init() {
   int least = 0, greatest = 0;
   BX_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
@@ -557,9 +794,14 @@ int32_t cholesky_inplace(cudaStream_t s, float* A, int np, int lda, float* Dinv,
   // `c` right away, the rest on `s`; the bulk update of panel p-1 and the next-panel update of panel p both modify the
   // columns of panel p+1, so the chain waits for the former (ev_bulk) before the latter.
   static const int PW = [] { const char* e = getenv("BX_CHOL_PW"); const int v = e ? atoi(e) : 2; return v < 1 ? 1 : v; }();
+  static const bool fused = [] { const char* e = getenv("BX_CHOL_FUSED"); return !e || atoi(e) != 0; }();
   const int nb = np / NB;
   cudaStream_t c = la ? la->chain : s;
   bool bulk_pending = false;
+  if (fused) {
+    static const cudaError_t attr = cudaFuncSetAttribute(potrf_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PS_SMEM);
+    BX_CUDA(attr);
+  }
   if (la) {
     BX_CUDA(cudaEventRecord(la->ev_bulk, s));
     BX_CUDA(cudaStreamWaitEvent(c, la->ev_bulk, 0));
@@ -568,6 +810,11 @@ int32_t cholesky_inplace(cudaStream_t s, float* A, int np, int lda, float* Dinv,
     const int pw = min(PW, nb - k0);
     for (int t = 0; t < pw; ++t) {
       const int k = k0 + t;
+      if (fused) {  // one launch per block column: pre-update from the panel's earlier columns, potrf, panel solve
+        potrf_solve_kernel<<<nb - k, 256, PS_SMEM, c>>>(A, lda, k, t, Dinv, logdet_part, status);
+        BX_LAUNCH_CHECK();
+        continue;
+      }
       potrf_diag_kernel<<<1, 256, 0, c>>>(A, lda, k, Dinv, logdet_part, status);
       BX_LAUNCH_CHECK();
       const int rem = nb - k - 1;
@@ -622,6 +869,10 @@ int32_t cholesky_inplace(cudaStream_t s, float* A, int np, int lda, float* Dinv,
   if (la) {
     BX_CUDA(cudaEventRecord(la->ev_chain, c));
     BX_CUDA(cudaStreamWaitEvent(s, la->ev_chain, 0));
+  }
+  if (fused) {
+    diag_inverse_kernel<<<nb, 256, 0, s>>>(A, lda, Dinv);
+    BX_LAUNCH_CHECK();
   }
   return 0;
 }
