@@ -530,16 +530,31 @@ int32_t launch_factor(cudaStream_t s, const float* d_X, const float* d_y, int n,
   const size_t gsm = 2 * 32 * (d4 + 1) * sizeof(float);
   gram_kernel<<<dim3(np / 32, np / 32), 256, gsm, s>>>(U, n, np, d4, hyp, T, np);
   BX_LAUNCH_CHECK();
-  int32_t rc = cholesky_inplace(s, T, np, np, w.Dinv, w.logdet_part, w.status, w.la);
+  int32_t rc = cholesky_inplace(s, T, np, np, w.Dinv, w.logdet_part, w.status, lookahead_wanted(np) ? w.la : nullptr);
   if (rc) return rc;
   rc = tri_inverse_inplace(s, T, np, np, w.Dinv, w.TMP);
   if (rc) return rc;
-  rc = trmv_lower(s, T, np, np, w.yc, w.v);
+  // alpha = T^T (T yc) and the NLML are three latency-bound launches that need only T: with a helper stream they run
+  // beside whatever the caller queues on `s` next (K^-1 = T^T T, the operand splits); join_alpha() orders `s` after them.
+  cudaStream_t a = s;
+  if (w.la) {
+    a = w.la->chain;
+    BX_CUDA(cudaEventRecord(w.la->ev_bulk, s));
+    BX_CUDA(cudaStreamWaitEvent(a, w.la->ev_bulk, 0));
+  }
+  rc = trmv_lower(a, T, np, np, w.yc, w.v);
   if (rc) return rc;
-  rc = trmv_lower_t(s, T, np, np, w.v, alpha);
+  rc = trmv_lower_t(a, T, np, np, w.v, alpha);
   if (rc) return rc;
-  nlml_kernel<<<1, 256, 0, s>>>(w.v, np, w.logdet_part, w.nb, n, hyp, w.status);
+  nlml_kernel<<<1, 256, 0, a>>>(w.v, np, w.logdet_part, w.nb, n, hyp, w.status);
   BX_LAUNCH_CHECK();
+  if (w.la) BX_CUDA(cudaEventRecord(w.la->ev_chain, a));
+  return 0;
+}
+
+// Orders `s` after the alpha / NLML launches of launch_factor (no-op without a helper stream).
+static int32_t join_alpha(cudaStream_t s, const FitWs& w) {
+  if (w.la) BX_CUDA(cudaStreamWaitEvent(s, w.la->ev_chain, 0));
   return 0;
 }
 
@@ -552,6 +567,7 @@ static int32_t launch_grad(cudaStream_t s, const float* d_X, const float* d_y, i
   g.M = g.N = g.K = w.np; g.alpha = 1.f; g.beta = 0.f; g.kmode = KM_TN_BOTH; g.lower_only = 1;
   rc = gemm(s, true, false, g);
   if (rc) return rc;
+  if ((rc = join_alpha(s, w))) return rc;
   const size_t gsm = 2 * 32 * (w.d4 + 1) * sizeof(float);
   grad_contract_kernel<<<w.ntiles, 256, gsm, s>>>(w.TMP, w.np, w.alpha, w.U, n, d, w.d4, w.part);
   BX_LAUNCH_CHECK();
@@ -607,8 +623,8 @@ extern "C" int32_t bx_fit_adamw(const float* d_X, const float* d_y, int32_t n, i
   if (fit_small_ok(n, d) && !getenv("BX_NO_FIT_SMALL"))  // whole loop in one launch
     return launch_fit_small(s, d_X, d_y, n, d, d_raw, lr, steps, d_trace, nullptr, 0);
   BX_CUDA(cudaMemsetAsync(w.adam, 0, sizeof(float) * (2 * (d + 2) + 1), s));  // fresh moments per call (gp.py:100)
-  Lookahead la;
-  if (lookahead_wanted(w.np)) { if ((rc = la.init())) return rc; w.la = &la; }
+  Lookahead la;  // helper stream: its cost is amortised over the loop, so always
+  if (!getenv("BX_NO_HELPER_STREAM")) { if ((rc = la.init())) return rc; w.la = &la; }
   if (use_graph && !d_trace) {
     // One step is captured once and replayed `steps` times: the loop never returns to the host.
     cudaGraph_t graph = nullptr;
@@ -777,6 +793,7 @@ extern "C" int32_t bx_factor_build(const float* d_X, const float* d_y, int32_t n
   if (lookahead_wanted(w.np)) { if ((rc = la.init())) return rc; w.la = &la; }
   rc = launch_factor(s, d_X, d_y, n, d, d_raw, w, d_T, d_U, d_alpha, d_scale, d_hyp);
   if (rc) return rc;
+  if ((rc = join_alpha(s, w))) return rc;  // zero_pad_absmax_kernel below rewrites the padding of T
   const size_t tot = (size_t)w.np * w.np;
   unsigned int* amax = reinterpret_cast<unsigned int*>(w.status) + 1;  // second word of the status slot
   BX_CUDA(cudaMemsetAsync(amax, 0, sizeof(unsigned int), s));

@@ -379,6 +379,69 @@ __device__ __forceinline__ float chol32_warp(float (&a)[32], int lane, float* cs
   }
   return diag;  // l_ii of this lane's row
 }
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float rsqrt_approx(float x) {
+  float r;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+// Same contract as chol32_warp, two columns per shared-memory round trip (16 instead of 32 publish -> __syncwarp -> read
+// chains; measured 4.0k clocks per 32x32 block against 5.5k): both raw columns j, j+1 are published together; every lane rebuilds column j+1 as it is after the column-j
+// update (w_c = a_c,j+1 - a_c,j e / d0, e = a_j+1,j) and applies both rank-1 updates.  The update factors come from
+// rcp + one Newton step (a shorter dependent chain than rsqrt -> square); the rsqrt for the entries of L is off the chain.
+// cs = [2][2][32] floats.
+__device__ __forceinline__ float chol32_warp2(float (&a)[32], int lane, float* cs, float* LT, bool& bad) {
+  float diag = 1.f;
+#pragma unroll
+  for (int j = 0; j < 32; j += 2) {
+    float* cA = cs + ((j >> 1) & 1) * 64;
+    float* cB = cA + 32;
+    cA[lane] = a[j];
+    cB[lane] = a[j + 1];
+    __syncwarp();
+    float va[32], vb[32];
+#pragma unroll
+    for (int c4 = (j + 2) & ~3; c4 < 32; c4 += 4) {
+      const float4 u = *reinterpret_cast<const float4*>(cA + c4);
+      const float4 v = *reinterpret_cast<const float4*>(cB + c4);
+      va[c4] = u.x; va[c4 + 1] = u.y; va[c4 + 2] = u.z; va[c4 + 3] = u.w;
+      vb[c4] = v.x; vb[c4 + 1] = v.y; vb[c4 + 2] = v.z; vb[c4 + 3] = v.w;
+    }
+    // (fetching this 2x2 pivot block by warp shuffle instead was measured: no faster)
+    const float2 de = *reinterpret_cast<const float2*>(cA + j);  // pivot of column j, a_j+1,j
+    const float d0 = de.x, e = de.y, d1raw = cB[j + 1];
+    float r0 = rcp_approx(d0);
+    r0 = r0 * fmaf(-d0, r0, 2.f);
+    const float m = e * r0;
+    const float d1 = fmaf(-m, e, d1raw);  // pivot of column j+1 (the same operation lane j+1 applies to its own entry)
+    float r1 = rcp_approx(d1);
+    r1 = r1 * fmaf(-d1, r1, 2.f);
+    if (!(d0 > 0.f) || !(d0 < CUDART_INF_F) || !(d1 > 0.f) || !(d1 < CUDART_INF_F)) bad = true;
+    const float f0 = a[j] * r0;
+    const float a1 = fmaf(-f0, e, a[j + 1]);
+    const float f1 = a1 * r1;
+#pragma unroll
+    for (int c = j + 2; c < 32; ++c) {
+      const float w = fmaf(-va[c], m, vb[c]);
+      a[c] = fmaf(-f1, w, fmaf(-f0, va[c], a[c]));
+    }
+    float rs0 = rsqrt_approx(d0), rs1 = rsqrt_approx(d1);
+    rs0 = rs0 * fmaf(-0.5f * d0, rs0 * rs0, 1.5f);  // one Newton step: full fp32 accuracy
+    rs1 = rs1 * fmaf(-0.5f * d1, rs1 * rs1, 1.5f);
+    const float l0 = a[j] * rs0, l1 = a1 * rs1;  // lanes j / j+1 hold d0 / d1 there: l_jj = d rsqrt(d)
+    a[j] = l0;
+    a[j + 1] = l1;
+    LT[j * LTP + lane] = l0;  // column j of L as a contiguous row: the triangular solves read it as broadcast LDS.128
+    LT[(j + 1) * LTP + lane] = l1;
+    if (lane == j) diag = l0;
+    if (lane == j + 1) diag = l1;
+  }
+  return diag;  // l_ii of this lane's row
+}
 // lane r holds row r of B; solves X L^T = B in place.  LT = L^T (row j = column j of L, stride LTP) in shared memory,
 // rdiag = 1 / diag(L).  With B = identity this gives row r of L^-T = column r of L^-1.
 __device__ __forceinline__ void trsm32_warp(float (&b)[32], const float* LT, const float* rdiag) {
@@ -539,12 +602,13 @@ __global__ void __launch_bounds__(256) potrf_diag_kernel(float* A, int lda, int 
 // removes the separate rank-64 update launch:  D -= sum_j P_j P_j^T,  B -= sum_j Q_j P_j^T  with P_j = L[k][k-t+j],
 // Q_j = L[k+b][k-t+j].  CTA 0 stores L_kk to Ldiag[k] (not in place: the other CTAs still read A_kk), sum(log diag)
 // and the pivot status; diag_inverse_kernel below turns Ldiag into the block inverses off the chain, for all blocks
-// at once.  Phases (clocks, estimated from the potrf_diag stamps): load 1.5k [+ 3k per previous column] | chol32 5.5k |
-// L10 and X0 solves 3k | rank-32 updates 1k | chol32 5.5k | X1 solve 3k | store 1k  =  ~20k (10 us) against
-// 25.6k + a 5.6 us GEMM launch before.
+// at once.  Measured phase clocks of one CTA (scripts/dev/bench_potrf_solve.cu, B200): load 1.7k | chol32 4.0k | L10 / X0
+// solves + rank-32 updates 4.0k | chol32 3.4-4.0k | X1 solve + store 1.9k = 14.9k (7.6 us); a previous column of the
+// panel adds 9.2k (two 64^3 products on one SM: FMA-issue-bound) - against potrf_diag 25.6k + a 5.6 us GEMM launch
+// (+ another for the in-panel update) before.
 constexpr int LQ = 68;  // shared-memory row stride of the 64x64 tiles: 16-byte aligned rows, LDS.128 along k
 constexpr int PS_TILE = NB * LQ;
-constexpr size_t PS_SMEM = sizeof(float) * (4 * PS_TILE + 2 * 32 * LTP + 64 + 64);
+constexpr size_t PS_SMEM = sizeof(float) * (4 * PS_TILE + 2 * 32 * LTP + 128 + 64);
 
 // C[r][c] -= sum_k A[r][k] B[c][k]   (r < NR, c < NC, k < KK; shared memory, stride LQ; 256 threads, no barrier inside)
 template <int NR, int NC, int KK>
@@ -601,6 +665,12 @@ __device__ __forceinline__ void row_store32(float* row, const float (&a)[32]) {
   for (int c = 0; c < 32; c += 4) *reinterpret_cast<float4*>(row + c) = make_float4(a[c], a[c + 1], a[c + 2], a[c + 3]);
 }
 
+#ifdef BX_PS_STAMPS  // scripts/dev/bench_potrf_solve.cu: clock64 at the phase boundaries of CTA 1
+__device__ long long bx_ps_stamps[8];
+#define PS_STAMP(i) do { if (threadIdx.x == 0 && blockIdx.x == 1) bx_ps_stamps[i] = clock64(); } while (0)
+#else
+#define PS_STAMP(i)
+#endif
 __global__ void __launch_bounds__(256) potrf_solve_kernel(float* A, int lda, int k, int t, float* Ldiag, float* logdet_part,
                                                           int* status) {
   extern __shared__ __align__(16) float ps_smem[];
@@ -610,11 +680,12 @@ __global__ void __launch_bounds__(256) potrf_solve_kernel(float* A, int lda, int
   float* Qm = Pm + PS_TILE;       // staging: Q_j
   float* LT0 = Qm + PS_TILE;      // L00^T, L11^T (stride LTP)
   float* LT1 = LT0 + 32 * LTP;
-  float* colbuf = LT1 + 32 * LTP;  // [2][32]
-  float* rdiag = colbuf + 64;      // [64]
+  float* colbuf = LT1 + 32 * LTP;  // [2][2][32]
+  float* rdiag = colbuf + 128;     // [64]
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(FULLW, tid >> 5, 0);  // provably warp-uniform: the role branches below stay convergent
   const int b = blockIdx.x;                          // 0: diagonal duty only; b >= 1: row block k + b of the panel
+  PS_STAMP(0);
   const float* Dg = A + (size_t)k * NB * lda + (size_t)k * NB;
   float* Bg = A + (size_t)(k + b) * NB * lda + (size_t)k * NB;
   load_tile64(S, Dg, lda, tid);
@@ -629,6 +700,7 @@ __global__ void __launch_bounds__(256) potrf_solve_kernel(float* A, int lda, int
     __syncthreads();
   }
   __syncthreads();
+  PS_STAMP(1);
   bool bad = false;
   // 1. D00 = L00 L00^T
   if (warp == 0) {
@@ -636,11 +708,12 @@ __global__ void __launch_bounds__(256) potrf_solve_kernel(float* A, int lda, int
     row_load32(a, S + lane * LQ);
 #pragma unroll
     for (int c = 0; c < 32; ++c) if (c > lane) a[c] = 0.f;
-    const float dg = chol32_warp(a, lane, colbuf, LT0, bad);
+    const float dg = chol32_warp2(a, lane, colbuf, LT0, bad);
     row_store32(S + lane * LQ, a);
     rdiag[lane] = 1.f / dg;
   }
   __syncthreads();
+  PS_STAMP(2);
   // 2. L10 = D10 L00^-T (warp 2) and X0 = B[:, 0:32] L00^-T (warps 3, 4), independent
   if (warp == 2) {
     float x[32];
@@ -655,22 +728,25 @@ __global__ void __launch_bounds__(256) potrf_solve_kernel(float* A, int lda, int
     row_store32(row, x);
   }
   __syncthreads();
+  PS_STAMP(3);
   // 3. D11 -= L10 L10^T,  B[:, 32:64] -= X0 L10^T
   mm_nt_sub<32, 32, 32>(S + 32 * LQ + 32, S + 32 * LQ, S + 32 * LQ, tid);
   if (b) mm_nt_sub<64, 32, 32>(Bm + 32, Bm, S + 32 * LQ, tid);
   __syncthreads();
+  PS_STAMP(4);
   // 4. D11 = L11 L11^T
   if (warp == 0) {
     float a[32];
     row_load32(a, S + (32 + lane) * LQ + 32);
 #pragma unroll
     for (int c = 0; c < 32; ++c) if (c > lane) a[c] = 0.f;
-    const float dg = chol32_warp(a, lane, colbuf, LT1, bad);
+    const float dg = chol32_warp2(a, lane, colbuf, LT1, bad);
     row_store32(S + (32 + lane) * LQ + 32, a);
     rdiag[32 + lane] = 1.f / dg;
     if (bad && lane == 0 && b == 0) atomicOr(status, 1);
   }
   __syncthreads();
+  PS_STAMP(5);
   // 5. X1 = B[:, 32:64] L11^-T
   if (b) {
     if (warp == 3 || warp == 4) {
@@ -681,6 +757,7 @@ __global__ void __launch_bounds__(256) potrf_solve_kernel(float* A, int lda, int
       row_store32(row, x);
     }
     __syncthreads();
+    PS_STAMP(6);
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const int e4 = tid + q * 256, r = e4 >> 4, c = (e4 & 15) * 4;
@@ -698,6 +775,7 @@ __global__ void __launch_bounds__(256) potrf_solve_kernel(float* A, int lda, int
       if (tid == 0) logdet_part[k] = l;
     }
   }
+  PS_STAMP(7);
 }
 
 // Block inverses off the chain: Dinv[k] holds L_kk on entry (from potrf_solve_kernel) and L_kk^-1 on return; L_kk is also

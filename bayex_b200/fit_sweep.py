@@ -14,7 +14,11 @@ from . import _lib, engine
 from .gp import params_from_raw
 
 
-CONCURRENT_RESTARTS = 4  # restarts fitted side by side per GPU (workspace: 2 np^2 floats each)
+def concurrent_restarts(n: int) -> int:
+    """Restarts fitted side by side per GPU by default (workspace: ~2 np^2 floats each).  Measured on one B200 (32
+    restarts x 100 steps): n = 1024 1.85 s one after the other -> 0.29 / 0.22 / 0.20 s at 8 / 16 / 32 in flight; n = 4096
+    (8 restarts) 3.19 -> 1.58 s at 8, no further gain at 16; n = 8192 (4 restarts) 7.0 -> 5.3 s at 4."""
+    return 32 if n <= 1024 else 16 if n <= 2048 else 8
 
 
 def shard_restarts(n_restarts: int, rank: int, world: int):
@@ -55,7 +59,7 @@ def fit_restarts(x, y, raws, lr: float = 1e-3, trainsteps: int = 100, concurrent
     """Run ``posterior_fit`` from every row of ``raws`` ((R, d + 2): [noise, amplitude, lengthscale...] raw values) on
     the compacted observations (x (n, d), y (n,)), sharded over the ``torch.distributed`` ranks if a group is
     initialised.  A rank fits its restarts ``concurrent`` at a time side by side on its GPU (``bx_fit_adamw_batch``;
-    default ``CONCURRENT_RESTARTS``; 1 = one after the other) - the results do not depend on it.  Returns
+    default ``concurrent_restarts(n)``; 1 = one after the other) - the results do not depend on it.  Returns
     ``(best GPParams, best index, table)`` with ``table[r] = [loss_r, fitted raw_r...]``; the loss is
     ``neg_log_likelihood`` (gp.py:78-87) at the fitted hypers."""
     import torch.distributed as tdist
@@ -63,7 +67,7 @@ def fit_restarts(x, y, raws, lr: float = 1e-3, trainsteps: int = 100, concurrent
     R, P = raws.shape
     d = np.asarray(x).shape[1]
     assert P == d + 2, "raws must have d + 2 columns"
-    concurrent = CONCURRENT_RESTARTS if concurrent is None else int(concurrent)
+    concurrent = concurrent_restarts(np.asarray(x).shape[0]) if concurrent is None else int(concurrent)
     if not 1 <= concurrent <= _lib.FIT_BATCH_MAX:
         raise ValueError(f"concurrent must be in [1, {_lib.FIT_BATCH_MAX}]")
     dist = tdist if (tdist.is_available() and tdist.is_initialized() and tdist.get_world_size() > 1) else None

@@ -19,7 +19,7 @@ from bayex_b200 import fit_sweep
 
 sizes = [int(a) for a in sys.argv[1:]] or [1024, 4096, 8192]
 d, R, steps = 8, int(os.environ.get("BX_C5_RESTARTS", "32")), 100
-conc = [int(c) for c in os.environ.get("BX_C5_CONCURRENT", str(fit_sweep.CONCURRENT_RESTARTS)).split(",")]
+conc = [int(c) for c in os.environ["BX_C5_CONCURRENT"].split(",")] if "BX_C5_CONCURRENT" in os.environ else [None]
 out = {}
 for n, C in [(n, c) for n in sizes for c in conc]:
     rng = np.random.default_rng(5)
@@ -27,7 +27,7 @@ for n, C in [(n, c) for n in sizes for c in conc]:
     centres = rng.uniform(0.2, 0.8, (3, d))
     Y = sum(np.exp(-np.sum((X - c) ** 2, axis=1) / 0.1) for c in centres) + 0.01 * rng.standard_normal(n)
     raws = np.concatenate([rng.uniform(-8, -2, (R, 1)), rng.uniform(-1, 1, (R, 1 + d))], axis=1).astype(np.float32)
-    fit_sweep.fit_restarts(X, Y.astype(np.float32), raws[:world * C], trainsteps=2, concurrent=C)  # warm-up: allocations, graph capture
+    fit_sweep.fit_restarts(X, Y.astype(np.float32), raws[:world * (C or 4)], trainsteps=2, concurrent=C)  # warm-up: allocations, graph capture
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -39,7 +39,7 @@ for n, C in [(n, c) for n in sizes for c in conc]:
     dt = time.perf_counter() - t0
     if rank == 0:
         flops = R * steps * (float(n) ** 3 + float(n) * n * (3 * d + 4))  # F_step ~ n^3
-        out[f"n{n}_c{C}"] = dict(n_gpus=world, concurrent=C, restarts=R, steps=steps, sweep_s=dt, restarts_per_s=R / dt, fit_steps_per_s=R * steps / dt,
+        out[f"n{n}_c{C}"] = dict(n_gpus=world, concurrent=C or fit_sweep.concurrent_restarts(n), restarts=R, steps=steps, sweep_s=dt, restarts_per_s=R / dt, fit_steps_per_s=R * steps / dt,
                             algorithmic_tflops=flops / dt / 1e12, best_restart=idx, best_loss=float(table[idx, 0]),
                             finite_losses=int(np.isfinite(table[:, 0]).sum()))
         print(n, out[f"n{n}_c{C}"], flush=True)

@@ -1,0 +1,41 @@
+// Phase clocks and launch time of potrf_solve_kernel (the chain element of the blocked Cholesky).
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 --expt-relaxed-constexpr -I include -o bayex_b200/csrc/build/bench_potrf_solve scripts/dev/bench_potrf_solve.cu
+#define BX_PS_STAMPS
+#include "../../bayex_b200/csrc/linalg.cu"
+#include <cstdio>
+#include <vector>
+using namespace bx;
+int main() {
+  const int np = 512, nb = np / NB;
+  std::vector<float> h((size_t)np * np);
+  for (int i = 0; i < np; ++i)
+    for (int j = 0; j < np; ++j) h[(size_t)i * np + j] = (i == j ? 2.0f : 0.f) + 0.5f * expf(-0.001f * (i - j) * (i - j));
+  float *A, *A0, *Ld, *logdet; int* status;
+  cudaMalloc(&A, h.size() * 4); cudaMalloc(&A0, h.size() * 4); cudaMalloc(&Ld, (size_t)nb * NB * NB * 4);
+  cudaMalloc(&logdet, nb * 4); cudaMalloc(&status, 8);
+  cudaMemcpy(A0, h.data(), h.size() * 4, cudaMemcpyHostToDevice);
+  cudaMemset(status, 0, 8);
+  cudaFuncSetAttribute(potrf_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PS_SMEM);
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  for (int t = 0; t < 2; ++t) {
+    float best = 1e9f;
+    long long st[8];
+    for (int rep = 0; rep < 20; ++rep) {
+      cudaMemcpy(A, A0, h.size() * 4, cudaMemcpyDeviceToDevice);
+      if (t == 1) potrf_solve_kernel<<<nb, 256, PS_SMEM>>>(A, np, 0, 0, Ld, logdet, status);
+      cudaDeviceSynchronize();
+      cudaEventRecord(e0);
+      potrf_solve_kernel<<<nb - t, 256, PS_SMEM>>>(A, np, t, t, Ld, logdet, status);
+      cudaEventRecord(e1); cudaEventSynchronize(e1);
+      float ms; cudaEventElapsedTime(&ms, e0, e1); best = fminf(best, ms);
+    }
+    cudaMemcpyFromSymbol(st, bx_ps_stamps, sizeof(st));
+    printf("t=%d launch %.2f us; phase clocks:", t, best * 1e3f);
+    const char* nm[7] = {"load+preupdate", "chol32", "trsm L10/X0", "rank-32 updates", "chol32", "trsm X1", "store"};
+    for (int i = 0; i < 7; ++i) printf(" %s %lld |", nm[i], st[i + 1] - st[i]);
+    printf(" total %lld\n", st[7] - st[0]);
+  }
+  int hs[2]; cudaMemcpy(hs, status, 8, cudaMemcpyDeviceToHost);
+  printf("status %d err %s\n", hs[0], cudaGetErrorString(cudaGetLastError()));
+  return 0;
+}
