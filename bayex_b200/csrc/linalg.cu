@@ -390,8 +390,8 @@ __device__ __forceinline__ float rsqrt_approx(float x) {
   return r;
 }
 // Same contract as chol32_warp, two columns per shared-memory round trip (16 instead of 32 publish -> __syncwarp -> read
-// chains; measured 4.0k clocks per 32x32 block against 5.5k): both raw columns j, j+1 are published together; every lane rebuilds column j+1 as it is after the column-j
-// update (w_c = a_c,j+1 - a_c,j e / d0, e = a_j+1,j) and applies both rank-1 updates.  The update factors come from
+// chains; measured 4.0k clocks per 32x32 block against 5.5k): both raw columns j, j+1 are published together; every lane folds the column-j update of column j+1
+// (w_c = a_c,j+1 - a_c,j e / d0, e = a_j+1,j) into the factors and applies both rank-1 updates with two FMAs per entry.  The update factors come from
 // rcp + one Newton step (a shorter dependent chain than rsqrt -> square); the rsqrt for the entries of L is off the chain.
 // cs = [2][2][32] floats.
 __device__ __forceinline__ float chol32_warp2(float (&a)[32], int lane, float* cs, float* LT, bool& bad) {
@@ -424,11 +424,9 @@ __device__ __forceinline__ float chol32_warp2(float (&a)[32], int lane, float* c
     const float f0 = a[j] * r0;
     const float a1 = fmaf(-f0, e, a[j + 1]);
     const float f1 = a1 * r1;
+    const float g0 = fmaf(-f1, m, f0);  // a_c -= f0 va_c + f1 (vb_c - m va_c)  =  g0 va_c + f1 vb_c : two FMAs per entry
 #pragma unroll
-    for (int c = j + 2; c < 32; ++c) {
-      const float w = fmaf(-va[c], m, vb[c]);
-      a[c] = fmaf(-f1, w, fmaf(-f0, va[c], a[c]));
-    }
+    for (int c = j + 2; c < 32; ++c) a[c] = fmaf(-f1, vb[c], fmaf(-g0, va[c], a[c]));
     float rs0 = rsqrt_approx(d0), rs1 = rsqrt_approx(d1);
     rs0 = rs0 * fmaf(-0.5f * d0, rs0 * rs0, 1.5f);  // one Newton step: full fp32 accuracy
     rs1 = rs1 * fmaf(-0.5f * d1, rs1 * rs1, 1.5f);
@@ -602,8 +600,8 @@ __global__ void __launch_bounds__(256) potrf_diag_kernel(float* A, int lda, int 
 // removes the separate rank-64 update launch:  D -= sum_j P_j P_j^T,  B -= sum_j Q_j P_j^T  with P_j = L[k][k-t+j],
 // Q_j = L[k+b][k-t+j].  CTA 0 stores L_kk to Ldiag[k] (not in place: the other CTAs still read A_kk), sum(log diag)
 // and the pivot status; diag_inverse_kernel below turns Ldiag into the block inverses off the chain, for all blocks
-// at once.  Measured phase clocks of one CTA (scripts/dev/bench_potrf_solve.cu, B200): load 1.7k | chol32 4.0k | L10 / X0
-// solves + rank-32 updates 4.0k | chol32 3.4-4.0k | X1 solve + store 1.9k = 14.9k (7.6 us); a previous column of the
+// at once.  Measured phase clocks of one CTA (scripts/dev/bench_potrf_solve.cu, B200): load 1.6k | chol32 3.3-4.0k | L10 / X0
+// solves + rank-32 updates 3.9k | chol32 3.5-4.0k | X1 solve 2.0k | store 0.3k = 14.6k (7.4 us); a previous column of the
 // panel adds 9.2k (two 64^3 products on one SM: FMA-issue-bound) - against potrf_diag 25.6k + a 5.6 us GEMM launch
 // (+ another for the in-panel update) before.
 constexpr int LQ = 68;  // shared-memory row stride of the 64x64 tiles: 16-byte aligned rows, LDS.128 along k
@@ -666,7 +664,7 @@ __device__ __forceinline__ void row_store32(float* row, const float (&a)[32]) {
 }
 
 #ifdef BX_PS_STAMPS  // scripts/dev/bench_potrf_solve.cu: clock64 at the phase boundaries of CTA 1
-__device__ long long bx_ps_stamps[8];
+__device__ long long bx_ps_stamps[8];  // 0 start | 1 loaded | 2 chol | 3 solves + updates | 4 chol | 5 solves | 6 stored
 #define PS_STAMP(i) do { if (threadIdx.x == 0 && blockIdx.x == 1) bx_ps_stamps[i] = clock64(); } while (0)
 #else
 #define PS_STAMP(i)
@@ -678,9 +676,8 @@ __global__ void __launch_bounds__(256) potrf_solve_kernel(float* A, int lda, int
   float* Bm = S + PS_TILE;        // B -> X (this CTA's block of the panel)
   float* Pm = Bm + PS_TILE;       // staging: P_j
   float* Qm = Pm + PS_TILE;       // staging: Q_j
-  float* LT0 = Qm + PS_TILE;      // L00^T, L11^T (stride LTP)
-  float* LT1 = LT0 + 32 * LTP;
-  float* colbuf = LT1 + 32 * LTP;  // [2][2][32]
+  float* LT0 = Qm + PS_TILE;      // L00^T, then L11^T (stride LTP)
+  float* colbuf = LT0 + 2 * 32 * LTP;  // [2][2][32]
   float* rdiag = colbuf + 128;     // [64]
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(FULLW, tid >> 5, 0);  // provably warp-uniform: the role branches below stay convergent
@@ -702,62 +699,47 @@ __global__ void __launch_bounds__(256) potrf_solve_kernel(float* A, int lda, int
   __syncthreads();
   PS_STAMP(1);
   bool bad = false;
-  // 1. D00 = L00 L00^T
-  if (warp == 0) {
-    float a[32];
-    row_load32(a, S + lane * LQ);
+  // Both halves of the 2x2 blocking go through the SAME straight-line warp code (a rolled loop over `half` with
+  // run-time pointers): the kernel shrinks from 7.0k to 3.6k SASS instructions (112 -> 58 KB of code every CTA has to
+  // fetch once), worth 4-6 % of a fit step; the phase clocks themselves did not move, so the warp code is bound by its
+  // dependent chain, not by instruction fetch.
+#pragma unroll 1
+  for (int half = 0; half < 2; ++half) {
+    float* Dh = S + half * (32 * LQ + 32);  // D00 / D11
+    float* LTh = LT0 + half * (32 * LTP);   // L00^T / L11^T (LT1 follows LT0)
+    float* rdh = rdiag + 32 * half;
+    if (warp == 0) {  // D_hh = L_hh L_hh^T
+      float a[32];
+      row_load32(a, Dh + lane * LQ);
 #pragma unroll
-    for (int c = 0; c < 32; ++c) if (c > lane) a[c] = 0.f;
-    const float dg = chol32_warp2(a, lane, colbuf, LT0, bad);
-    row_store32(S + lane * LQ, a);
-    rdiag[lane] = 1.f / dg;
-  }
-  __syncthreads();
-  PS_STAMP(2);
-  // 2. L10 = D10 L00^-T (warp 2) and X0 = B[:, 0:32] L00^-T (warps 3, 4), independent
-  if (warp == 2) {
-    float x[32];
-    row_load32(x, S + (32 + lane) * LQ);
-    trsm32_warp(x, LT0, rdiag);
-    row_store32(S + (32 + lane) * LQ, x);
-  } else if (b && (warp == 3 || warp == 4)) {
-    float x[32];
-    float* row = Bm + ((warp - 3) * 32 + lane) * LQ;
-    row_load32(x, row);
-    trsm32_warp(x, LT0, rdiag);
-    row_store32(row, x);
-  }
-  __syncthreads();
-  PS_STAMP(3);
-  // 3. D11 -= L10 L10^T,  B[:, 32:64] -= X0 L10^T
-  mm_nt_sub<32, 32, 32>(S + 32 * LQ + 32, S + 32 * LQ, S + 32 * LQ, tid);
-  if (b) mm_nt_sub<64, 32, 32>(Bm + 32, Bm, S + 32 * LQ, tid);
-  __syncthreads();
-  PS_STAMP(4);
-  // 4. D11 = L11 L11^T
-  if (warp == 0) {
-    float a[32];
-    row_load32(a, S + (32 + lane) * LQ + 32);
-#pragma unroll
-    for (int c = 0; c < 32; ++c) if (c > lane) a[c] = 0.f;
-    const float dg = chol32_warp2(a, lane, colbuf, LT1, bad);
-    row_store32(S + (32 + lane) * LQ + 32, a);
-    rdiag[32 + lane] = 1.f / dg;
-    if (bad && lane == 0 && b == 0) atomicOr(status, 1);
-  }
-  __syncthreads();
-  PS_STAMP(5);
-  // 5. X1 = B[:, 32:64] L11^-T
-  if (b) {
-    if (warp == 3 || warp == 4) {
-      float x[32];
-      float* row = Bm + ((warp - 3) * 32 + lane) * LQ + 32;
-      row_load32(x, row);
-      trsm32_warp(x, LT1, rdiag + 32);
-      row_store32(row, x);
+      for (int c = 0; c < 32; ++c) if (c > lane) a[c] = 0.f;
+      const float dg = chol32_warp2(a, lane, colbuf, LTh, bad);
+      row_store32(Dh + lane * LQ, a);
+      rdh[lane] = 1.f / dg;
     }
     __syncthreads();
-    PS_STAMP(6);
+    PS_STAMP(2 + 2 * half);
+    {  // forward substitution against L_hh: L10 = D10 L00^-T (warp 2, first half), X_h = B_h L_hh^-T (warps 3, 4)
+      float* row = nullptr;
+      if (warp == 2 && half == 0) row = S + (32 + lane) * LQ;
+      else if (b && (warp == 3 || warp == 4)) row = Bm + ((warp - 3) * 32 + lane) * LQ + 32 * half;
+      if (row) {
+        float x[32];
+        row_load32(x, row);
+        trsm32_warp(x, LTh, rdh);
+        row_store32(row, x);
+      }
+    }
+    __syncthreads();
+    if (half == 0) {  // D11 -= L10 L10^T,  B[:, 32:64] -= X0 L10^T
+      mm_nt_sub<32, 32, 32>(S + 32 * LQ + 32, S + 32 * LQ, S + 32 * LQ, tid);
+      if (b) mm_nt_sub<64, 32, 32>(Bm + 32, Bm, S + 32 * LQ, tid);
+      __syncthreads();
+    }
+    PS_STAMP(3 + 2 * half);
+  }
+  if (warp == 0 && bad && lane == 0 && b == 0) atomicOr(status, 1);
+  if (b) {
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const int e4 = tid + q * 256, r = e4 >> 4, c = (e4 & 15) * 4;
@@ -775,7 +757,7 @@ __global__ void __launch_bounds__(256) potrf_solve_kernel(float* A, int lda, int
       if (tid == 0) logdet_part[k] = l;
     }
   }
-  PS_STAMP(7);
+  PS_STAMP(6);
 }
 
 // Block inverses off the chain: Dinv[k] holds L_kk on entry (from potrf_solve_kernel) and L_kk^-1 on return; L_kk is also
