@@ -530,7 +530,7 @@ int32_t launch_factor(cudaStream_t s, const float* d_X, const float* d_y, int n,
   const size_t gsm = 2 * 32 * (d4 + 1) * sizeof(float);
   gram_kernel<<<dim3(np / 32, np / 32), 256, gsm, s>>>(U, n, np, d4, hyp, T, np);
   BX_LAUNCH_CHECK();
-  int32_t rc = cholesky_inplace(s, T, np, np, w.Dinv, w.logdet_part, w.status, lookahead_wanted(np) ? w.la : nullptr);
+  int32_t rc = cholesky_inplace(s, T, np, np, w.Dinv, w.logdet_part, w.status, lookahead_wanted(np) ? w.la : nullptr, w.TMP);
   if (rc) return rc;
   rc = tri_inverse_inplace(s, T, np, np, w.Dinv, w.TMP);
   if (rc) return rc;

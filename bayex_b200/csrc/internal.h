@@ -48,8 +48,9 @@ struct Lookahead {
   ~Lookahead();
 };
 bool lookahead_wanted(int np);
+// `scratch` (optional, (np/128 + 1) * 4096 floats): lets the first column of a panel also update the second one.
 int32_t cholesky_inplace(cudaStream_t s, float* A, int np, int lda, float* Dinv, float* logdet_part, int* status,
-                         const Lookahead* la = nullptr);
+                         const Lookahead* la = nullptr, float* scratch = nullptr);
 // In place L -> T = L^-1 (upper triangle zeroed), using Dinv from cholesky_inplace and a np x np scratch matrix.
 int32_t tri_inverse_inplace(cudaStream_t s, float* A, int np, int lda, const float* Dinv, float* TMP);
 // out = T * x (lower) and out = T^T * x

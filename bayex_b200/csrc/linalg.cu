@@ -669,8 +669,8 @@ __device__ long long bx_ps_stamps[8];  // 0 start | 1 loaded | 2 chol | 3 solves
 #else
 #define PS_STAMP(i)
 #endif
-__global__ void __launch_bounds__(256) potrf_solve_kernel(float* A, int lda, int k, int t, float* Ldiag, float* logdet_part,
-                                                          int* status) {
+__global__ void __launch_bounds__(256) potrf_solve_kernel(float* A, int lda, int k, int t, int next, float* Ldiag,
+                                                          float* Xnext, float* logdet_part, int* status) {
   extern __shared__ __align__(16) float ps_smem[];
   float* S = ps_smem;             // D -> L_kk
   float* Bm = S + PS_TILE;        // B -> X (this CTA's block of the panel)
@@ -687,6 +687,16 @@ __global__ void __launch_bounds__(256) potrf_solve_kernel(float* A, int lda, int
   float* Bg = A + (size_t)(k + b) * NB * lda + (size_t)k * NB;
   load_tile64(S, Dg, lda, tid);
   if (b) load_tile64(Bm, Bg, lda, tid);
+  // next = 1 (first column of a two-column panel, t = 0): CTA b also applies this column's update to its block of column
+  // k + 1, A[k+b][k+1] -= X_b X_1^T (b = 1: the next diagonal block), so the launch for column k + 1 starts without
+  // any pre-update (9.2k clocks there against ~3.5k here).  X_1 = A[k+1][k] L_kk^-T is another CTA's result: every CTA
+  // recomputes it from the raw block on two otherwise idle warps - which is why CTA 1 must not overwrite the raw block
+  // while a late-starting CTA may still read it: X_1 goes to `Xnext`, diag_inverse_kernel copies it into place.
+  const bool fn = next && b;
+  if (fn) {
+    load_tile64(Pm, A + (size_t)(k + 1) * NB * lda + (size_t)k * NB, lda, tid);
+    load_tile64(Qm, A + (size_t)(k + b) * NB * lda + (size_t)(k + 1) * NB, lda, tid);
+  }
   for (int j = 0; j < t; ++j) {
     const size_t col = (size_t)(k - t + j) * NB;
     load_tile64(Pm, A + (size_t)k * NB * lda + col, lda, tid);
@@ -723,6 +733,7 @@ __global__ void __launch_bounds__(256) potrf_solve_kernel(float* A, int lda, int
       float* row = nullptr;
       if (warp == 2 && half == 0) row = S + (32 + lane) * LQ;
       else if (b && (warp == 3 || warp == 4)) row = Bm + ((warp - 3) * 32 + lane) * LQ + 32 * half;
+      else if (fn && (warp == 5 || warp == 6)) row = Pm + ((warp - 5) * 32 + lane) * LQ + 32 * half;  // X_1
       if (row) {
         float x[32];
         row_load32(x, row);
@@ -734,16 +745,29 @@ __global__ void __launch_bounds__(256) potrf_solve_kernel(float* A, int lda, int
     if (half == 0) {  // D11 -= L10 L10^T,  B[:, 32:64] -= X0 L10^T
       mm_nt_sub<32, 32, 32>(S + 32 * LQ + 32, S + 32 * LQ, S + 32 * LQ, tid);
       if (b) mm_nt_sub<64, 32, 32>(Bm + 32, Bm, S + 32 * LQ, tid);
+      if (fn) mm_nt_sub<64, 32, 32>(Pm + 32, Pm, S + 32 * LQ, tid);
       __syncthreads();
     }
     PS_STAMP(3 + 2 * half);
   }
   if (warp == 0 && bad && lane == 0 && b == 0) atomicOr(status, 1);
-  if (b) {
+  if (fn) {
+    mm_nt_sub<64, 64, 64>(Qm, Bm, Pm, tid);
+    __syncthreads();
+    float* Qg = A + (size_t)(k + b) * NB * lda + (size_t)(k + 1) * NB;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const int e4 = tid + q * 256, r = e4 >> 4, c = (e4 & 15) * 4;
-      *reinterpret_cast<float4*>(Bg + (size_t)r * lda + c) = *reinterpret_cast<const float4*>(Bm + r * LQ + c);
+      *reinterpret_cast<float4*>(Qg + (size_t)r * lda + c) = *reinterpret_cast<const float4*>(Qm + r * LQ + c);
+    }
+  }
+  if (b) {
+    float* dst = (next && b == 1) ? Xnext : Bg;
+    const size_t ldd = (next && b == 1) ? (size_t)NB : (size_t)lda;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int e4 = tid + q * 256, r = e4 >> 4, c = (e4 & 15) * 4;
+      *reinterpret_cast<float4*>(dst + r * ldd + c) = *reinterpret_cast<const float4*>(Bm + r * LQ + c);
     }
   } else {
     float* ld = Ldiag + (size_t)k * NB * NB;
@@ -761,9 +785,9 @@ __global__ void __launch_bounds__(256) potrf_solve_kernel(float* A, int lda, int
 }
 
 // Block inverses off the chain: Dinv[k] holds L_kk on entry (from potrf_solve_kernel) and L_kk^-1 on return; L_kk is also
-// written in place into the diagonal block of A.  One CTA per block, all blocks in one launch.
+// written in place into the diagonal block of A (and the parked sub-diagonal block of every two-column panel next to it).  One CTA per block, all blocks in one launch.
 //   T00 = L00^-1, T11 = L11^-1 (one warp each), W = L10 T00, T10 = -T11 W.
-__global__ void __launch_bounds__(256) diag_inverse_kernel(float* A, int lda, float* Dinv) {
+__global__ void __launch_bounds__(256) diag_inverse_kernel(float* A, int lda, float* Dinv, const float* Xnext) {
   __shared__ float S[NB][LP];  // L
   __shared__ float X[NB][LP];  // L^-1
   __shared__ float W[32][33];
@@ -774,6 +798,10 @@ __global__ void __launch_bounds__(256) diag_inverse_kernel(float* A, int lda, fl
   const int kb = blockIdx.x;
   float* dinv = Dinv + (size_t)kb * NB * NB;
   float* blk = A + (size_t)kb * NB * lda + (size_t)kb * NB;
+  if (Xnext && (kb & 1)) {  // the sub-diagonal block of this panel, parked by potrf_solve_kernel(next = 1)
+    const float* xn = Xnext + (size_t)(kb >> 1) * NB * NB;
+    for (int e = tid; e < NB * NB; e += 256) blk[(size_t)(e >> 6) * lda + (e & 63) - NB] = xn[e];
+  }
   for (int e = tid; e < NB * NB; e += 256) {
     const int r = e >> 6, c = e & 63;
     const float v = dinv[e];
@@ -846,7 +874,7 @@ bool lookahead_wanted(int np) {
 }
 
 int32_t cholesky_inplace(cudaStream_t s, float* A, int np, int lda, float* Dinv, float* logdet_part, int* status,
-                         const Lookahead* la) {
+                         const Lookahead* la, float* scratch) {
   // Two-level right-looking blocking: 64-wide steps (potrf of the diagonal block, panel solve) are applied only inside a
   // panel of PW blocks; the trailing matrix is updated once per panel with K = 64 PW (a rank-64 update per step moves
   // the whole trailing matrix through the SMs for 64 FMAs per element: 27 TFLOP/s measured at n = 8192).
@@ -855,6 +883,8 @@ int32_t cholesky_inplace(cudaStream_t s, float* A, int np, int lda, float* Dinv,
   // columns of panel p+1, so the chain waits for the former (ev_bulk) before the latter.
   static const int PW = [] { const char* e = getenv("BX_CHOL_PW"); const int v = e ? atoi(e) : 2; return v < 1 ? 1 : v; }();
   static const bool fused = [] { const char* e = getenv("BX_CHOL_FUSED"); return !e || atoi(e) != 0; }();
+  static const bool fuse_next_env = [] { const char* e = getenv("BX_CHOL_FUSE_NEXT"); return !e || atoi(e) != 0; }();
+  const bool fuse_next = fused && PW == 2 && scratch != nullptr && fuse_next_env;
   const int nb = np / NB;
   cudaStream_t c = la ? la->chain : s;
   bool bulk_pending = false;
@@ -870,8 +900,10 @@ int32_t cholesky_inplace(cudaStream_t s, float* A, int np, int lda, float* Dinv,
     const int pw = min(PW, nb - k0);
     for (int t = 0; t < pw; ++t) {
       const int k = k0 + t;
-      if (fused) {  // one launch per block column: pre-update from the panel's earlier columns, potrf, panel solve
-        potrf_solve_kernel<<<nb - k, 256, PS_SMEM, c>>>(A, lda, k, t, Dinv, logdet_part, status);
+      if (fused) {  // one launch per block column: potrf, panel solve and the update between the panel's two columns
+        const int next = (fuse_next && t == 0 && pw == 2) ? 1 : 0;
+        potrf_solve_kernel<<<nb - k, 256, PS_SMEM, c>>>(A, lda, k, fuse_next ? 0 : t, next, Dinv,
+                                                        fuse_next ? scratch + (size_t)(k >> 1) * NB * NB : nullptr, logdet_part, status);
         BX_LAUNCH_CHECK();
         continue;
       }
@@ -931,7 +963,7 @@ int32_t cholesky_inplace(cudaStream_t s, float* A, int np, int lda, float* Dinv,
     BX_CUDA(cudaStreamWaitEvent(s, la->ev_chain, 0));
   }
   if (fused) {
-    diag_inverse_kernel<<<nb, 256, 0, s>>>(A, lda, Dinv);
+    diag_inverse_kernel<<<nb, 256, 0, s>>>(A, lda, Dinv, fuse_next ? scratch : nullptr);
     BX_LAUNCH_CHECK();
   }
   return 0;
