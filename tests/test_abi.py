@@ -54,3 +54,18 @@ def test_bad_arguments_are_rejected_without_a_gpu():
     assert _lib.lib.bx_fit_workspace_bytes(100, 3) > 2 * 128 * 128 * 4
     rc = _lib.lib.bx_topk(None, 10, 5, 0, None, None, None, 0, None)
     assert rc == -1 and b"null" in _lib.lib.bx_last_error()
+
+
+def test_batched_fit_rejects_bad_arguments_without_a_gpu():
+    """bx_fit_adamw_batch validates before touching the device: null pointers, R outside [1, BX_FIT_BATCH_MAX], a
+    workspace smaller than R slots."""
+    import ctypes
+    from bayex_b200 import _lib
+    f = _lib.lib.bx_fit_adamw_batch
+    fake = ctypes.c_void_p(256)  # never dereferenced: every call below fails validation first
+    assert f(None, fake, 100, 3, fake, 4, 1e-3, 10, None, fake, 1 << 30, None) == -1
+    assert f(fake, fake, 100, 3, fake, 0, 1e-3, 10, None, fake, 1 << 30, None) == -2
+    assert f(fake, fake, 100, 3, fake, _lib.FIT_BATCH_MAX + 1, 1e-3, 10, None, fake, 1 << 30, None) == -2
+    slot = _lib.lib.bx_fit_workspace_bytes(100, 3)
+    assert f(fake, fake, 100, 3, fake, 4, 1e-3, 10, None, fake, 4 * slot - 1, None) == -3
+    assert b"workspace" in _lib.lib.bx_last_error()

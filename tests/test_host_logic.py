@@ -155,3 +155,18 @@ def test_acq_param_passthrough_keeps_reference_defaults():
     assert bayex.Optimizer(dom, acq="LCB").acq_param == 2.576
     assert bayex.Optimizer(dom, acq="UCB", acq_param=1.5).acq_param == 1.5
     assert bayex.Optimizer(dom, "PI", True).sign == 1  # positional order of the reference is untouched
+
+
+def test_restart_sweep_concurrency_policy_and_validation():
+    """fit_sweep: restarts in flight per GPU by problem size; a bad ``concurrent`` is rejected before any device work."""
+    import numpy as np
+    import pytest
+    from bayex_b200 import _lib, fit_sweep
+    assert [fit_sweep.concurrent_restarts(n) for n in (100, 1024, 1025, 2048, 4096, 8192)] == [32, 32, 16, 16, 8, 8]
+    assert all(1 <= fit_sweep.concurrent_restarts(n) <= _lib.FIT_BATCH_MAX for n in (1, 10 ** 6))
+    x, y, raws = np.zeros((10, 2), np.float32), np.zeros(10, np.float32), np.zeros((3, 4), np.float32)
+    for bad in (0, _lib.FIT_BATCH_MAX + 1):
+        with pytest.raises(ValueError):
+            fit_sweep.fit_restarts(x, y, raws, concurrent=bad)
+    with pytest.raises(AssertionError):
+        fit_sweep.fit_restarts(x, y, np.zeros((3, 5), np.float32))
