@@ -666,6 +666,7 @@ extern "C" int32_t bx_nlml_grad(const float* d_X, const float* d_y, int32_t n, i
   FitWs w = carve_fit_ws(d_ws, n, d);
   if (fit_small_ok(n, d) && !getenv("BX_NO_FIT_SMALL"))  // one-kernel evaluation (raw is left untouched: steps = 0)
     return launch_fit_small(s, d_X, d_y, n, d, const_cast<float*>(d_raw), 0.f, 0, nullptr, d_out, 1);
+  if ((rc = cholesky_prepare())) return rc;
   Lookahead la;
   if (lookahead_wanted(w.np)) { if ((rc = la.init())) return rc; w.la = &la; }
   rc = launch_grad(s, d_X, d_y, n, d, d_raw, w);
@@ -686,6 +687,7 @@ extern "C" int32_t bx_fit_adamw(const float* d_X, const float* d_y, int32_t n, i
   if (fit_small_ok(n, d) && !getenv("BX_NO_FIT_SMALL"))  // whole loop in one launch
     return launch_fit_small(s, d_X, d_y, n, d, d_raw, lr, steps, d_trace, nullptr, 0);
   BX_CUDA(cudaMemsetAsync(w.adam, 0, sizeof(float) * (2 * (d + 2) + 1), s));  // fresh moments per call (gp.py:100)
+  if ((rc = cholesky_prepare())) return rc;
   Lookahead la;  // helper stream: its cost is amortised over the loop, so always
   if (!getenv("BX_NO_HELPER_STREAM")) { if ((rc = la.init())) return rc; w.la = &la; }
   if (use_graph && !d_trace) {
@@ -785,6 +787,7 @@ extern "C" int32_t bx_fit_adamw_batch(const float* d_X, const float* d_y, int32_
   Branches br;
   int32_t rc = br.init(R, s);
   if (rc) return rc;
+  if ((rc = cholesky_prepare())) return rc;
 
   if (fit_small_ok(n, d) && !getenv("BX_NO_FIT_SMALL")) {  // one launch per restart and phase, all restarts side by side
     if ((rc = br.fork())) return rc;
@@ -852,6 +855,7 @@ extern "C" int32_t bx_factor_build(const float* d_X, const float* d_y, int32_t n
   BX_CHECK_ARG((d_T16hi == nullptr) == (d_T16lo == nullptr), BX_E_ARG, "T16hi and T16lo must be given together");
   cudaStream_t s = (cudaStream_t)stream;
   FitWs w = carve_fit_ws(d_ws, n, d);
+  if ((rc = cholesky_prepare())) return rc;
   Lookahead la;
   if (lookahead_wanted(w.np)) { if ((rc = la.init())) return rc; w.la = &la; }
   rc = launch_factor(s, d_X, d_y, n, d, d_raw, w, d_T, d_U, d_alpha, d_scale, d_hyp);

@@ -48,6 +48,7 @@ struct Lookahead {
   ~Lookahead();
 };
 bool lookahead_wanted(int np);
+int32_t cholesky_prepare();  // call once per entry point, outside stream capture, before cholesky_inplace
 // `scratch` (optional, (np/128 + 1) * 4096 floats): lets the first column of a panel also update the second one.
 int32_t cholesky_inplace(cudaStream_t s, float* A, int np, int lda, float* Dinv, float* logdet_part, int* status,
                          const Lookahead* la = nullptr, float* scratch = nullptr);

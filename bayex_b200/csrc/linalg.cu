@@ -873,6 +873,13 @@ bool lookahead_wanted(int np) {
   return min_np > 0 && np >= min_np;
 }
 
+// Per-device function attributes of the factorisation kernels; the entry points call it once per call, before any
+// stream capture (a process may drive several devices, so this is not a one-time static).
+int32_t cholesky_prepare() {
+  BX_CUDA(cudaFuncSetAttribute(potrf_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PS_SMEM));
+  return 0;
+}
+
 int32_t cholesky_inplace(cudaStream_t s, float* A, int np, int lda, float* Dinv, float* logdet_part, int* status,
                          const Lookahead* la, float* scratch) {
   // Two-level right-looking blocking: 64-wide steps (potrf of the diagonal block, panel solve) are applied only inside a
@@ -888,10 +895,6 @@ int32_t cholesky_inplace(cudaStream_t s, float* A, int np, int lda, float* Dinv,
   const int nb = np / NB;
   cudaStream_t c = la ? la->chain : s;
   bool bulk_pending = false;
-  if (fused) {
-    static const cudaError_t attr = cudaFuncSetAttribute(potrf_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PS_SMEM);
-    BX_CUDA(attr);
-  }
   if (la) {
     BX_CUDA(cudaEventRecord(la->ev_bulk, s));
     BX_CUDA(cudaStreamWaitEvent(c, la->ev_bulk, 0));
