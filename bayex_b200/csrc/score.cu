@@ -207,6 +207,8 @@ bool score_tc16_supported(const bx_factor_t& f);
 int32_t launch_score_tc16p(cudaStream_t s, const ScoreArgs& a, const SamplerPack& sp);
 // implemented in score_tc16s.cu (fp16 head/tail, K* generation shared by a 2-CTA cluster through DSMEM)
 int32_t launch_score_tc16s(cudaStream_t s, const ScoreArgs& a, const SamplerPack& sp);
+// implemented in score_tc16t.cu (experimental: fp16 head/tail, CTA pair, transposed tiling)
+int32_t launch_score_tc16t(cudaStream_t s, const ScoreArgs& a, const SamplerPack& sp);
 
 }  // namespace bx
 
@@ -292,10 +294,12 @@ extern "C" int32_t bx_score_generated(const bx_factor_t* f, const uint32_t key[2
     BX_CHECK_ARG(score_tc_supported(*f), BX_E_UNSUPPORTED, "tcgen05 engines need the Thi/Tlo split of the factor and d <= 32");
     return engine == BX_ENGINE_TCGEN05 ? launch_score_tc((cudaStream_t)stream, a, sp) : launch_score_tc2((cudaStream_t)stream, a, sp);
   }
-  if (engine == BX_ENGINE_TCGEN05_F16 || engine == BX_ENGINE_TCGEN05_F16_PAIR || engine == BX_ENGINE_TCGEN05_F16_SHARED) {
+  if (engine == BX_ENGINE_TCGEN05_F16 || engine == BX_ENGINE_TCGEN05_F16_PAIR || engine == BX_ENGINE_TCGEN05_F16_SHARED ||
+      engine == BX_ENGINE_TCGEN05_F16_T) {
     BX_CHECK_ARG(score_tc16_supported(*f), BX_E_UNSUPPORTED, "fp16 tcgen05 engines need the T16hi/T16lo split of the factor and d <= 32");
     if (engine == BX_ENGINE_TCGEN05_F16) return launch_score_tc16((cudaStream_t)stream, a, sp);
     if (engine == BX_ENGINE_TCGEN05_F16_PAIR) return launch_score_tc16p((cudaStream_t)stream, a, sp);
+    if (engine == BX_ENGINE_TCGEN05_F16_T) return launch_score_tc16t((cudaStream_t)stream, a, sp);
     return launch_score_tc16s((cudaStream_t)stream, a, sp);
   }
   BX_CHECK_ARG(engine == BX_ENGINE_SIMT, BX_E_ARG, "unknown engine %d", engine);

@@ -51,7 +51,8 @@ enum {
   BX_ENGINE_TCGEN05_PAIR = 3, /* 3xTF32, cta_group::2 */
   BX_ENGINE_TCGEN05_F16 = 4,  /* fp16 head/tail split (same 22-bit operands, half the tensor work) */
   BX_ENGINE_TCGEN05_F16_PAIR = 5, /* fp16 head/tail split, cta_group::2, register-tiled K* producers (AUTO picks this) */
-  BX_ENGINE_TCGEN05_F16_SHARED = 6 /* fp16 head/tail split, K* generation shared by a 2-CTA cluster through DSMEM */
+  BX_ENGINE_TCGEN05_F16_SHARED = 6, /* fp16 head/tail split, K* generation shared by a 2-CTA cluster through DSMEM */
+  BX_ENGINE_TCGEN05_F16_T = 7 /* experimental: fp16 head/tail split, CTA pair, transposed tiling (T rows on the TMEM lanes: K* generated once per 1024 rows) */
 };
 
 /* One dimension of the parameter space - mirrors bayex.domain.Real / Integer (domain.py:22-131). */

@@ -466,8 +466,10 @@ def test_tcgen05_engine_matches_simt_engine_and_oracle(n, d, M, acq):
     v_h, b_h = post.score_generated(key, dims, 5, M, acq, param, ystar, engine=_lib.ENGINE_TCGEN05_F16)
     v_q, b_q = post.score_generated(key, dims, 5, M, acq, param, ystar, engine=_lib.ENGINE_TCGEN05_F16_PAIR)
     v_r, b_r = post.score_generated(key, dims, 5, M, acq, param, ystar, engine=_lib.ENGINE_TCGEN05_F16_SHARED)
-    s, t, pr, hf, hp, hs = (v.cpu().numpy().astype(np.float64) for v in (v_s, v_t, v_p, v_h, v_q, v_r))
+    v_x, b_x = post.score_generated(key, dims, 5, M, acq, param, ystar, engine=_lib.ENGINE_TCGEN05_F16_T)
+    s, t, pr, hf, hp, hs, hx = (v.cpu().numpy().astype(np.float64) for v in (v_s, v_t, v_p, v_h, v_q, v_r, v_x))
     assert np.all(np.isfinite(t)) and np.all(np.isfinite(pr)) and np.all(np.isfinite(hf)) and np.all(np.isfinite(hp)) and np.all(np.isfinite(hs))
+    assert np.all(np.isfinite(hx))
     cand = engine.threefry_fill(key, dims, d, 5, M).cpu().numpy()
     f64, f32 = ogp.Factor(P, X, Y, np.ones(n), np.float64), ogp.Factor(P, X, Y, np.ones(n), np.float32)
     mu64, sd64 = f64.predict(cand.astype(np.float64))
@@ -491,11 +493,12 @@ def test_tcgen05_engine_matches_simt_engine_and_oracle(n, d, M, acq):
     # fp32 summation order of mu = sum alpha_j k_j (|alpha| ~ 1e3 at n = 8192), which differs from engine to engine.
     tol_tc = np.maximum.reduce([tol, 2 * np.abs(s - a64), np.full_like(tol, 2 * np.abs(a32 - a64).max())])
     for name, got, bar in (("simt", s, tol), ("tcgen05", t, tol_tc), ("tcgen05_pair", pr, tol_tc), ("tcgen05_f16", hf, tol_tc),
-                           ("tcgen05_f16_pair", hp, tol_tc), ("tcgen05_f16_shared", hs, tol_tc)):
+                           ("tcgen05_f16_pair", hp, tol_tc), ("tcgen05_f16_shared", hs, tol_tc),
+                           ("tcgen05_f16_transposed", hx, tol_tc)):
         err = np.abs(got - a64)
         assert np.all(err <= bar), f"{name}: {np.sum(err > bar)}/{M} outside tolerance, worst {err.max():.3e} at {np.argmax(err)}"
     assert np.abs(s - t).max() <= 2 * tol.max() and np.abs(s - pr).max() <= 2 * tol.max()
-    for vv, bb in ((v_t, b_t), (v_p, b_p), (v_h, b_h), (v_q, b_q), (v_r, b_r)):
+    for vv, bb in ((v_t, b_t), (v_p, b_p), (v_h, b_h), (v_q, b_q), (v_r, b_r), (v_x, b_x)):
         vt, it = _lib.unpack(engine.to_unsigned(int(bb.item())))
         assert it == 5 + oopt.jnp_argmax(vv.cpu().numpy()) and np.float32(vt) == vv.cpu().numpy()[it - 5]
 
