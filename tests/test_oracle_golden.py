@@ -201,3 +201,30 @@ def test_refine_ascent_is_monotone(golden):
         xb, fb = oopt.refine_ascent(nm, f, Y, mask, XT[:8])
         assert np.all(fb >= v0) and np.any(fb > v0)
         assert np.allclose(fb, oacq.BY_NAME[nm](xb, X, Y, mask, P, dtype=np.float64, factor=f), rtol=1e-9, atol=1e-12)
+
+
+def test_adamw_restatement_matches_an_independent_implementation():
+    """optax is unpinned and absent, so ``adamw_step`` (clip_by_global_norm(10) + adamw, gp.py:99) is restated from the
+    published algorithm; torch.optim.AdamW + clip_grad_norm_ implement the same published algorithm independently
+    (decoupled weight decay, bias-corrected moments, eps outside the square root).  60 steps on a gradient field that
+    crosses the clipping threshold in both directions, fp64: the two trajectories agree to rounding."""
+    import torch
+    from oracle import gp as ogp
+    rng = np.random.default_rng(3)
+    P = 7
+    A = rng.standard_normal((P, P))
+    grad = lambda p, t: A @ p * (30.0 if t % 7 < 3 else 0.3) + np.sin(np.arange(P) + t)  # norms from ~1 to ~100
+    p = rng.standard_normal(P)
+    m, v, t = np.zeros(P), np.zeros(P), 0
+    tp = torch.tensor(p, dtype=torch.float64, requires_grad=True)
+    opt = torch.optim.AdamW([tp], lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-4)
+    clipped = 0
+    for step in range(60):
+        g = grad(p, step)
+        clipped += np.linalg.norm(g) > 10.0
+        tp.grad = torch.tensor(grad(tp.detach().numpy(), step), dtype=torch.float64)
+        torch.nn.utils.clip_grad_norm_([tp], 10.0)
+        opt.step()
+        p, m, v, t = ogp.adamw_step(p, g, m, v, t, 1e-3, np.float64)
+        assert np.allclose(p, tp.detach().numpy(), rtol=0, atol=5e-9), (step, np.abs(p - tp.detach().numpy()).max())
+    assert 0 < clipped < 60
