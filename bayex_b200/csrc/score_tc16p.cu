@@ -64,65 +64,6 @@ struct __align__(16) Smem {
   uint32_t tmem_base;
 };
 
-__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {  // the same barrier in CTA rank 0
-  asm volatile(
-      "{\n\t.reg .b32 ra;\n\t"
-      "mapa.shared::cluster.u32 ra, %0, 0;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
-      ::"r"(bar)
-      : "memory");
-}
-// Same, with the default (.release.cta) semantics: no MEMBAR.ALL.GPU in front of the arrive (ncu: 8 % of the rank-1
-// producers' samples sat on that fence).  Used where the data being published was written to this CTA's own shared
-// memory and already made visible to the async proxy by fence.proxy.async - the consumer is this SM's tensor core.
-__device__ __forceinline__ void mbar_arrive_leader_relaxed(uint32_t bar) {
-  asm volatile(
-      "{\n\t.reg .b32 ra;\n\t"
-      "mapa.shared::cluster.u32 ra, %0, 0;\n\t"
-      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
-      ::"r"(bar)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar, int x, int y) {
-  // complete_tx lands on the leader CTA's barrier: clear the peer bit of the shared::cluster address
-  asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(dst), "l"((uint64_t)map), "r"(bar & 0xFEFFFFFFu), "r"(x), "r"(y)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_alloc_pair(uint32_t dst_smem, uint32_t cols) {
-  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t cols) {
-  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
-}
-__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {  // arrives on `bar` in both CTAs
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-               ::"r"(bar), "h"((uint16_t)3)
-               : "memory");
-}
-__device__ __forceinline__ float4 lds128f(uint32_t addr) {
-  float4 v;
-  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
-  return v;
-}
-
-// Raw coordinate k of candidate `row` (position in this launch): generated from the Threefry key (optimizer.py:183-184) or
-// read from the caller's explicit points (gp.predict / acq.* on large point sets); rows past the end read as 0.
-__device__ __forceinline__ float cand_coord(const ScoreArgs& a, const SamplerPack& sp, uint64_t row, int k) {
-  if (a.cand) return row < a.m_count ? __ldg(a.cand + row * (uint64_t)a.f.d + k) : 0.f;
-  return sample_coord(sp.dim[k], a.m_begin + row);
-}
-
 // ------------------------------------------------------------------------------------------------------------------
 // RC = candidates per producer thread.  128 / RC candidate groups x (2 RC) observation parts = 256 producer threads;
 // a thread generates RC candidates x (32 / RC) observations of every K-block.
@@ -181,7 +122,7 @@ score_tc16p_kernel(const __grid_constant__ ScoreArgs a, const __grid_constant__ 
               mbar_wait<256>(smem_u32(&S.empty_b[st]), ph ^ 1);
               const uint32_t bar = smem_u32(&S.full_b[st]);
               if (leader) mbar_expect_tx(bar, 4 * BTILE);  // both halves, head + tail
-              else mbar_arrive_leader(bar);
+              else mbar_arrive_rank(bar, 0);
               tma_load_2d_pair(smem_u32(S.b_hi[st]), &map_hi, bar, J * BKH, rb * BN + (int)rank * HN);
               tma_load_2d_pair(smem_u32(S.b_lo[st]), &map_lo, bar, J * BKH, rb * BN + (int)rank * HN);
             }
@@ -281,7 +222,7 @@ score_tc16p_kernel(const __grid_constant__ ScoreArgs a, const __grid_constant__ 
           __syncwarp();
           if (lane == 0) {
             if (leader) mbar_arrive(smem_u32(&S.tmem_empty[acc]));
-            else mbar_arrive_leader(smem_u32(&S.tmem_empty[acc]));
+            else mbar_arrive_rank(smem_u32(&S.tmem_empty[acc]), 0);
           }
         }
       }
@@ -400,7 +341,7 @@ score_tc16p_kernel(const __grid_constant__ ScoreArgs a, const __grid_constant__ 
                 }
             }
             if (last_sb) {  // gp.py:66-67: the last super-block visits every K-block, so the mean rides along there
-              const float4 a0 = lds128f(al_addr + (uint32_t)(g * 32)), a1 = lds128f(al_addr + (uint32_t)(g * 32 + 16));
+              const float4 a0 = lds128(al_addr + (uint32_t)(g * 32)), a1 = lds128(al_addr + (uint32_t)(g * 32 + 16));
               const float al[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
 #pragma unroll
               for (int j = 0; j < RC; ++j)
@@ -414,7 +355,7 @@ score_tc16p_kernel(const __grid_constant__ ScoreArgs a, const __grid_constant__ 
           __syncwarp();
           if (lane == 0) {
             if (leader) mbar_arrive(smem_u32(&S.full_a[sa]));
-            else mbar_arrive_leader_relaxed(smem_u32(&S.full_a[sa]));
+            else mbar_arrive_rank_relaxed(smem_u32(&S.full_a[sa]), 0);
             mbar_arrive(smem_u32(&S.empty_u[su]));
           }
         }

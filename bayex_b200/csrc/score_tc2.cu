@@ -36,43 +36,6 @@ struct __align__(16) Smem {
   uint32_t tmem_base;
 };
 
-// arrive on the leader's copy of `bar` (same smem offset in CTA rank 0)
-__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {
-  asm volatile(
-      "{\n\t.reg .b32 ra;\n\t"
-      "mapa.shared::cluster.u32 ra, %0, 0;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
-      ::"r"(bar)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar, int x, int y) {
-  // complete_tx lands on the leader CTA's barrier: clear the peer bit of the shared::cluster address
-  asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(dst), "l"((uint64_t)map), "r"(bar & 0xFEFFFFFFu), "r"(x), "r"(y)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_alloc_pair(uint32_t dst_smem, uint32_t cols) {
-  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t cols) {
-  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
-}
-__device__ __forceinline__ void umma_tf32_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {  // arrives on `bar` in both CTAs
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-               ::"r"(bar), "h"((uint16_t)3)
-               : "memory");
-}
-
 template <int D4>
 __global__ void __launch_bounds__(NTHREADS, 1)
 score_tc2_kernel(const __grid_constant__ ScoreArgs a, const __grid_constant__ SamplerPack sp,
@@ -121,7 +84,7 @@ score_tc2_kernel(const __grid_constant__ ScoreArgs a, const __grid_constant__ Sa
               mbar_wait<64>(smem_u32(&S.empty_b[st]), ph ^ 1);
               const uint32_t bar = smem_u32(&S.full_b[st]);
               if (leader) mbar_expect_tx(bar, 4 * TILE_BYTES);  // both halves, head + tail
-              else mbar_arrive_leader(bar);
+              else mbar_arrive_rank(bar, 0);
               tma_load_2d_pair(smem_u32(S.b_hi[st]), &map_hi, bar, J * BK, rb * BN + (int)rank * HN);
               tma_load_2d_pair(smem_u32(S.b_lo[st]), &map_lo, bar, J * BK, rb * BN + (int)rank * HN);
             }
@@ -202,7 +165,7 @@ score_tc2_kernel(const __grid_constant__ ScoreArgs a, const __grid_constant__ Sa
           __syncwarp();
           if (lane == 0) {
             if (leader) mbar_arrive(smem_u32(&S.tmem_empty[acc]));
-            else mbar_arrive_leader(smem_u32(&S.tmem_empty[acc]));
+            else mbar_arrive_rank(smem_u32(&S.tmem_empty[acc]), 0);
           }
         }
       }
@@ -295,7 +258,7 @@ score_tc2_kernel(const __grid_constant__ ScoreArgs a, const __grid_constant__ Sa
           __syncwarp();
           if (lane == 0) {
             if (leader) mbar_arrive(smem_u32(&S.full_a[sa]));
-            else mbar_arrive_leader(smem_u32(&S.full_a[sa]));
+            else mbar_arrive_rank(smem_u32(&S.full_a[sa]), 0);
           }
           if (J + 1 < nJ) {
             const uint32_t un = us_addr + (uint32_t)(((J + 1) & 1) * US * 4);

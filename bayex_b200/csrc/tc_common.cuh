@@ -199,6 +199,78 @@ __device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint
 template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 
+// Raw coordinate k of candidate `row` (position in this launch): generated from the Threefry key (optimizer.py:183-184) or
+// read from the caller's explicit points (gp.predict / acq.* on large point sets); rows past the end read as 0.
+__device__ __forceinline__ float cand_coord(const ScoreArgs& a, const SamplerPack& sp, uint64_t row, int k) {
+  if (a.cand) return row < a.m_count ? __ldg(a.cand + row * (uint64_t)a.f.d + k) : 0.f;
+  return sample_coord(sp.dim[k], a.m_begin + row);
+}
+
+// ---- CTA pair (cta_group::2) -----------------------------------------------------------------------------------------
+// Arrive on the copy of `bar` (same shared-memory offset) in CTA `rank` of the cluster.  The plain form carries
+// .release.cluster (it compiles to MEMBAR.ALL.GPU in front of the arrive); the relaxed form keeps the default .release.cta
+// semantics and is for data that was written to this CTA's own shared memory and already made visible to the async proxy
+// by fence.proxy.async - the consumer is this SM's tensor core (ncu: 8 % of the rank-1 producers' samples sat on the fence).
+__device__ __forceinline__ void mbar_arrive_rank(uint32_t bar, uint32_t rank) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(bar), "r"(rank)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_rank_relaxed(uint32_t bar, uint32_t rank) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(bar), "r"(rank)
+      : "memory");
+}
+__device__ __forceinline__ void st_remote_f32(uint32_t addr, uint32_t rank, float v) {  // same offset in CTA `rank`
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "st.shared::cluster.f32 [ra], %2;\n\t}"
+      ::"r"(addr), "r"(rank), "f"(v)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar, int x, int y) {
+  // complete_tx lands on the leader CTA's barrier: clear the peer bit of the shared::cluster address
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"((uint64_t)map), "r"(bar & 0xFEFFFFFFu), "r"(x), "r"(y)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_tf32_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {  // arrives on `bar` in both CTAs
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3)
+               : "memory");
+}
+
 // ---- fp16 head/tail split (kind::f16 engines) ------------------------------------------------------------------
 // x = hi + lo with hi = fp16(x), lo = fp16(x - hi): 22 significand bits like the TF32 split, at twice the MMA rate.
 // fp16's narrow exponent is handled with two power-of-two scales: K* * 2^a (largest entry near 2^14, from the
