@@ -19,9 +19,7 @@ if not os.path.exists(LIB_PATH):
 lib = C.CDLL(LIB_PATH)
 
 ACQ_IDS = {"EI": 0, "PI": 1, "UCB": 2, "LCB": 3}
-ENGINE_AUTO, ENGINE_SIMT, ENGINE_TCGEN05, ENGINE_TCGEN05_PAIR, ENGINE_TCGEN05_F16, ENGINE_TCGEN05_F16_PAIR = 0, 1, 2, 3, 4, 5
-ENGINE_TCGEN05_F16_SHARED = 6
-ENGINE_TCGEN05_F16_T = 7  # experimental transposed tiling (score_tc16t.cu)
+ENGINE_AUTO, ENGINE_SIMT, ENGINE_TCGEN05_TF32, ENGINE_TCGEN05_F16 = 0, 1, 2, 3
 MAX_D, MAX_K, TILE, FIT_BATCH_MAX = 64, 1024, 128, 32
 POINTS_TC_MIN = 65536  # BX_POINTS_TC_MIN
 

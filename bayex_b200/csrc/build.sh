@@ -6,12 +6,15 @@ OUT="$HERE/../libbayex_b200.so"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -Wall
        --expt-relaxed-constexpr -Xptxas -v)
+UNITS="linalg fit score score_tc2 score_tc16p selftest topk refine"
 mkdir -p "$HERE/build"
+rm -f "$HERE"/build/*.o
 pids=()
-for f in linalg fit score score_tc score_tc2 score_tc16 score_tc16p score_tc16s score_tc16t topk refine; do
+for f in $UNITS; do
   ( "$NVCC" "${FLAGS[@]}" -c "$HERE/$f.cu" -o "$HERE/build/$f.o" > "$HERE/build/$f.log" 2>&1 || { cat "$HERE/build/$f.log"; exit 1; } ) &
   pids+=($!)
 done
 for p in "${pids[@]}"; do wait "$p"; done
-"$NVCC" -shared -o "$OUT" "$HERE"/build/{linalg,fit,score,score_tc,score_tc2,score_tc16,score_tc16p,score_tc16s,score_tc16t,topk,refine}.o
+OBJS=(); for f in $UNITS; do OBJS+=("$HERE/build/$f.o"); done
+"$NVCC" -shared -o "$OUT" "${OBJS[@]}"
 echo "built $OUT"

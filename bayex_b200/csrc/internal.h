@@ -86,6 +86,24 @@ struct ScoreArgs {
   unsigned long long* best;
   uint64_t index_base;
   int debug;  // profiling ablations of the tcgen05 engine (env BX_TC_ABLATE): 1 = skip K* math, 2 = skip MMA issue
+  // fused per-CTA top-k (topk_fused.cuh; fp16 tcgen05 engine only): slab of CTA b = topk_slab + b * tk::CAP keys,
+  // topk_count[b] = survivors it left there; topk_k == 0 switches it off
+  unsigned long long* topk_slab;
+  unsigned int* topk_count;
+  int topk_k;
 };
+
+// Fused-top-k plumbing shared by score.cu / topk.cu / score_tc16p.cu
+unsigned score_tc16p_grid(uint64_t m_count);  // CTAs the fp16 engine launches for m_count candidates (slabs to merge)
+// Reduce `nslabs` key slabs (`stride` keys apart, counts[b] valid keys each; counts == nullptr: every non-zero key is
+// valid) to the sorted list format: list_out[0..k) ascending keys (empty slots = 0 first), list_out[k] = max of the
+// n_best keys best_in[i * best_stride].  Optional unpacked outputs: the `count` valid entries ascending at the front of
+// out_vals / out_idx.  scratch: nslabs * min(stride, k) keys.
+int32_t launch_topk_merge(cudaStream_t s, const unsigned long long* slabs, const unsigned int* counts, int nslabs, int stride,
+                          int k, unsigned long long* scratch, unsigned long long* list_out, const unsigned long long* best_in,
+                          int n_best, int best_stride, float* out_vals, uint32_t* out_idx, int32_t* out_count);
+// Top-k of a value vector by radix select (bx_topk) into the same list format (list_out[k] is left untouched).
+int32_t launch_topk_values(cudaStream_t s, const float* d_vals, uint64_t M, int k, uint64_t index_base, float* d_out_vals,
+                           uint32_t* d_out_idx, unsigned long long* list_out, void* d_ws);
 
 }  // namespace bx

@@ -7,6 +7,7 @@
 // This engine backs bx_score_points (explicit candidates: gp.predict, acq.*, refinement scoring) and is the
 // reference implementation the tcgen05 engine (score_tc.cu) is validated against on the GPU.
 #include "internal.h"
+#include "topk_fused.cuh"
 
 namespace bx {
 
@@ -195,20 +196,12 @@ int32_t launch_score_simt(cudaStream_t s, const ScoreArgs& a, const SamplerPack*
   return 0;
 }
 
-// implemented in score_tc.cu
-int32_t launch_score_tc(cudaStream_t s, const ScoreArgs& a, const SamplerPack& sp);
-bool score_tc_supported(const bx_factor_t& f);
-// implemented in score_tc2.cu (CTA-pair engine)
+// implemented in score_tc2.cu (3xTF32, CTA pair: the full fp32 exponent range of T; opt-in)
 int32_t launch_score_tc2(cudaStream_t s, const ScoreArgs& a, const SamplerPack& sp);
-// implemented in score_tc16.cu (fp16 head/tail engine)
-int32_t launch_score_tc16(cudaStream_t s, const ScoreArgs& a, const SamplerPack& sp);
-bool score_tc16_supported(const bx_factor_t& f);
+bool score_tc_supported(const bx_factor_t& f);
 // implemented in score_tc16p.cu (fp16 head/tail, CTA pair, register-tiled producers): the production engine
 int32_t launch_score_tc16p(cudaStream_t s, const ScoreArgs& a, const SamplerPack& sp);
-// implemented in score_tc16s.cu (fp16 head/tail, K* generation shared by a 2-CTA cluster through DSMEM)
-int32_t launch_score_tc16s(cudaStream_t s, const ScoreArgs& a, const SamplerPack& sp);
-// implemented in score_tc16t.cu (experimental: fp16 head/tail, CTA pair, transposed tiling)
-int32_t launch_score_tc16t(cudaStream_t s, const ScoreArgs& a, const SamplerPack& sp);
+bool score_tc16_supported(const bx_factor_t& f);
 
 }  // namespace bx
 
@@ -286,24 +279,185 @@ extern "C" int32_t bx_score_generated(const bx_factor_t* f, const uint32_t key[2
   ScoreArgs a{};
   a.f = *f; a.cand = nullptr; a.m_begin = m_begin; a.m_count = m_count; a.acq_id = acq_id; a.acq_param = acq_param;
   a.ystar = ystar; a.acq = d_acq; a.best = reinterpret_cast<unsigned long long*>(d_best); a.index_base = m_begin;
-  // AUTO: the fp16 head/tail engines carry the same 22 operand bits as 3xTF32 at half the tensor work; the CTA-pair version
-  // is the fastest (profiles/README.md).  The TF32 engines remain selectable (full fp32 exponent range of T); SIMT covers d > 32.
-  if (engine == BX_ENGINE_AUTO)
-    engine = score_tc16_supported(*f) ? BX_ENGINE_TCGEN05_F16_PAIR : (score_tc_supported(*f) ? BX_ENGINE_TCGEN05 : BX_ENGINE_SIMT);
-  if (engine == BX_ENGINE_TCGEN05 || engine == BX_ENGINE_TCGEN05_PAIR) {
-    BX_CHECK_ARG(score_tc_supported(*f), BX_E_UNSUPPORTED, "tcgen05 engines need the Thi/Tlo split of the factor and d <= 32");
-    return engine == BX_ENGINE_TCGEN05 ? launch_score_tc((cudaStream_t)stream, a, sp) : launch_score_tc2((cudaStream_t)stream, a, sp);
+  // AUTO: the fp16 head/tail CTA-pair engine whenever the factor carries its fp16 copies and d <= 32 (same 22 operand bits
+  // as 3xTF32 at half the tensor work); otherwise the fp32 SIMT engine.  The 3xTF32 engine (full fp32 exponent range of T)
+  // is opt-in and needs the Thi/Tlo copies.
+  if (engine == BX_ENGINE_AUTO) engine = score_tc16_supported(*f) ? BX_ENGINE_TCGEN05_F16 : BX_ENGINE_SIMT;
+  if (engine == BX_ENGINE_TCGEN05_TF32) {
+    BX_CHECK_ARG(score_tc_supported(*f), BX_E_UNSUPPORTED, "the 3xTF32 tcgen05 engine needs the Thi/Tlo split of the factor and d <= 32");
+    return launch_score_tc2((cudaStream_t)stream, a, sp);
   }
-  if (engine == BX_ENGINE_TCGEN05_F16 || engine == BX_ENGINE_TCGEN05_F16_PAIR || engine == BX_ENGINE_TCGEN05_F16_SHARED ||
-      engine == BX_ENGINE_TCGEN05_F16_T) {
-    BX_CHECK_ARG(score_tc16_supported(*f), BX_E_UNSUPPORTED, "fp16 tcgen05 engines need the T16hi/T16lo split of the factor and d <= 32");
-    if (engine == BX_ENGINE_TCGEN05_F16) return launch_score_tc16((cudaStream_t)stream, a, sp);
-    if (engine == BX_ENGINE_TCGEN05_F16_PAIR) return launch_score_tc16p((cudaStream_t)stream, a, sp);
-    if (engine == BX_ENGINE_TCGEN05_F16_T) return launch_score_tc16t((cudaStream_t)stream, a, sp);
-    return launch_score_tc16s((cudaStream_t)stream, a, sp);
+  if (engine == BX_ENGINE_TCGEN05_F16) {
+    BX_CHECK_ARG(score_tc16_supported(*f), BX_E_UNSUPPORTED, "the fp16 tcgen05 engine needs the T16hi/T16lo split of the factor and d <= 32");
+    return launch_score_tc16p((cudaStream_t)stream, a, sp);
   }
   BX_CHECK_ARG(engine == BX_ENGINE_SIMT, BX_E_ARG, "unknown engine %d", engine);
   return launch_score_simt((cudaStream_t)stream, a, &sp, true);
+}
+
+// ---- fused sample() front half: generate -> score -> top-k -> arg-max (optimizer.py:183-197, :205) ---------------------
+namespace bx {
+
+static int sm_count() {
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return sms;
+}
+static size_t align256(size_t b) { return (b + 255) / 256 * 256; }
+
+struct SampleWs {
+  unsigned long long *best, *slabs, *scratch;
+  unsigned int* counts;
+  float* acq;   // un-fused engines only
+  void* topk;   // un-fused engines only (bx_topk workspace)
+  size_t bytes;
+};
+static SampleWs carve_sample_ws(void* base, uint64_t m_count, int k) {
+  SampleWs w{};
+  const size_t grid = (size_t)sm_count();
+  size_t off = 0;
+  auto take = [&](size_t nbytes) {
+    char* p = base ? reinterpret_cast<char*>(base) + off : nullptr;
+    off += align256(nbytes);
+    return p;
+  };
+  w.best = reinterpret_cast<unsigned long long*>(take(8));
+  w.counts = reinterpret_cast<unsigned int*>(take(4 * grid));
+  w.slabs = reinterpret_cast<unsigned long long*>(take(8 * grid * tk::CAP));
+  w.scratch = reinterpret_cast<unsigned long long*>(take(8 * grid * (size_t)k));
+  const size_t fused = off;
+  // the un-fused path (SIMT / 3xTF32 engines) reuses the same memory: acquisition vector + radix-select state
+  off = align256(8);
+  w.acq = reinterpret_cast<float*>(take(4 * (size_t)m_count));
+  w.topk = take(bx_topk_workspace_bytes(m_count, k));
+  w.bytes = off > fused ? off : fused;
+  return w;
+}
+
+// zero the leading (k - kk) slots of a list whose kk valid entries were written at list + (k - kk)
+__global__ void list_pad_kernel(unsigned long long* list, int n_zero, const unsigned long long* best, unsigned long long* best_slot) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n_zero) list[t] = 0ull;
+  if (t == 0) *best_slot = *best;
+}
+__global__ void list_unpack_kernel(const unsigned long long* list, int k, float* vals, uint32_t* idx, int32_t* count) {
+  // valid entries (non-zero) are at the end of the ascending list: compact them to the front of vals / idx
+  __shared__ int nz;
+  if (threadIdx.x == 0) {
+    int z = 0;
+    while (z < k && list[z] == 0ull) ++z;
+    nz = z;
+    if (count) *count = k - z;
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t + nz < k; t += blockDim.x) {
+    const unsigned long long key = list[nz + t];
+    if (vals) vals[t] = from_orderable_u32((unsigned)(key >> 32));
+    if (idx) idx[t] = (uint32_t)(key & 0xFFFFFFFFull);
+  }
+}
+
+// optimizer.py:203-207: arg-max over concat(refined points, random candidates), first occurrence (a refined point wins a
+// tie); the winner's raw coordinates (projection onto the domain happens in to_dict on the host: quirk Q11).
+__global__ void propose_kernel(const __grid_constant__ SamplerPack sp, const float* __restrict__ opt_x, const float* __restrict__ opt_val,
+                               int S, const unsigned long long* __restrict__ best_rnd, float* out) {
+  __shared__ unsigned long long red[32];
+  const int t = threadIdx.x, d = sp.d;
+  unsigned long long b = 0ull;
+  for (int j = t; j < S; j += blockDim.x) {
+    const unsigned long long key = pack_best(opt_val[j], (uint32_t)j);
+    b = key > b ? key : b;
+  }
+  b = warp_max_u64(b);
+  if ((t & 31) == 0) red[t >> 5] = b;
+  __syncthreads();
+  if (t < 32) {
+    b = t < (int)(blockDim.x >> 5) ? red[t] : 0ull;
+    b = warp_max_u64(b);
+    if (t == 0) red[0] = b;
+  }
+  __syncthreads();
+  const unsigned long long b_opt = red[0], b_rnd = best_rnd ? *best_rnd : 0ull;
+  const bool take_opt = S > 0 && (b_opt >> 32) >= (b_rnd >> 32);
+  const uint32_t j = 0xFFFFFFFFu - (uint32_t)((take_opt ? b_opt : b_rnd) & 0xFFFFFFFFull);
+  if (t < d) out[t] = take_opt ? opt_x[(size_t)j * d + t] : sample_coord(sp.dim[t], (uint64_t)j);
+  if (t == 0) {
+    out[d] = from_orderable_u32((uint32_t)((take_opt ? b_opt : b_rnd) >> 32));
+    out[d + 1] = __uint_as_float(take_opt ? j : (uint32_t)S + j);  // position in the concatenation, as raw bits
+  }
+}
+
+}  // namespace bx
+
+extern "C" size_t bx_score_topk_workspace_bytes(uint64_t m_count, int32_t k) {
+  if (k <= 0 || k > BX_MAX_K) return 0;
+  return carve_sample_ws(nullptr, m_count, k).bytes;
+}
+
+extern "C" int32_t bx_score_generated_topk(const bx_factor_t* f, const uint32_t key[2], const bx_dim_t* dims, uint64_t m_begin,
+                                           uint64_t m_count, int32_t acq_id, float acq_param, float ystar, int32_t k,
+                                           uint64_t* d_list, float* d_vals, uint32_t* d_idx, int32_t* d_count, float* d_acq,
+                                           int32_t engine, void* d_ws, size_t ws_bytes, void* stream) {
+  int32_t rc = check_factor(f);
+  if (rc) return rc;
+  BX_CHECK_ARG(d_list && d_ws, BX_E_ARG, "null pointer argument");
+  BX_CHECK_ARG(acq_id >= 0 && acq_id <= 3, BX_E_ARG, "unknown acquisition id %d", acq_id);
+  BX_CHECK_ARG(k > 0 && k <= BX_MAX_K, BX_E_RANGE, "k=%d outside [1, %d]", k, BX_MAX_K);
+  BX_CHECK_ARG(m_count > 0 && m_begin + m_count <= 0x100000000ull, BX_E_RANGE, "candidate indices must stay in [0, 2^32)");
+  BX_CHECK_ARG(ws_bytes >= bx_score_topk_workspace_bytes(m_count, k), BX_E_WORKSPACE, "workspace too small");
+  SamplerPack sp;
+  rc = make_sampler(key, dims, f->d, &sp);
+  if (rc) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  SampleWs w = carve_sample_ws(d_ws, m_count, k);
+  unsigned long long* list = reinterpret_cast<unsigned long long*>(d_list);
+  BX_CUDA(cudaMemsetAsync(w.best, 0, 8, s));
+  ScoreArgs a{};
+  a.f = *f; a.cand = nullptr; a.m_begin = m_begin; a.m_count = m_count; a.acq_id = acq_id; a.acq_param = acq_param;
+  a.ystar = ystar; a.acq = d_acq; a.best = w.best; a.index_base = m_begin;
+  if (engine == BX_ENGINE_AUTO) engine = score_tc16_supported(*f) ? BX_ENGINE_TCGEN05_F16 : BX_ENGINE_SIMT;
+  if (engine == BX_ENGINE_TCGEN05_F16) {
+    BX_CHECK_ARG(score_tc16_supported(*f), BX_E_UNSUPPORTED, "the fp16 tcgen05 engine needs the T16hi/T16lo split of the factor and d <= 32");
+    const unsigned grid = score_tc16p_grid(m_count);
+    BX_CHECK_ARG((int)grid <= sm_count(), BX_E_WORKSPACE, "grid %u exceeds the slab workspace", grid);
+    a.topk_slab = w.slabs; a.topk_count = w.counts; a.topk_k = k;
+    rc = launch_score_tc16p(s, a, sp);
+    if (rc) return rc;
+    return launch_topk_merge(s, w.slabs, w.counts, (int)grid, tk::CAP, k, w.scratch, list, w.best, 1, 1, d_vals, d_idx, d_count);
+  }
+  // un-fused engines: acquisition vector into the workspace (or the caller's d_acq), radix select over it
+  float* acq = d_acq ? d_acq : w.acq;
+  a.acq = acq;
+  if (engine == BX_ENGINE_TCGEN05_TF32) {
+    BX_CHECK_ARG(score_tc_supported(*f), BX_E_UNSUPPORTED, "the 3xTF32 tcgen05 engine needs the Thi/Tlo split of the factor and d <= 32");
+    rc = launch_score_tc2(s, a, sp);
+  } else {
+    BX_CHECK_ARG(engine == BX_ENGINE_SIMT, BX_E_ARG, "unknown engine %d", engine);
+    rc = launch_score_simt(s, a, &sp, true);
+  }
+  if (rc) return rc;
+  const int kk = (uint64_t)k <= m_count ? k : (int)m_count;
+  rc = launch_topk_values(s, acq, m_count, kk, m_begin, nullptr, nullptr, list + (k - kk), w.topk);
+  if (rc) return rc;
+  list_pad_kernel<<<(k - kk + 255) / 256 + 1, 256, 0, s>>>(list, k - kk, w.best, list + k);
+  BX_LAUNCH_CHECK();
+  if (d_vals || d_idx || d_count) {
+    list_unpack_kernel<<<1, 256, 0, s>>>(list, k, d_vals, d_idx, d_count);
+    BX_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+extern "C" int32_t bx_propose(const uint32_t key[2], const bx_dim_t* dims, int32_t d, const float* d_opt_x, const float* d_opt_val,
+                              int32_t S, const uint64_t* d_best, float* d_out, void* stream) {
+  SamplerPack sp;
+  int32_t rc = make_sampler(key, dims, d, &sp);
+  if (rc) return rc;
+  BX_CHECK_ARG(d_out && (S == 0 || (d_opt_x && d_opt_val)) && (S > 0 || d_best), BX_E_ARG, "null pointer argument");
+  BX_CHECK_ARG(S >= 0 && S <= BX_MAX_K, BX_E_RANGE, "S=%d outside [0, %d]", S, BX_MAX_K);
+  propose_kernel<<<1, 128, 0, (cudaStream_t)stream>>>(sp, d_opt_x, d_opt_val, S, reinterpret_cast<const unsigned long long*>(d_best), d_out);
+  BX_LAUNCH_CHECK();
+  return 0;
 }
 
 // Masked pairwise kernel matrix - replaces: gp.py:20-23 cov (x1 [n1 x d], x2 [n2 x d] already divided by the length scale).

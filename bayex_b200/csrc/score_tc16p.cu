@@ -24,6 +24,7 @@
 //   empty_b[s], tmem_full[a] (both) <- tcgen05.commit.multicast;  tmem_empty[a] (leader, count 8) <- epilogue warps
 //   full_u[s] / empty_u[s] (CTA-local) <- bulk copy complete_tx / 8 producer warps
 #include "tc_common.cuh"
+#include "topk_fused.cuh"
 
 namespace bx {
 namespace tc16p {
@@ -62,6 +63,7 @@ struct __align__(16) Smem {
   unsigned long long full_a[SA], empty_a[SA], full_b[SB], empty_b[SB], full_u[NU], empty_u[NU], tmem_full[NACC],
       tmem_empty[NACC], mean_full, mean_empty;
   uint32_t tmem_base;
+  tk::Shared topk;  // fused per-CTA top-k (epilogue warps)
 };
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -199,6 +201,14 @@ score_tc16p_kernel(const __grid_constant__ ScoreArgs a, const __grid_constant__ 
     const float unscale2 = unscale * unscale, mean_unscale = 1.f / ksc;
     uint32_t acc_ph = 0, tiles_done = 0;
     unsigned long long best = 0ull;
+    // fused top-k (optimizer.py:196): this CTA's slab of survivors; named barrier 2 = the four epilogue warps
+    const int et = tid - 4 * 32;
+    const int topk_k = a.topk_k;
+    unsigned long long* const slab = topk_k ? a.topk_slab + (size_t)blockIdx.x * tk::CAP : nullptr;
+    if (topk_k) {
+      tk::init(S.topk, et);
+      tk::bar<2>();
+    }
     for (uint64_t pt = pair0; pt < npairs; pt += pstride, ++tiles_done) {
       const uint64_t tile = 2 * pt + rank;
       float ss = 0.f;
@@ -243,8 +253,11 @@ score_tc16p_kernel(const __grid_constant__ ScoreArgs a, const __grid_constant__ 
         if (a.acq) a.acq[row] = av;
         const unsigned long long key = pack_best(av, (uint32_t)(a.index_base + row));
         best = key > best ? key : best;
+        if (topk_k) tk::push(S.topk, slab, tk::topk_key(av, (uint32_t)(a.index_base + row)));
       }
+      if (topk_k) tk::end_tile<2>(S.topk, slab, topk_k, et);
     }
+    if (topk_k) tk::finish<2>(S.topk, slab, topk_k, et, a.topk_count + blockIdx.x);
     if (a.best) {
       best = warp_max_u64(best);
       if (lane == 0 && best) atomicMax(a.best, best);
@@ -376,6 +389,12 @@ score_tc16p_kernel(const __grid_constant__ ScoreArgs a, const __grid_constant__ 
   }
 }
 
+static unsigned pair_grid(uint64_t m_count, int sms) {
+  const uint64_t ntiles = (m_count + TM - 1) / TM, npairs = (ntiles + 1) / 2;
+  const uint64_t max_pairs = (uint64_t)(sms / 2);
+  return 2u * (unsigned)(npairs < max_pairs ? npairs : max_pairs);
+}
+
 template <int D4, int RC>
 static int32_t launch_d4(cudaStream_t s, const ScoreArgs& a, const SamplerPack& sp, const CUtensorMap& mh, const CUtensorMap& ml) {
   const size_t smem = sizeof(Smem) + sizeof(float) * NU * (BKH * D4 + BKH) + (D4 <= 28 ? sizeof(float) * TM * D4 : 0);
@@ -383,9 +402,7 @@ static int32_t launch_d4(cudaStream_t s, const ScoreArgs& a, const SamplerPack& 
   int dev = 0, sms = 0;
   BX_CUDA(cudaGetDevice(&dev));
   BX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  const uint64_t ntiles = (a.m_count + TM - 1) / TM, npairs = (ntiles + 1) / 2;
-  const uint64_t max_pairs = (uint64_t)(sms / 2);
-  const unsigned grid = 2u * (unsigned)(npairs < max_pairs ? npairs : max_pairs);
+  const unsigned grid = pair_grid(a.m_count, sms);
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(NTHREADS);
@@ -403,6 +420,14 @@ static int32_t launch_d4(cudaStream_t s, const ScoreArgs& a, const SamplerPack& 
 }
 
 }  // namespace tc16p
+
+unsigned score_tc16p_grid(uint64_t m_count) {
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return tc16p::pair_grid(m_count, sms);
+}
+
+bool score_tc16_supported(const bx_factor_t& f) { return f.d_T16hi && f.d_T16lo && f.d4 <= 32; }
 
 int32_t launch_score_tc16p(cudaStream_t s, const ScoreArgs& a_in, const SamplerPack& sp) {
   ScoreArgs a = a_in;

@@ -314,6 +314,8 @@ static int32_t launch_d4(cudaStream_t s, const ScoreArgs& a, const SamplerPack& 
 
 }  // namespace tc2
 
+bool score_tc_supported(const bx_factor_t& f) { return f.d_Thi && f.d_Tlo && f.d4 <= 32; }
+
 int32_t launch_score_tc2(cudaStream_t s, const ScoreArgs& a_in, const SamplerPack& sp) {
   ScoreArgs a = a_in;
   if (const char* e = getenv("BX_TC_ABLATE")) a.debug = atoi(e);

@@ -43,16 +43,12 @@ extern "C" {
 
 /* acquisition ids - names follow bayex.acq (acq.py:8,53,90,124) */
 enum { BX_ACQ_EI = 0, BX_ACQ_PI = 1, BX_ACQ_UCB = 2, BX_ACQ_LCB = 3 };
-/* scoring engines */
+/* scoring engines: one production engine per regime, no zoo (the superseded experiments live in scripts/dev/engines) */
 enum {
-  BX_ENGINE_AUTO = 0,
-  BX_ENGINE_SIMT = 1,
-  BX_ENGINE_TCGEN05 = 2,      /* 3xTF32, one CTA per tile */
-  BX_ENGINE_TCGEN05_PAIR = 3, /* 3xTF32, cta_group::2 */
-  BX_ENGINE_TCGEN05_F16 = 4,  /* fp16 head/tail split (same 22-bit operands, half the tensor work) */
-  BX_ENGINE_TCGEN05_F16_PAIR = 5, /* fp16 head/tail split, cta_group::2, register-tiled K* producers (AUTO picks this) */
-  BX_ENGINE_TCGEN05_F16_SHARED = 6, /* fp16 head/tail split, K* generation shared by a 2-CTA cluster through DSMEM */
-  BX_ENGINE_TCGEN05_F16_T = 7 /* experimental: fp16 head/tail split, CTA pair, transposed tiling (T rows on the TMEM lanes: K* generated once per 1024 rows) */
+  BX_ENGINE_AUTO = 0,          /* fp16 tcgen05 engine when the factor has its fp16 copies and d <= 32, else SIMT */
+  BX_ENGINE_SIMT = 1,          /* fp32 FFMA pipes: explicit point sets, d > 32, and the on-GPU cross-check */
+  BX_ENGINE_TCGEN05_TF32 = 2,  /* 3xTF32, cta_group::2 (full fp32 exponent range of T; needs d_Thi / d_Tlo; opt-in) */
+  BX_ENGINE_TCGEN05_F16 = 3    /* fp16 head/tail split, cta_group::2, register-tiled K* producers: the production engine */
 };
 
 /* One dimension of the parameter space - mirrors bayex.domain.Real / Integer (domain.py:22-131). */
@@ -154,6 +150,32 @@ int32_t bx_score_generated(const bx_factor_t* f, const uint32_t key[2], const bx
 size_t bx_topk_workspace_bytes(uint64_t M, int32_t k);
 int32_t bx_topk(const float* d_vals, uint64_t M, int32_t k, uint64_t index_base, float* d_out_vals,
                 uint32_t* d_out_idx, void* d_ws, size_t ws_bytes, void* stream);
+
+/* The list format of the fused top-k: uint64 [k + 1].  Entries [0, k) are the k largest (orderable(value) << 32 | global
+ * candidate index) keys in ascending order - the order of `jnp.argsort(acq_vals)[-k:]` (optimizer.py:196: stable, NaN
+ * last, the higher index wins among equal values); when fewer than k candidates exist the leading slots are 0.  Entry [k]
+ * is the packed arg-max key of the same candidates (bx_pack: first occurrence wins, optimizer.py:205). */
+
+/* Fused generate -> score -> top-k -> arg-max over candidates [m_begin, m_begin + m_count) of sample_params(key, (M,)) -
+ * replaces: optimizer.py:183-197 + :205.  On the fp16 tcgen05 engine the top-k is kept per CTA
+ * inside the scoring epilogue and nothing per candidate is written to HBM (d_acq == NULL); d_acq (optional, [m_count])
+ * additionally receives every acquisition value.  d_vals / d_idx / d_count (optional): the valid entries of the list
+ * unpacked, ascending, at the front of d_vals [k] / d_idx [k]. */
+size_t bx_score_topk_workspace_bytes(uint64_t m_count, int32_t k);
+int32_t bx_score_generated_topk(const bx_factor_t* f, const uint32_t key[2], const bx_dim_t* dims, uint64_t m_begin,
+                                uint64_t m_count, int32_t acq_id, float acq_param, float ystar, int32_t k, uint64_t* d_list,
+                                float* d_vals, uint32_t* d_idx, int32_t* d_count, float* d_acq, int32_t engine, void* d_ws,
+                                size_t ws_bytes, void* stream);
+/* Merge n_lists lists (k + 1 entries each, contiguous) into one - the candidate shards of a multi-GPU sample() after their
+ * all-gather.  d_ws: n_lists * k * 8 bytes.  Outputs as above. */
+int32_t bx_topk_merge(const uint64_t* d_lists, int32_t n_lists, int32_t k, uint64_t* d_list_out, float* d_vals,
+                      uint32_t* d_idx, int32_t* d_count, void* d_ws, size_t ws_bytes, void* stream);
+/* The proposal - replaces: optimizer.py:203-207 (concat(refined, random), arg-max with first occurrence, gather).
+ * d_opt_x [S x d] / d_opt_val [S]: refined points and their acquisition values; d_best: packed arg-max key of the random
+ * candidates (entry [k] of a list).  d_out [d + 2]: the winner's raw coordinates (a random winner is regenerated from
+ * the key), its acquisition value, and its position in the concatenation as uint32 bits. */
+int32_t bx_propose(const uint32_t key[2], const bx_dim_t* dims, int32_t d, const float* d_opt_x, const float* d_opt_val,
+                   int32_t S, const uint64_t* d_best, float* d_out, void* stream);
 
 /* Multi-start refinement - replaces: optimizer.py:39-73,198-199 (L-BFGS, parity unpinned -> monotone analytic-gradient
  * ascent).  d_x [S x d] start points in, refined points out; d_val [S] acquisition at the result. */
