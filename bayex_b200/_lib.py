@@ -19,8 +19,9 @@ if not os.path.exists(LIB_PATH):
 lib = C.CDLL(LIB_PATH)
 
 ACQ_IDS = {"EI": 0, "PI": 1, "UCB": 2, "LCB": 3}
-ENGINE_AUTO, ENGINE_SIMT, ENGINE_TCGEN05_TF32, ENGINE_TCGEN05_F16 = 0, 1, 2, 3
+ENGINE_AUTO, ENGINE_SIMT, ENGINE_TCGEN05_F16, ENGINE_TCGEN05_F16_RAW = 0, 1, 2, 3
 MAX_D, MAX_K, TILE, FIT_BATCH_MAX = 64, 1024, 128, 32
+E_ARG, E_RANGE, E_WORKSPACE, E_NOTPD, E_UNSUPPORTED = -1, -2, -3, -4, -5
 POINTS_TC_MIN = 65536  # BX_POINTS_TC_MIN
 
 
@@ -30,7 +31,7 @@ class DimT(C.Structure):
 
 class FactorT(C.Structure):
     _fields_ = [("n", C.c_int32), ("np", C.c_int32), ("d", C.c_int32), ("d4", C.c_int32),
-                ("d_U", C.c_void_p), ("d_T", C.c_void_p), ("d_Thi", C.c_void_p), ("d_Tlo", C.c_void_p),
+                ("d_U", C.c_void_p), ("d_T", C.c_void_p),
                 ("d_T16hi", C.c_void_p), ("d_T16lo", C.c_void_p), ("d_alpha", C.c_void_p), ("d_scale", C.c_void_p), ("d_hyp", C.c_void_p)]
 
 
@@ -41,6 +42,7 @@ _key = C.POINTER(C.c_uint32)
 SIGNATURES = {
     "bx_version": (_i32, []),
     "bx_last_error": (C.c_char_p, []),
+    "bx_check_status": (_i32, [_vp, _vp]),
     "bx_threefry_fill": (_i32, [_key, C.POINTER(DimT), _i32, _u64, _u64, _vp, _vp]),
     "bx_domain_sample": (_i32, [_key, C.POINTER(DimT), _u64, _u64, _vp, _vp]),
     "bx_threefry_gather": (_i32, [_key, C.POINTER(DimT), _i32, _vp, _i32, _vp, _vp]),
@@ -49,10 +51,16 @@ SIGNATURES = {
     "bx_nlml_grad": (_i32, [_vp, _vp, _i32, _i32, _vp, _vp, _vp, _sz, _vp]),
     "bx_fit_adamw": (_i32, [_vp, _vp, _i32, _i32, _vp, _f32, _i32, _vp, _vp, _sz, _i32, _vp]),
     "bx_fit_adamw_batch": (_i32, [_vp, _vp, _i32, _i32, _vp, _i32, _f32, _i32, _vp, _vp, _sz, _vp]),
-    "bx_factor_build": (_i32, [_vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
-    "bx_score_points": (_i32, [C.POINTER(FactorT), _vp, _u64, _i32, _f32, _f32, _vp, _vp, _vp, _vp, _u64, _vp]),
+    "bx_factor_build": (_i32, [_vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "bx_score_workspace_bytes": (_sz, [_u64]),
+    "bx_score_points": (_i32, [C.POINTER(FactorT), _vp, _u64, _i32, _f32, _f32, _vp, _vp, _vp, _vp, _u64, _vp, _sz, _vp]),
     "bx_score_generated": (_i32, [C.POINTER(FactorT), _key, C.POINTER(DimT), _u64, _u64, _i32, _f32, _f32, _vp, _vp,
-                                  _i32, _vp]),
+                                  _i32, _vp, _sz, _vp]),
+    "bx_score_topk_workspace_bytes": (_sz, [_u64, _i32]),
+    "bx_score_generated_topk": (_i32, [C.POINTER(FactorT), _key, C.POINTER(DimT), _u64, _u64, _i32, _f32, _f32, _i32, _vp,
+                                       _vp, _vp, _vp, _vp, _i32, _vp, _sz, _vp]),
+    "bx_topk_merge": (_i32, [_vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "bx_propose": (_i32, [_key, C.POINTER(DimT), _i32, _vp, _vp, _i32, _vp, _vp, _vp]),
     "bx_topk_workspace_bytes": (_sz, [_u64, _i32]),
     "bx_topk": (_i32, [_vp, _u64, _i32, _u64, _vp, _vp, _vp, _sz, _vp]),
     "bx_refine_workspace_bytes": (_sz, [C.POINTER(FactorT), _i32]),
@@ -60,6 +68,7 @@ SIGNATURES = {
     "bx_pack": (_u64, [_f32, C.c_uint32]),
     "bx_unpack": (None, [_u64, C.POINTER(_f32), C.POINTER(C.c_uint32)]),
     "bx_selftest_umma": (_i32, [_vp, _vp, _vp, _i32, _i32, _vp]),
+    "bx_selftest_ffma": (_i32, [_vp, _i32, _i32, _vp]),
 }
 for _name, (_res, _args) in SIGNATURES.items():
     _fn = getattr(lib, _name)

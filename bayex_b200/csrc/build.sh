@@ -6,7 +6,7 @@ OUT="$HERE/../libbayex_b200.so"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -Wall
        --expt-relaxed-constexpr -Xptxas -v)
-UNITS="linalg fit score score_tc2 score_tc16p selftest topk refine"
+UNITS="linalg fit score score_tc16p selftest topk refine"
 mkdir -p "$HERE/build"
 rm -f "$HERE"/build/*.o
 pids=()

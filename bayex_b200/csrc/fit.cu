@@ -119,8 +119,8 @@ __global__ void zero_pad_absmax_kernel(float* T, int n, int np, unsigned int* ab
   for (int o = 16; o > 0; o >>= 1) b = max(b, __shfl_xor_sync(0xffffffffu, b, o));
   if ((threadIdx.x & 31) == 0 && b) atomicMax(absmax_bits, b);
 }
-// TF32 head/tail (T & 0xFFFFE000, T - head) and fp16 head/tail of T * 2^b, 2^b chosen so max|T| 2^b is in [2^13, 2^14].
-__global__ void split_T_kernel(const float* __restrict__ T, int np, float* Thi, float* Tlo, __half* H16, __half* L16,
+// fp16 head/tail of T * 2^b, 2^b chosen so max|T| 2^b is in [2^13, 2^14].
+__global__ void split_T_kernel(const float* __restrict__ T, int np, __half* H16, __half* L16,
                                const unsigned int* absmax_bits, float* hyp) {
   const float amax = __uint_as_float(*absmax_bits);
   const float sc = (amax > 0.f) ? exp2f(floorf(log2f(16384.f / amax))) : 1.f;
@@ -128,11 +128,6 @@ __global__ void split_T_kernel(const float* __restrict__ T, int np, float* Thi, 
   if (e == 0) hyp[HYP_T16SCALE] = sc;
   if (e >= (size_t)np * np) return;
   const float t = T[e];
-  if (Thi) {
-    const float hi = __uint_as_float(__float_as_uint(t) & 0xFFFFE000u);  // 10-bit mantissa: exact in TF32
-    Thi[e] = hi;
-    Tlo[e] = t - hi;
-  }
   if (H16) {
     const float ts = t * sc;
     const __half h = __float2half_rn(ts);
@@ -255,6 +250,11 @@ __global__ void __launch_bounds__(256) grad_finalize_kernel(const float* __restr
 }
 
 // clip_by_global_norm(10) + adamw(lr) on the d+2 raw hypers (gp.py:99,105-106).  adam = [m | v | t].
+// The moment weights are 0.1f / 0.001f: optax writes (1 - decay) with `decay` a Python float, so the subtraction happens in
+// double (0.09999999999999998, 0.0010000000000000009) and is then rounded to float32 when it meets the float32 gradient -
+// that is float32(0.1) and float32(0.001), not the float32 differences 1.f - 0.9f / 1.f - 0.999f (= 0.00100005).  The
+// oracle (oracle/gp.py:adamw_step) does the same; tests/test_gpu_parity.py::test_adamw_kernel_step_by_step holds this
+// kernel to it at 1e-6 per step.
 __global__ void adamw_kernel(float* raw, const float* __restrict__ gbuf, int d, float lr, float* adam, float* trace,
                              int step) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
@@ -703,8 +703,17 @@ extern "C" int32_t bx_fit_adamw(const float* d_X, const float* d_y, int32_t n, i
     }
     cudaError_t ce = cudaStreamEndCapture(s, &graph);
     if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
-    BX_CUDA(ce);
-    BX_CUDA(cudaGraphInstantiate(&exec, graph, 0));
+    if (ce != cudaSuccess) {
+      if (graph) cudaGraphDestroy(graph);
+      BX_CUDA(ce);
+    }
+    {
+      const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
+      if (ie != cudaSuccess) {  // the captured graph must not leak when instantiation fails
+        cudaGraphDestroy(graph);
+        BX_CUDA(ie);
+      }
+    }
     for (int i = 0; i < steps; ++i) {
       cudaError_t e = cudaGraphLaunch(exec, s);
       if (e != cudaSuccess) {
@@ -846,12 +855,11 @@ extern "C" int32_t bx_fit_adamw_batch(const float* d_X, const float* d_y, int32_
 }
 
 extern "C" int32_t bx_factor_build(const float* d_X, const float* d_y, int32_t n, int32_t d, const float* d_raw,
-                                   float* d_U, float* d_T, float* d_Thi, float* d_Tlo, void* d_T16hi, void* d_T16lo,
+                                   float* d_U, float* d_T, void* d_T16hi, void* d_T16lo,
                                    float* d_alpha, float* d_scale, float* d_hyp, void* d_ws, size_t ws_bytes, void* stream) {
   int32_t rc = check_fit_args(d_X, d_y, n, d, d_raw, d_ws, ws_bytes);
   if (rc) return rc;
   BX_CHECK_ARG(d_U && d_T && d_alpha && d_scale && d_hyp, BX_E_ARG, "null factor output");
-  BX_CHECK_ARG((d_Thi == nullptr) == (d_Tlo == nullptr), BX_E_ARG, "Thi and Tlo must be given together");
   BX_CHECK_ARG((d_T16hi == nullptr) == (d_T16lo == nullptr), BX_E_ARG, "T16hi and T16lo must be given together");
   cudaStream_t s = (cudaStream_t)stream;
   FitWs w = carve_fit_ws(d_ws, n, d);
@@ -866,8 +874,20 @@ extern "C" int32_t bx_factor_build(const float* d_X, const float* d_y, int32_t n
   BX_CUDA(cudaMemsetAsync(amax, 0, sizeof(unsigned int), s));
   zero_pad_absmax_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(d_T, n, w.np, amax);
   BX_LAUNCH_CHECK();
-  split_T_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(d_T, w.np, d_Thi, d_Tlo, reinterpret_cast<__half*>(d_T16hi),
+  split_T_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(d_T, w.np, reinterpret_cast<__half*>(d_T16hi),
                                                                reinterpret_cast<__half*>(d_T16lo), amax, d_hyp);
   BX_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int32_t bx_check_status(const float* d_hyp, void* stream) {
+  BX_CHECK_ARG(d_hyp, BX_E_ARG, "null pointer argument");
+  float st = 0.f;
+  BX_CUDA(cudaMemcpyAsync(&st, d_hyp + HYP_STATUS, sizeof(float), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  BX_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  if (st != 0.f) {
+    set_error("Cholesky met a non-finite or non-positive pivot (status %g): the Gram matrix is not positive definite", (double)st);
+    return BX_E_NOTPD;
+  }
   return 0;
 }

@@ -91,10 +91,17 @@ struct ScoreArgs {
   unsigned long long* topk_slab;
   unsigned int* topk_count;
   int topk_k;
+  // hand-over of cancellation-regime candidates from the fp16 tcgen05 engine to the fp32 SIMT engine: the tensor engine
+  // appends the launch-relative row of every candidate whose variance is below flag_tau * amp to flag_list (and writes no
+  // output for it); the SIMT engine then scores exactly the rows flag_list[0 .. *flag_count)
+  uint32_t* flag_list;
+  unsigned int* flag_count;
+  float flag_tau;
 };
 
 // Fused-top-k plumbing shared by score.cu / topk.cu / score_tc16p.cu
 unsigned score_tc16p_grid(uint64_t m_count);  // CTAs the fp16 engine launches for m_count candidates (slabs to merge)
+unsigned score_simt_grid(uint64_t m_count, int sms);
 // Reduce `nslabs` key slabs (`stride` keys apart, counts[b] valid keys each; counts == nullptr: every non-zero key is
 // valid) to the sorted list format: list_out[0..k) ascending keys (empty slots = 0 first), list_out[k] = max of the
 // n_best keys best_in[i * best_stride].  Optional unpacked outputs: the `count` valid entries ascending at the front of

@@ -61,9 +61,17 @@ constexpr int KS = 16;   // observations per k-step
 constexpr int SP = CT + 4;
 
 
+// Persistent over 64-candidate tiles.  Two ways to name the candidates of a launch:
+//   direct (a.flag_list == nullptr): rows [0, m_count) of the launch;
+//   list   (a.flag_list != nullptr): rows flag_list[0 .. *flag_count) - the candidates the fp16 tcgen05 engine handed over
+//           because their variance sits in the cancellation regime (score_tc16p.cu); count read on the device.
+// A row's candidate is generated from the key (GEN, index m_begin + row) or read from a.cand[row]; outputs go to slot
+// `row`.  With a.topk_k > 0 threads 0..127 also run the fused top-k collector (topk_fused.cuh), one slab per CTA.
 template <bool GEN>
 __global__ void __launch_bounds__(256) score_simt_kernel(const __grid_constant__ ScoreArgs a, const __grid_constant__ SamplerPack sp) {
   extern __shared__ __align__(16) float sm[];
+  __shared__ tk::Shared tks;
+  __shared__ uint32_t rows_s[CT];
   const int d = a.f.d, d4 = a.f.d4, np = a.f.np, cs_ld = d4 + 1;
   float* cs = sm;                         // [CT][d4+1] scaled candidate coordinates
   float* us = cs + CT * cs_ld;            // [KS][d4]   scaled observation rows of the current k-step
@@ -71,18 +79,29 @@ __global__ void __launch_bounds__(256) score_simt_kernel(const __grid_constant__
   float* Ks = Ts + KS * SP;               // [KS][SP]   K* tile, k-major
   float* red = Ks + KS * SP;              // [4][CT]    mean partials, then sum v^2
   const int tid = threadIdx.x;
-  const uint64_t c_base = (uint64_t)blockIdx.x * CT;
+  const uint64_t total = a.flag_list ? (uint64_t)*a.flag_count : a.m_count;
+  const float amp = a.f.d_hyp[HYP_AMP];
+  const int topk_k = a.topk_k;
+  unsigned long long* const slab = topk_k ? a.topk_slab + (size_t)blockIdx.x * tk::CAP : nullptr;
+  if (topk_k && tid < tk::TPB) {
+    tk::init(tks, tid);
+    tk::bar<1>();
+  }
+  unsigned long long best = 0ull;
 
+  for (uint64_t c_base = (uint64_t)blockIdx.x * CT; c_base < total; c_base += (uint64_t)gridDim.x * CT) {
+  if (tid < CT) rows_s[tid] = (c_base + tid < total) ? (a.flag_list ? a.flag_list[c_base + tid] : (uint32_t)(c_base + tid)) : 0xFFFFFFFFu;
+  __syncthreads();
   for (int e = tid; e < CT * d4; e += 256) {
     const int c = e / d4, k = e % d4;
     float v = 0.f;
-    if (k < d && c_base + c < a.m_count) {
-      const float raw = GEN ? sample_coord(sp.dim[k], a.m_begin + c_base + c) : a.cand[(c_base + c) * d + k];
+    const uint32_t row = rows_s[c];
+    if (k < d && row != 0xFFFFFFFFu) {
+      const float raw = GEN ? sample_coord(sp.dim[k], a.m_begin + row) : a.cand[(uint64_t)row * d + k];
       v = raw * a.f.d_scale[k];
     }
     cs[c * cs_ld + k] = v;
   }
-  const float amp = a.f.d_hyp[HYP_AMP];
   __syncthreads();
 
   const int rg = tid & 15, cg = tid >> 4;    // accumulator mapping: rows 4rg.., candidates 4cg..
@@ -154,20 +173,25 @@ __global__ void __launch_bounds__(256) score_simt_kernel(const __grid_constant__
     for (int c = 0; c < 4; ++c) red[cg * 4 + c] = ss[c];
   }
   __syncthreads();
-  unsigned long long key = 0ull;
-  if (tid < CT && c_base + tid < a.m_count) {
+  if (tid < CT && rows_s[tid] != 0xFFFFFFFFu) {
     const float var = amp - red[tid];                 // diag(amp*cov(xt,xt) - v^T v)   gp.py:69
     const float sd = sqrtf(fmaxf(var, 1e-10f));       // gp.py:70
     const float av = acquisition(a.acq_id, mu, sd, a.ystar, a.acq_param);
-    const uint64_t row = c_base + tid;
+    const uint64_t row = rows_s[tid];
     if (a.mu) a.mu[row] = mu;
     if (a.sigma) a.sigma[row] = sd;
     if (a.acq) a.acq[row] = av;
-    key = pack_best(av, (uint32_t)(a.index_base + row));
+    const unsigned long long key = pack_best(av, (uint32_t)(a.index_base + row));
+    best = key > best ? key : best;
+    if (topk_k) tk::push(tks, slab, tk::topk_key(av, (uint32_t)(a.index_base + row)));
   }
+  if (topk_k && tid < tk::TPB) tk::end_tile<1>(tks, slab, topk_k, tid);
+  __syncthreads();  // rows_s / red are rewritten by the next tile
+  }
+  if (topk_k && tid < tk::TPB) tk::finish<1>(tks, slab, topk_k, tid, a.topk_count + blockIdx.x);
   if (a.best && tid < CT) {
-    key = warp_max_u64(key);
-    if ((tid & 31) == 0 && key) atomicMax(a.best, key);
+    best = warp_max_u64(best);
+    if ((tid & 31) == 0 && best) atomicMax(a.best, best);
   }
 }
 
@@ -181,10 +205,20 @@ int32_t check_factor(const bx_factor_t* f) {
   return 0;
 }
 
+// CTAs the SIMT engine launches for up to `m_count` candidates: persistent, at most SIMT_CTAS_PER_SM per SM
+constexpr int SIMT_CTAS_PER_SM = 3;
+unsigned score_simt_grid(uint64_t m_count, int sms) {
+  const uint64_t ntiles = (m_count + CT - 1) / CT, cap = (uint64_t)sms * SIMT_CTAS_PER_SM;
+  return (unsigned)(ntiles < cap ? (ntiles ? ntiles : 1) : cap);
+}
+
 int32_t launch_score_simt(cudaStream_t s, const ScoreArgs& a, const SamplerPack* sp, bool gen) {
   static SamplerPack empty{};
   const size_t smem = score_simt_smem(a.f.d4);
-  const unsigned grid = (unsigned)((a.m_count + CT - 1) / CT);
+  int dev = 0, sms = 148;
+  BX_CUDA(cudaGetDevice(&dev));
+  BX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const unsigned grid = score_simt_grid(a.m_count, sms);
   if (gen) {
     BX_CUDA(cudaFuncSetAttribute(score_simt_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     score_simt_kernel<true><<<grid, 256, smem, s>>>(a, *sp);
@@ -196,9 +230,6 @@ int32_t launch_score_simt(cudaStream_t s, const ScoreArgs& a, const SamplerPack*
   return 0;
 }
 
-// implemented in score_tc2.cu (3xTF32, CTA pair: the full fp32 exponent range of T; opt-in)
-int32_t launch_score_tc2(cudaStream_t s, const ScoreArgs& a, const SamplerPack& sp);
-bool score_tc_supported(const bx_factor_t& f);
 // implemented in score_tc16p.cu (fp16 head/tail, CTA pair, register-tiled producers): the production engine
 int32_t launch_score_tc16p(cudaStream_t s, const ScoreArgs& a, const SamplerPack& sp);
 bool score_tc16_supported(const bx_factor_t& f);
@@ -246,56 +277,7 @@ extern "C" int32_t bx_threefry_gather(const uint32_t key[2], const bx_dim_t* dim
   return 0;
 }
 
-extern "C" int32_t bx_score_points(const bx_factor_t* f, const float* d_cand, uint64_t M, int32_t acq_id, float acq_param,
-                                   float ystar, float* d_mu, float* d_sigma, float* d_acq, uint64_t* d_best,
-                                   uint64_t index_base, void* stream) {
-  int32_t rc = check_factor(f);
-  if (rc) return rc;
-  BX_CHECK_ARG(d_cand, BX_E_ARG, "null candidates");
-  BX_CHECK_ARG(acq_id >= 0 && acq_id <= 3, BX_E_ARG, "unknown acquisition id %d", acq_id);
-  BX_CHECK_ARG(index_base + M <= 0x100000000ull, BX_E_RANGE, "candidate indices must stay below 2^32");
-  if (M == 0) return 0;
-  ScoreArgs a{};
-  a.f = *f; a.cand = d_cand; a.m_begin = 0; a.m_count = M; a.acq_id = acq_id; a.acq_param = acq_param; a.ystar = ystar;
-  a.mu = d_mu; a.sigma = d_sigma; a.acq = d_acq; a.best = reinterpret_cast<unsigned long long*>(d_best); a.index_base = index_base;
-  // large explicit point sets (gp.predict / acq.* with M >= 2^16) take the production tcgen05 engine when the factor
-  // carries its fp16 copies: same fused pipeline, coordinates read from d_cand instead of drawn (SIMT: 16 TFLOP/s)
-  static const SamplerPack no_sampler{};
-  if (M >= BX_POINTS_TC_MIN && score_tc16_supported(*f)) return launch_score_tc16p((cudaStream_t)stream, a, no_sampler);
-  return launch_score_simt((cudaStream_t)stream, a, nullptr, false);
-}
-
-extern "C" int32_t bx_score_generated(const bx_factor_t* f, const uint32_t key[2], const bx_dim_t* dims, uint64_t m_begin,
-                                      uint64_t m_count, int32_t acq_id, float acq_param, float ystar, float* d_acq,
-                                      uint64_t* d_best, int32_t engine, void* stream) {
-  int32_t rc = check_factor(f);
-  if (rc) return rc;
-  BX_CHECK_ARG(acq_id >= 0 && acq_id <= 3, BX_E_ARG, "unknown acquisition id %d", acq_id);
-  BX_CHECK_ARG(m_begin + m_count <= 0x100000000ull, BX_E_RANGE, "candidate indices must stay below 2^32");
-  SamplerPack sp;
-  rc = make_sampler(key, dims, f->d, &sp);
-  if (rc) return rc;
-  if (m_count == 0) return 0;
-  ScoreArgs a{};
-  a.f = *f; a.cand = nullptr; a.m_begin = m_begin; a.m_count = m_count; a.acq_id = acq_id; a.acq_param = acq_param;
-  a.ystar = ystar; a.acq = d_acq; a.best = reinterpret_cast<unsigned long long*>(d_best); a.index_base = m_begin;
-  // AUTO: the fp16 head/tail CTA-pair engine whenever the factor carries its fp16 copies and d <= 32 (same 22 operand bits
-  // as 3xTF32 at half the tensor work); otherwise the fp32 SIMT engine.  The 3xTF32 engine (full fp32 exponent range of T)
-  // is opt-in and needs the Thi/Tlo copies.
-  if (engine == BX_ENGINE_AUTO) engine = score_tc16_supported(*f) ? BX_ENGINE_TCGEN05_F16 : BX_ENGINE_SIMT;
-  if (engine == BX_ENGINE_TCGEN05_TF32) {
-    BX_CHECK_ARG(score_tc_supported(*f), BX_E_UNSUPPORTED, "the 3xTF32 tcgen05 engine needs the Thi/Tlo split of the factor and d <= 32");
-    return launch_score_tc2((cudaStream_t)stream, a, sp);
-  }
-  if (engine == BX_ENGINE_TCGEN05_F16) {
-    BX_CHECK_ARG(score_tc16_supported(*f), BX_E_UNSUPPORTED, "the fp16 tcgen05 engine needs the T16hi/T16lo split of the factor and d <= 32");
-    return launch_score_tc16p((cudaStream_t)stream, a, sp);
-  }
-  BX_CHECK_ARG(engine == BX_ENGINE_SIMT, BX_E_ARG, "unknown engine %d", engine);
-  return launch_score_simt((cudaStream_t)stream, a, &sp, true);
-}
-
-// ---- fused sample() front half: generate -> score -> top-k -> arg-max (optimizer.py:183-197, :205) ---------------------
+// ---- the two-tier production path ---------------------------------------------------------------------------------------
 namespace bx {
 
 static int sm_count() {
@@ -305,16 +287,53 @@ static int sm_count() {
 }
 static size_t align256(size_t b) { return (b + 255) / 256 * 256; }
 
+// Share of the prior variance below which a candidate of the fp16 tcgen05 engine is handed to the fp32 SIMT engine.
+// Measured bias of the tensor engine on sum v^2: 3e-6 .. 6e-5 relative (scripts/dev/diag_bias_sign.py; worst on ill-
+// conditioned factors, noise = softplus(-8)); for var >= tau amp that is at most 6e-5 (1 - tau) / tau of var.
+static float handover_tau() {
+  if (const char* e = getenv("BX_HANDOVER_TAU")) return (float)atof(e);
+  return 0.5f;
+}
+
+struct HandoverWs {
+  unsigned int* count;
+  uint32_t* list;
+  size_t bytes;
+};
+static HandoverWs carve_handover(void* base, uint64_t m_count) {
+  HandoverWs h{};
+  h.count = reinterpret_cast<unsigned int*>(base);
+  h.list = base ? reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(base) + 256) : nullptr;
+  h.bytes = 256 + align256(4 * (size_t)m_count);
+  return h;
+}
+
+// fp16 tcgen05 engine over every candidate of the launch, then the fp32 SIMT engine over the rows it handed over
+// (variance in the cancellation regime).  a.topk_* (optional) name the slabs of the FIRST pass; the SIMT pass uses the
+// `grid1` slabs after them.  Returns the number of slabs in use through *nslabs.
+static int32_t launch_two_tier(cudaStream_t s, ScoreArgs a, const SamplerPack& sp, bool gen, const HandoverWs& h, bool raw,
+                               int* nslabs) {
+  const unsigned grid1 = score_tc16p_grid(a.m_count);
+  if (nslabs) *nslabs = (int)grid1;
+  if (raw) return launch_score_tc16p(s, a, sp);
+  BX_CUDA(cudaMemsetAsync(h.count, 0, sizeof(unsigned int), s));
+  a.flag_list = h.list; a.flag_count = h.count; a.flag_tau = handover_tau();
+  int32_t rc = launch_score_tc16p(s, a, sp);
+  if (rc) return rc;
+  if (a.topk_k) { a.topk_slab += (size_t)grid1 * tk::CAP; a.topk_count += grid1; }
+  if (nslabs) *nslabs = (int)(grid1 + score_simt_grid(a.m_count, sm_count()));
+  return launch_score_simt(s, a, &sp, gen);  // list mode: a.flag_list is set
+}
+
 struct SampleWs {
   unsigned long long *best, *slabs, *scratch;
   unsigned int* counts;
-  float* acq;   // un-fused engines only
-  void* topk;   // un-fused engines only (bx_topk workspace)
+  HandoverWs h;
   size_t bytes;
 };
 static SampleWs carve_sample_ws(void* base, uint64_t m_count, int k) {
   SampleWs w{};
-  const size_t grid = (size_t)sm_count();
+  const size_t nsl = (size_t)sm_count() * (1 + SIMT_CTAS_PER_SM);  // slabs: tensor pass + SIMT pass
   size_t off = 0;
   auto take = [&](size_t nbytes) {
     char* p = base ? reinterpret_cast<char*>(base) + off : nullptr;
@@ -322,39 +341,12 @@ static SampleWs carve_sample_ws(void* base, uint64_t m_count, int k) {
     return p;
   };
   w.best = reinterpret_cast<unsigned long long*>(take(8));
-  w.counts = reinterpret_cast<unsigned int*>(take(4 * grid));
-  w.slabs = reinterpret_cast<unsigned long long*>(take(8 * grid * tk::CAP));
-  w.scratch = reinterpret_cast<unsigned long long*>(take(8 * grid * (size_t)k));
-  const size_t fused = off;
-  // the un-fused path (SIMT / 3xTF32 engines) reuses the same memory: acquisition vector + radix-select state
-  off = align256(8);
-  w.acq = reinterpret_cast<float*>(take(4 * (size_t)m_count));
-  w.topk = take(bx_topk_workspace_bytes(m_count, k));
-  w.bytes = off > fused ? off : fused;
+  w.counts = reinterpret_cast<unsigned int*>(take(4 * nsl));
+  w.slabs = reinterpret_cast<unsigned long long*>(take(8 * nsl * tk::CAP));
+  w.scratch = reinterpret_cast<unsigned long long*>(take(8 * nsl * (size_t)k));
+  w.h = carve_handover(take(carve_handover(nullptr, m_count).bytes), m_count);
+  w.bytes = off;
   return w;
-}
-
-// zero the leading (k - kk) slots of a list whose kk valid entries were written at list + (k - kk)
-__global__ void list_pad_kernel(unsigned long long* list, int n_zero, const unsigned long long* best, unsigned long long* best_slot) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t < n_zero) list[t] = 0ull;
-  if (t == 0) *best_slot = *best;
-}
-__global__ void list_unpack_kernel(const unsigned long long* list, int k, float* vals, uint32_t* idx, int32_t* count) {
-  // valid entries (non-zero) are at the end of the ascending list: compact them to the front of vals / idx
-  __shared__ int nz;
-  if (threadIdx.x == 0) {
-    int z = 0;
-    while (z < k && list[z] == 0ull) ++z;
-    nz = z;
-    if (count) *count = k - z;
-  }
-  __syncthreads();
-  for (int t = threadIdx.x; t + nz < k; t += blockDim.x) {
-    const unsigned long long key = list[nz + t];
-    if (vals) vals[t] = from_orderable_u32((unsigned)(key >> 32));
-    if (idx) idx[t] = (uint32_t)(key & 0xFFFFFFFFull);
-  }
 }
 
 // optimizer.py:203-207: arg-max over concat(refined points, random candidates), first occurrence (a refined point wins a
@@ -389,11 +381,64 @@ __global__ void propose_kernel(const __grid_constant__ SamplerPack sp, const flo
 
 }  // namespace bx
 
+extern "C" size_t bx_score_workspace_bytes(uint64_t M) { return carve_handover(nullptr, M).bytes; }
+
+extern "C" int32_t bx_score_points(const bx_factor_t* f, const float* d_cand, uint64_t M, int32_t acq_id, float acq_param,
+                                   float ystar, float* d_mu, float* d_sigma, float* d_acq, uint64_t* d_best,
+                                   uint64_t index_base, void* d_ws, size_t ws_bytes, void* stream) {
+  int32_t rc = check_factor(f);
+  if (rc) return rc;
+  BX_CHECK_ARG(d_cand, BX_E_ARG, "null candidates");
+  BX_CHECK_ARG(acq_id >= 0 && acq_id <= 3, BX_E_ARG, "unknown acquisition id %d", acq_id);
+  BX_CHECK_ARG(index_base + M <= 0x100000000ull, BX_E_RANGE, "candidate indices must stay below 2^32");
+  if (M == 0) return 0;
+  ScoreArgs a{};
+  a.f = *f; a.cand = d_cand; a.m_begin = 0; a.m_count = M; a.acq_id = acq_id; a.acq_param = acq_param; a.ystar = ystar;
+  a.mu = d_mu; a.sigma = d_sigma; a.acq = d_acq; a.best = reinterpret_cast<unsigned long long*>(d_best); a.index_base = index_base;
+  // large explicit point sets (gp.predict / acq.* with M >= 2^16) take the two-tier production path when the factor
+  // carries its fp16 copies and the caller gave the hand-over workspace: same fused pipeline, coordinates read from
+  // d_cand instead of drawn
+  static const SamplerPack no_sampler{};
+  if (M >= BX_POINTS_TC_MIN && score_tc16_supported(*f) && d_ws) {
+    BX_CHECK_ARG(ws_bytes >= bx_score_workspace_bytes(M), BX_E_WORKSPACE, "workspace too small");
+    return launch_two_tier((cudaStream_t)stream, a, no_sampler, false, carve_handover(d_ws, M), false, nullptr);
+  }
+  return launch_score_simt((cudaStream_t)stream, a, nullptr, false);
+}
+
+extern "C" int32_t bx_score_generated(const bx_factor_t* f, const uint32_t key[2], const bx_dim_t* dims, uint64_t m_begin,
+                                      uint64_t m_count, int32_t acq_id, float acq_param, float ystar, float* d_acq,
+                                      uint64_t* d_best, int32_t engine, void* d_ws, size_t ws_bytes, void* stream) {
+  int32_t rc = check_factor(f);
+  if (rc) return rc;
+  BX_CHECK_ARG(acq_id >= 0 && acq_id <= 3, BX_E_ARG, "unknown acquisition id %d", acq_id);
+  BX_CHECK_ARG(m_begin + m_count <= 0x100000000ull, BX_E_RANGE, "candidate indices must stay below 2^32");
+  SamplerPack sp;
+  rc = make_sampler(key, dims, f->d, &sp);
+  if (rc) return rc;
+  if (m_count == 0) return 0;
+  ScoreArgs a{};
+  a.f = *f; a.cand = nullptr; a.m_begin = m_begin; a.m_count = m_count; a.acq_id = acq_id; a.acq_param = acq_param;
+  a.ystar = ystar; a.acq = d_acq; a.best = reinterpret_cast<unsigned long long*>(d_best); a.index_base = m_begin;
+  // AUTO: the two-tier production path (fp16 tcgen05 engine + fp32 SIMT engine on the cancellation-regime candidates)
+  // whenever the factor carries its fp16 copies and d <= 32; otherwise the fp32 SIMT engine alone.
+  if (engine == BX_ENGINE_AUTO) engine = score_tc16_supported(*f) ? BX_ENGINE_TCGEN05_F16 : BX_ENGINE_SIMT;
+  if (engine == BX_ENGINE_TCGEN05_F16 || engine == BX_ENGINE_TCGEN05_F16_RAW) {
+    BX_CHECK_ARG(score_tc16_supported(*f), BX_E_UNSUPPORTED, "the fp16 tcgen05 engine needs the T16hi/T16lo split of the factor and d <= 32");
+    const bool raw = engine == BX_ENGINE_TCGEN05_F16_RAW;
+    BX_CHECK_ARG(raw || (d_ws && ws_bytes >= bx_score_workspace_bytes(m_count)), BX_E_WORKSPACE, "hand-over workspace missing or too small");
+    return launch_two_tier((cudaStream_t)stream, a, sp, true, carve_handover(d_ws, m_count), raw, nullptr);
+  }
+  BX_CHECK_ARG(engine == BX_ENGINE_SIMT, BX_E_ARG, "unknown engine %d", engine);
+  return launch_score_simt((cudaStream_t)stream, a, &sp, true);
+}
+
 extern "C" size_t bx_score_topk_workspace_bytes(uint64_t m_count, int32_t k) {
   if (k <= 0 || k > BX_MAX_K) return 0;
   return carve_sample_ws(nullptr, m_count, k).bytes;
 }
 
+// ---- fused sample() front half: generate -> score -> top-k -> arg-max (optimizer.py:183-197, :205) ---------------------
 extern "C" int32_t bx_score_generated_topk(const bx_factor_t* f, const uint32_t key[2], const bx_dim_t* dims, uint64_t m_begin,
                                            uint64_t m_count, int32_t acq_id, float acq_param, float ystar, int32_t k,
                                            uint64_t* d_list, float* d_vals, uint32_t* d_idx, int32_t* d_count, float* d_acq,
@@ -410,42 +455,24 @@ extern "C" int32_t bx_score_generated_topk(const bx_factor_t* f, const uint32_t 
   if (rc) return rc;
   cudaStream_t s = (cudaStream_t)stream;
   SampleWs w = carve_sample_ws(d_ws, m_count, k);
-  unsigned long long* list = reinterpret_cast<unsigned long long*>(d_list);
   BX_CUDA(cudaMemsetAsync(w.best, 0, 8, s));
   ScoreArgs a{};
   a.f = *f; a.cand = nullptr; a.m_begin = m_begin; a.m_count = m_count; a.acq_id = acq_id; a.acq_param = acq_param;
   a.ystar = ystar; a.acq = d_acq; a.best = w.best; a.index_base = m_begin;
+  a.topk_slab = w.slabs; a.topk_count = w.counts; a.topk_k = k;
   if (engine == BX_ENGINE_AUTO) engine = score_tc16_supported(*f) ? BX_ENGINE_TCGEN05_F16 : BX_ENGINE_SIMT;
-  if (engine == BX_ENGINE_TCGEN05_F16) {
+  int nslabs = 0;
+  if (engine == BX_ENGINE_TCGEN05_F16 || engine == BX_ENGINE_TCGEN05_F16_RAW) {
     BX_CHECK_ARG(score_tc16_supported(*f), BX_E_UNSUPPORTED, "the fp16 tcgen05 engine needs the T16hi/T16lo split of the factor and d <= 32");
-    const unsigned grid = score_tc16p_grid(m_count);
-    BX_CHECK_ARG((int)grid <= sm_count(), BX_E_WORKSPACE, "grid %u exceeds the slab workspace", grid);
-    a.topk_slab = w.slabs; a.topk_count = w.counts; a.topk_k = k;
-    rc = launch_score_tc16p(s, a, sp);
-    if (rc) return rc;
-    return launch_topk_merge(s, w.slabs, w.counts, (int)grid, tk::CAP, k, w.scratch, list, w.best, 1, 1, d_vals, d_idx, d_count);
-  }
-  // un-fused engines: acquisition vector into the workspace (or the caller's d_acq), radix select over it
-  float* acq = d_acq ? d_acq : w.acq;
-  a.acq = acq;
-  if (engine == BX_ENGINE_TCGEN05_TF32) {
-    BX_CHECK_ARG(score_tc_supported(*f), BX_E_UNSUPPORTED, "the 3xTF32 tcgen05 engine needs the Thi/Tlo split of the factor and d <= 32");
-    rc = launch_score_tc2(s, a, sp);
+    rc = launch_two_tier(s, a, sp, true, w.h, engine == BX_ENGINE_TCGEN05_F16_RAW, &nslabs);
   } else {
-    BX_CHECK_ARG(engine == BX_ENGINE_SIMT, BX_E_ARG, "unknown engine %d", engine);
+    BX_CHECK_ARG(engine == BX_ENGINE_SIMT, BX_E_UNSUPPORTED, "the fused top-k runs on the AUTO / SIMT / fp16 tcgen05 engines (engine %d)", engine);
+    nslabs = (int)score_simt_grid(m_count, sm_count());
     rc = launch_score_simt(s, a, &sp, true);
   }
   if (rc) return rc;
-  const int kk = (uint64_t)k <= m_count ? k : (int)m_count;
-  rc = launch_topk_values(s, acq, m_count, kk, m_begin, nullptr, nullptr, list + (k - kk), w.topk);
-  if (rc) return rc;
-  list_pad_kernel<<<(k - kk + 255) / 256 + 1, 256, 0, s>>>(list, k - kk, w.best, list + k);
-  BX_LAUNCH_CHECK();
-  if (d_vals || d_idx || d_count) {
-    list_unpack_kernel<<<1, 256, 0, s>>>(list, k, d_vals, d_idx, d_count);
-    BX_LAUNCH_CHECK();
-  }
-  return 0;
+  return launch_topk_merge(s, w.slabs, w.counts, nslabs, tk::CAP, k, w.scratch, reinterpret_cast<unsigned long long*>(d_list), w.best, 1,
+                           1, d_vals, d_idx, d_count);
 }
 
 extern "C" int32_t bx_propose(const uint32_t key[2], const bx_dim_t* dims, int32_t d, const float* d_opt_x, const float* d_opt_val,

@@ -244,8 +244,21 @@ score_tc16p_kernel(const __grid_constant__ ScoreArgs a, const __grid_constant__ 
       if (lane == 0) mbar_arrive(smem_u32(&S.mean_empty));
       const float mu = msum * mean_unscale + ymean;  // gp.py:67
       const uint64_t row = tile * TM + cl;
-      if (row < a.m_count) {
-        const float var = amp - ss * unscale2;       // gp.py:69 (diagonal only)
+      const bool valid = row < a.m_count;
+      const float var = amp - ss * unscale2;       // gp.py:69 (diagonal only)
+      // tcgen05.mma adds into its fp32 accumulator with truncation (toward zero, once per instruction, and every aligned
+      // addend at a quarter ulp: scripts/dev/umma_probe.py), which biases sum v^2 by 1e-6 .. 6e-5 relative.  That is
+      // harmless while var is a sizeable part of amp and ruinous where amp - sum v^2 cancels, so candidates with
+      // var < tau * amp are handed to the fp32 SIMT engine (launch_score_tc16p runs it on the list) and get no output here.
+      const bool hand_over = valid && a.flag_list != nullptr && var < a.flag_tau * amp;
+      const unsigned hm = __ballot_sync(0xffffffffu, hand_over);
+      if (hm) {
+        unsigned int base = 0;
+        if (lane == 0) base = atomicAdd(a.flag_count, (unsigned)__popc(hm));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (hand_over) a.flag_list[base + __popc(hm & ((1u << lane) - 1u))] = (uint32_t)row;
+      }
+      if (valid && !hand_over) {
         const float sd = sqrtf(fmaxf(var, 1e-10f));  // gp.py:70
         const float av = acquisition(a.acq_id, mu, sd, a.ystar, a.acq_param);
         if (a.mu) a.mu[row] = mu;

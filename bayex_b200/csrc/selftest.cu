@@ -114,3 +114,25 @@ extern "C" int32_t bx_selftest_umma(const float* d_A, const float* d_B, float* d
   cudaFreeAsync(lo, s);
   return rc;
 }
+
+// ---- fp32 SIMT peak: the denominator of the fit path's roofline (MEASURED_PEAKS.json has the HBM and 16-bit tensor
+// figures only).  Every thread runs 8 independent FFMA chains; flops = grid * 256 threads * iters * 8 * 2. -------------
+namespace bx {
+__global__ void __launch_bounds__(256) ffma_peak_kernel(float* out, int iters, float a, float b) {
+  float x0 = threadIdx.x, x1 = x0 + 1.f, x2 = x0 + 2.f, x3 = x0 + 3.f, x4 = x0 + 4.f, x5 = x0 + 5.f, x6 = x0 + 6.f, x7 = x0 + 7.f;
+#pragma unroll 4
+  for (int i = 0; i < iters; ++i) {
+    x0 = fmaf(x0, a, b); x1 = fmaf(x1, a, b); x2 = fmaf(x2, a, b); x3 = fmaf(x3, a, b);
+    x4 = fmaf(x4, a, b); x5 = fmaf(x5, a, b); x6 = fmaf(x6, a, b); x7 = fmaf(x7, a, b);
+  }
+  const float s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+  if (s == 123.456f) out[0] = s;  // keeps the chains alive without a store in the common case
+}
+}  // namespace bx
+
+extern "C" int32_t bx_selftest_ffma(float* d_out, int32_t blocks, int32_t iters, void* stream) {
+  BX_CHECK_ARG(d_out && blocks > 0 && iters > 0, BX_E_ARG, "bad argument");
+  bx::ffma_peak_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(d_out, iters, 0.999f, 0.001f);
+  BX_LAUNCH_CHECK();
+  return 0;
+}

@@ -45,7 +45,7 @@ __device__ __forceinline__ void push(Shared& S, unsigned long long* slab, unsign
 
 // All TPB threads.  Keeps the k largest keys of the slab (no-op when it holds at most k) and raises the threshold.
 template <int BAR_ID>
-__device__ void prune(Shared& S, unsigned long long* slab, int k, int t) {
+__device__ __noinline__ void prune(Shared& S, unsigned long long* slab, int k, int t) {
   bar<BAR_ID>();
   const unsigned int cnt = min(S.cnt, (unsigned)CAP);
   if (cnt <= (unsigned)k) return;  // uniform

@@ -104,7 +104,7 @@ class Posterior:
             raise ValueError(f"at most {_lib.MAX_D} dimensions are supported, got {self.d}")
         self.np_ = (self.n + _lib.TILE - 1) // _lib.TILE * _lib.TILE
         self.d4 = (self.d + 3) // 4 * 4
-        self.want_tc = want_tc
+        self.want_tc = want_tc        # fp16 head/tail copies of T: the production tcgen05 engine
         with on_stream(self.stream, self.dev):
             self.X = torch.from_numpy(x).to(self.dev, non_blocking=False)
             self.y = torch.from_numpy(np.ascontiguousarray(y, dtype=np.float32)).to(self.dev)
@@ -161,30 +161,49 @@ class Posterior:
         np_, d4 = self.np_, self.d4
         with on_stream(self.stream, self.dev):
             if self._bufs is None:
-                e = lambda *s: torch.empty(s, dtype=torch.float32, device=self.dev)
                 self._bufs = self._alloc_bufs()
             b = self._bufs
             check(lib.bx_factor_build(_ptr(self.X), _ptr(self.y), self.n, self.d, _ptr(self.raw), _ptr(b["U"]),
-                                      _ptr(b["T"]), _ptr(b["Thi"]), _ptr(b["Tlo"]), _ptr(b["T16hi"]), _ptr(b["T16lo"]),
+                                      _ptr(b["T"]), _ptr(b["T16hi"]), _ptr(b["T16lo"]),
                                       _ptr(b["alpha"]), _ptr(b["scale"]), _ptr(b["hyp"]), _ptr(ws), nbytes,
                                       C.c_void_p(self.stream.cuda_stream)),
                   "bx_factor_build")
         self._set_factor()
+        # gp.py:48: the reference's cholesky returns NaN silently on a non-PD Gram matrix; so do the kernels (hyp[7] records
+        # it).  Surface it as a warning - never an exception, the NaNs propagate exactly as they do upstream.
+        rc = lib.bx_check_status(_ptr(self._bufs["hyp"]), C.c_void_p(self.stream.cuda_stream))
+        if rc == _lib.E_NOTPD:
+            import warnings
+            warnings.warn("bayex_b200: " + lib.bx_last_error().decode("utf-8", "replace") + "; posterior values are NaN",
+                          RuntimeWarning, stacklevel=2)
+        elif rc != 0:
+            check(rc, "bx_check_status")
         return self
 
     def _alloc_bufs(self):
+        """Everything a scoring rank needs lives in ONE flat allocation (segments 256-byte aligned), so the multi-GPU
+        hand-out of a freshly built factor is a single NCCL broadcast: hyp | scale | alpha | raw | U | T | T16hi | T16lo."""
         np_, d4 = self.np_, self.d4
-        e = lambda *s: torch.empty(s, dtype=torch.float32, device=self.dev)
-        h = lambda *s: torch.empty(s, dtype=torch.float16, device=self.dev)
-        tc = self.want_tc
-        return dict(U=e(np_, d4), T=e(np_, np_), alpha=e(np_), scale=e(d4), hyp=torch.zeros(16, dtype=torch.float32, device=self.dev),
-                    Thi=e(np_, np_) if tc else None, Tlo=e(np_, np_) if tc else None,
-                    T16hi=h(np_, np_) if tc else None, T16lo=h(np_, np_) if tc else None)
+        seg = [("hyp", 16), ("scale", d4), ("alpha", np_), ("rawcopy", self.d + 2), ("U", np_ * d4), ("T", np_ * np_)]
+        if self.want_tc:
+            seg += [("T16hi", np_ * np_ // 2), ("T16lo", np_ * np_ // 2)]  # fp16 matrices, counted in float32 words
+        off, offs = 0, {}
+        for name, nfloat in seg:
+            offs[name] = (off, nfloat)
+            off += (nfloat + 63) // 64 * 64
+        flat = torch.zeros(off, dtype=torch.float32, device=self.dev)
+        view = lambda name: flat[offs[name][0]:offs[name][0] + offs[name][1]]
+        b = dict(flat=flat, hyp=view("hyp"), scale=view("scale"), alpha=view("alpha"), rawcopy=view("rawcopy"),
+                 U=view("U").view(np_, d4), T=view("T").view(np_, np_), T16hi=None, T16lo=None)
+        if self.want_tc:
+            b["T16hi"] = view("T16hi").view(torch.float16).view(np_, np_)
+            b["T16lo"] = view("T16lo").view(torch.float16).view(np_, np_)
+        return b
 
     def _set_factor(self):
         b = self._bufs
         p = lambda t: 0 if t is None else t.data_ptr()
-        self.factor = _lib.FactorT(self.n, self.np_, self.d, self.d4, p(b["U"]), p(b["T"]), p(b["Thi"]), p(b["Tlo"]),
+        self.factor = _lib.FactorT(self.n, self.np_, self.d, self.d4, p(b["U"]), p(b["T"]),
                                    p(b["T16hi"]), p(b["T16lo"]), p(b["alpha"]), p(b["scale"]), p(b["hyp"]))
 
     def hyp(self) -> np.ndarray:
@@ -208,15 +227,15 @@ class Posterior:
 
     # -- multi-GPU: the factor is built on one rank and broadcast (NCCL over NVLink) --------------------------
     def broadcast(self, src=0, group=None):
+        """One collective for the whole factor (flat buffer), stream-ordered on the library stream: no host sync."""
         import torch.distributed as dist
-        if self._bufs is None:
-            self._bufs = self._alloc_bufs()
-        self.stream.synchronize()
-        names = ["U", "alpha", "scale", "hyp", "T"] + (["Thi", "Tlo", "T16hi", "T16lo"] if self.want_tc else [])
-        for name in names:
-            dist.broadcast(self._bufs[name], src=src, group=group)
-        dist.broadcast(self.raw, src=src, group=group)
-        torch.cuda.current_stream(self.dev).synchronize()
+        with on_stream(self.stream, self.dev):
+            if self._bufs is None:
+                self._bufs = self._alloc_bufs()
+            b = self._bufs
+            b["rawcopy"].copy_(self.raw)
+            dist.broadcast(b["flat"], src=src, group=group)
+            self.raw.copy_(b["rawcopy"])
         self._set_factor()
         return self
 
@@ -232,8 +251,13 @@ class Posterior:
             out = {k: (torch.empty(M, dtype=torch.float32, device=self.dev) if k in want else None)
                    for k in ("mu", "sigma", "acq")}
             bst = torch.zeros(1, dtype=torch.int64, device=self.dev) if best else None
+            # point sets of at least BX_POINTS_TC_MIN take the two-tier tcgen05 path: it needs the hand-over workspace
+            ws, nbytes = None, 0
+            if M >= _lib.POINTS_TC_MIN and self.want_tc:
+                nbytes = lib.bx_score_workspace_bytes(M)
+                ws = _workspace(self.dev, nbytes)
             check(lib.bx_score_points(C.byref(self.factor), _ptr(cand), M, _lib.ACQ_IDS[acq], float(param), float(ystar),
-                                      _ptr(out["mu"]), _ptr(out["sigma"]), _ptr(out["acq"]), _ptr(bst), 0,
+                                      _ptr(out["mu"]), _ptr(out["sigma"]), _ptr(out["acq"]), _ptr(bst), 0, _ptr(ws), nbytes,
                                       C.c_void_p(self.stream.cuda_stream)), "bx_score_points")
         out["best"] = bst
         return out
@@ -246,10 +270,53 @@ class Posterior:
             vals = torch.empty(m_count, dtype=torch.float32, device=self.dev) if keep_acq else None
             if best is None:
                 best = torch.zeros(1, dtype=torch.int64, device=self.dev)
+            nbytes = lib.bx_score_workspace_bytes(int(m_count))
+            ws = _workspace(self.dev, nbytes)
             check(lib.bx_score_generated(C.byref(self.factor), _lib.key_words(key), dims, int(m_begin), int(m_count),
                                          _lib.ACQ_IDS[acq], float(param), float(ystar), _ptr(vals), _ptr(best),
-                                         int(engine), C.c_void_p(self.stream.cuda_stream)), "bx_score_generated")
+                                         int(engine), _ptr(ws), nbytes, C.c_void_p(self.stream.cuda_stream)), "bx_score_generated")
         return vals, best
+
+    # -- fused sample() pieces: everything below enqueues on the library stream and returns device tensors -------------
+    def sample_front(self, key, dims, m_begin, m_count, acq, param, ystar, k, engine=_lib.ENGINE_AUTO, keep_acq=False):
+        """optimizer.py:183-197 + :205 for one candidate shard: Threefry -> posterior -> acquisition -> per-CTA top-k ->
+        merge.  Returns ``(list, vals, idx, acq)``: the (k + 1)-entry key list (see include/bayex_b200.h), its valid
+        entries unpacked ascending at the front of ``vals`` / ``idx``, and the acquisition vector if ``keep_acq``."""
+        self._need_factor()
+        with on_stream(self.stream, self.dev):
+            lst = torch.zeros(k + 1, dtype=torch.int64, device=self.dev)
+            vals = torch.empty(k, dtype=torch.float32, device=self.dev)
+            idx = torch.empty(k, dtype=torch.int32, device=self.dev)
+            acq_out = torch.empty(m_count, dtype=torch.float32, device=self.dev) if keep_acq else None
+            if m_count > 0:
+                nbytes = lib.bx_score_topk_workspace_bytes(int(m_count), int(k))
+                ws = _workspace(self.dev, nbytes)
+                check(lib.bx_score_generated_topk(C.byref(self.factor), _lib.key_words(key), dims, int(m_begin), int(m_count),
+                                                  _lib.ACQ_IDS[acq], float(param), float(ystar), int(k), _ptr(lst), _ptr(vals),
+                                                  _ptr(idx), None, _ptr(acq_out), int(engine), _ptr(ws), nbytes,
+                                                  C.c_void_p(self.stream.cuda_stream)), "bx_score_generated_topk")
+        return lst, vals, idx, acq_out
+
+    def merge_lists(self, lists: torch.Tensor, n_lists: int, k: int):
+        """Merge the all-gathered key lists of the candidate shards into one; same outputs as above."""
+        with on_stream(self.stream, self.dev):
+            out = torch.empty(k + 1, dtype=torch.int64, device=self.dev)
+            vals = torch.empty(k, dtype=torch.float32, device=self.dev)
+            idx = torch.empty(k, dtype=torch.int32, device=self.dev)
+            nbytes = 8 * n_lists * k
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=self.dev)
+            check(lib.bx_topk_merge(_ptr(lists), int(n_lists), int(k), _ptr(out), _ptr(vals), _ptr(idx), None, _ptr(ws), nbytes,
+                                    C.c_void_p(self.stream.cuda_stream)), "bx_topk_merge")
+        return out, vals, idx
+
+    def propose(self, key, dims, opt_x, opt_val, S, best: torch.Tensor):
+        """optimizer.py:203-207 on the device: arg-max over concat(refined, random), the winner's raw coordinates.
+        Returns a device tensor [d + 2]: point, value, position in the concatenation (uint32 bits)."""
+        with on_stream(self.stream, self.dev):
+            out = torch.empty(self.d + 2, dtype=torch.float32, device=self.dev)
+            check(lib.bx_propose(_lib.key_words(key), dims, self.d, _ptr(opt_x), _ptr(opt_val), int(S), _ptr(best), _ptr(out),
+                                 C.c_void_p(self.stream.cuda_stream)), "bx_propose")
+        return out
 
     def topk(self, vals: torch.Tensor, k: int, index_base=0):
         with on_stream(self.stream, self.dev):

@@ -190,52 +190,59 @@ class Optimizer:
         dist, rank, world = self._dist()
         m_begin, m_count = shard_range(size, rank, world)
         name, param = self.acq_name, self.acq_param
+        d = len(self.domain)
+        k = max(1, min(n_starts, size))  # optimizer.py:196 takes what exists when size < 50
+        S = min(n_starts, size)
 
-        vals, best = post.score_generated(key, self._dims, m_begin, m_count, name, param, ystar, keep_acq=True,
-                                          engine=self.engine)  # optimizer.py:183-193
-        k_loc = min(n_starts, m_count)
-        if k_loc > 0:
-            tv, ti = post.topk(vals, k_loc, index_base=m_begin)  # optimizer.py:196
-        else:
-            tv = torch.empty(0, dtype=torch.float32, device=post.dev)
-            ti = torch.empty(0, dtype=torch.int32, device=post.dev)
-        if world > 1:
-            post.stream.synchronize()
-            best = allreduce_packed_max(best, dist)
-            gv, gi = allgather_topk(tv, ti, n_starts, dist, world)
-            torch.cuda.current_stream(post.dev).synchronize()
-            tv, ti = merge_topk(gv, gi, min(n_starts, size))
-            tv, ti = torch.from_numpy(tv).to(post.dev), torch.from_numpy(ti).to(post.dev)
-        starts = post.gather(key, self._dims, ti)  # optimizer.py:197
-        # optimizer.py:198-200: refined points and their acquisition values (bx_refine evaluates the same closed forms
-        # with the same ex2 path as the scoring kernels; the values at the returned points come back with them)
-        optimized, opt_vals = post.refine(starts, refine_rounds, name, param, ystar)
+        # Everything up to the proposal is enqueued on the library stream; the only host synchronisation of a sample()
+        # is the read-back of the proposal (d + 2 floats).
         with engine.on_stream(post.stream, post.dev):
-            b_rnd = engine.to_unsigned(int(best.item()))
-            opt_host = optimized.cpu().numpy()
-            ov_host = opt_vals.cpu().numpy()
-        j_opt = argmax_first(ov_host)
-        b_opt = int(_lib.lib.bx_pack(_lib.C.c_float(float(ov_host[j_opt])), j_opt))
-        # argmax over concat(optimised, random): first occurrence => optimised points win ties (optimizer.py:203-205)
-        if (b_opt >> 32) >= (b_rnd >> 32):
-            _, j = _lib.unpack(b_opt)
-            point, chosen = opt_host[j], j
-        else:
-            _, j = _lib.unpack(b_rnd)
-            idx = torch.tensor([j], dtype=torch.int64).to(torch.int32).to(post.dev)
+            # optimizer.py:183-197, :205 on this rank's candidate shard: fused generate -> score -> top-k -> arg-max
+            lst, tv, ti, vals = post.sample_front(key, self._dims, m_begin, m_count, name, param, ystar, k,
+                                                  engine=self.engine, keep_acq=details)
+            if world > 1:
+                # one packed all-gather (k top keys + the arg-max key per rank), merged identically on every rank
+                lists = torch.empty(world * (k + 1), dtype=torch.int64, device=post.dev)
+                dist.all_gather_into_tensor(lists, lst)
+                lst, tv, ti = post.merge_lists(lists, world, k)
+            # optimizer.py:197-200: the multi-start axis is sharded too: rank r refines starts
+            # [r c, (r + 1) c) of the merged list; a start's refinement does not depend on its neighbours in the batch
+            c = (S + world - 1) // world if S else 0
+            a, b = min(rank * c, S), min((rank + 1) * c, S)
+            rows = torch.zeros((max(c, 1), d + 1), dtype=torch.float32, device=post.dev)
+            if b > a:
+                starts = post.gather(key, self._dims, ti[a:b].contiguous())  # optimizer.py:197
+                x_mine, v_mine = post.refine(starts, refine_rounds, name, param, ystar)
+                rows[:b - a, :d] = x_mine
+                rows[:b - a, d] = v_mine
+            if world > 1 and S:
+                allrows = torch.empty((world * c, d + 1), dtype=torch.float32, device=post.dev)
+                dist.all_gather_into_tensor(allrows, rows)
+                rows = allrows[:S]  # slices are contiguous in rank order: the first S rows are the starts in list order
+            optimized = rows[:S, :d].contiguous()
+            opt_vals = rows[:S, d].contiguous()
+            # optimizer.py:203-207: arg-max over concat(optimised, random), first occurrence => optimised points win ties
+            out = post.propose(key, self._dims, optimized, opt_vals, S, lst[k:])
+            out_host = out.cpu().numpy()
+        point = out_host[:d].astype(np.float32)
+        chosen = int(out_host[d + 1:d + 2].view(np.uint32)[0])
+        if q > 1 or details:
             with engine.on_stream(post.stream, post.dev):
-                point = post.gather(key, self._dims, idx).cpu().numpy()[0]
-            chosen = len(opt_host) + j
+                opt_host, ov_host = optimized.cpu().numpy(), opt_vals.cpu().numpy()
+                tv_s, ti_s = tv[:S], ti[:S]
         if q > 1:
-            point = self._batch_points(post, key, point, opt_host, ov_host, tv, ti, q)
+            point = self._batch_points(post, key, point, opt_host, ov_host, tv_s, ti_s, q)
         else:
             point = point[None]
         best_params = self.param_space.to_dict(point)  # optimizer.py:207
-        best_params = {k: np.asarray(v, dtype=np.float32) for k, v in best_params.items()}
+        best_params = {k_: np.asarray(v, dtype=np.float32) for k_, v in best_params.items()}
         if details:
             with engine.on_stream(post.stream, post.dev):
-                info = dict(acq_vals=vals.cpu().numpy(), top_idxs=ti.cpu().numpy(), top_vals=tv.cpu().numpy(),
-                            optimized=opt_host, opt_vals=ov_host, chosen=chosen,
+                b_rnd = engine.to_unsigned(int(lst[k].item()))
+                j_opt = argmax_first(ov_host) if S else 0
+                b_opt = int(_lib.lib.bx_pack(_lib.C.c_float(float(ov_host[j_opt])), j_opt)) if S else 0
+                info = dict(acq_vals=vals.cpu().numpy(), top_idxs=ti_s.cpu().numpy(), top_vals=tv_s.cpu().numpy(),
+                            optimized=opt_host, opt_vals=ov_host, chosen=chosen, value=float(out_host[d]),
                             best_opt=_lib.unpack(b_opt), best_rnd=_lib.unpack(b_rnd), m_begin=m_begin, m_count=m_count)
             return best_params, info
         return best_params

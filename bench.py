@@ -102,31 +102,55 @@ class ClockSampler(threading.Thread):
                 "power_w_max": max(float(r[2]) for r in self.rows)}
 
 
-def cpu_baseline(d, n, acq, X, Y, sample=None, budget_s=20.0):
-    """Time the oracle (CPU restatement of gp.py:59-71 + acq.py) on a bounded sample; candidates/s on the host cores."""
-    from oracle import acq as oacq, domain as odom, gp as ogp, prng
+def host_threads():
+    """Host cores this process may use (torchrun pins OMP_NUM_THREADS=1 in the environment; that must not apply here)."""
     try:
-        from threadpoolctl import threadpool_info
-        threads = max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
-    except Exception:
-        threads = os.cpu_count()
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
+def cpu_baseline(d, n, acq, X, Y, sample=None, budget_s=20.0):
+    """Time the oracle (CPU restatement of gp.py:59-71 + acq.py) on a bounded sample; candidates/s on ALL host cores.
+
+    The candidate chunks are independent: they are spread over a thread pool of `cores` workers (NumPy releases the GIL in
+    the element-wise Gram build and inside BLAS) with BLAS itself limited to one thread per call, so Gram build, TRSM and
+    the reductions all run `cores` wide - whatever OMP_NUM_THREADS says.  The one-off factorisation uses BLAS threads."""
+    from threadpoolctl import threadpool_limits
+    from oracle import acq as oacq, domain as odom, gp as ogp, prng
+    from scipy.linalg import solve_triangular
+    cores = host_threads()
     P = ogp.GPParams(np.float32(-8.0), np.float32(0.0), np.zeros(d, np.float32))
-    f = ogp.Factor(P, X, Y, np.ones(n), np.float32)
+    with threadpool_limits(limits=cores):
+        f = ogp.Factor(P, X, Y, np.ones(n), np.float32)
     space = odom.ParamSpace({f"x{i}": odom.Real(0.0, 1.0) for i in range(d)})
-    chunk = 8192
+    chunk = 1024  # per worker: n x 1024 floats of K* and V
+
+    def score(m, key):
+        c = space.to_array(space.sample_params(prng.key(key), (m,)))
+        with threadpool_limits(limits=1):
+            mu, sd = f.predict(c, chunk=chunk, threads=cores)
+        vals = oacq.acq_from_moments(acq, mu, sd, Y, np.ones(n))
+        return int(np.argmax(vals))
+
     if sample is None:
         t0 = time.perf_counter()
-        c = space.to_array(space.sample_params(prng.key(1), (chunk,)))
-        mu, sd = f.predict(c, chunk=chunk)
-        oacq.acq_from_moments(acq, mu, sd, Y, np.ones(n))
+        score(cores * chunk, 1)
         one = time.perf_counter() - t0
-        sample = int(min(16, max(2, budget_s / max(one, 1e-3)))) * chunk
+        sample = int(min(16, max(1, budget_s / max(one, 1e-3)))) * cores * chunk
     t0 = time.perf_counter()
-    c = space.to_array(space.sample_params(prng.key(1), (sample,)))
-    mu, sd = f.predict(c, chunk=chunk)
-    vals = oacq.acq_from_moments(acq, mu, sd, Y, np.ones(n))
-    int(np.argmax(vals))
+    score(sample, 1)
     dt = time.perf_counter() - t0
+    # what the triangular solve alone costs on the same cores (the floor of this arm: gp.py:68)
+    kc = np.ones((n, chunk), np.float32)
+    def trsm(_):
+        solve_triangular(f.L, kc, lower=True, check_finite=False)
+    from concurrent.futures import ThreadPoolExecutor
+    with threadpool_limits(limits=1), ThreadPoolExecutor(max_workers=cores) as pool:
+        list(pool.map(trsm, range(cores)))
+        t1 = time.perf_counter()
+        list(pool.map(trsm, range(2 * cores)))
+        trsm_rate = 2 * cores * chunk / (time.perf_counter() - t1)
     # SURVEY 8(d): what bayex as written costs - predict forms the full M x M covariance (gp.py:69, quirk Q8; default
     # M = 10 000).  Timed at M = 4096 to stay inside the CPU budget (the M x M part grows with M^2); reported beside the
     # diagonal-only figure, which is the one compared against
@@ -134,16 +158,19 @@ def cpu_baseline(d, n, acq, X, Y, sample=None, budget_s=20.0):
     try:
         m_ref = 4096
         cf = space.to_array(space.sample_params(prng.key(2), (m_ref,)))
-        t1 = time.perf_counter()
-        ogp.predict_full_cov(P, X, Y, np.ones(n), cf)
-        full = {"candidates": m_ref, "seconds": time.perf_counter() - t1,
-                "note": "reference-style predict with the M x M product (gp.py:69), factorisation included"}
+        with threadpool_limits(limits=cores):
+            t1 = time.perf_counter()
+            ogp.predict_full_cov(P, X, Y, np.ones(n), cf)
+            full = {"candidates": m_ref, "seconds": time.perf_counter() - t1,
+                    "note": "reference-style predict with the M x M product (gp.py:69), factorisation included"}
         full["candidates_per_s"] = m_ref / full["seconds"]
     except Exception as exc:  # the extra figure must never break the bench line
         full = {"error": repr(exc)}
-    return {"value": sample / dt, "unit": "candidates/s", "cores": int(threads), "kind": "port", "reference_style_full_cov": full,
-            "sample": f"{sample} of the workload's candidates (chunks of {chunk}, diagonal-only variance, NumPy/SciPy fp32 "
-                      f"restatement of the reference; JAX unavailable), {dt:.1f} s", "host_cpus": os.cpu_count()}
+    return {"value": sample / dt, "unit": "candidates/s", "cores": int(cores), "kind": "port", "reference_style_full_cov": full,
+            "trsm_only_candidates_per_s": trsm_rate,
+            "sample": f"{sample} of the workload's candidates ({cores} worker threads x chunks of {chunk}, diagonal-only "
+                      f"variance, NumPy/SciPy fp32 restatement of the reference; JAX unavailable), {dt:.1f} s",
+            "host_cpus": os.cpu_count()}
 
 
 def run_reference(args, d, n, M, acq, desc):
@@ -154,6 +181,8 @@ def run_reference(args, d, n, M, acq, desc):
     _, X, Y = make_observations(d, n, odom)
     per_step = []
     base = None
+    if args.ref_sample is None:
+        args.ref_sample = 4 * host_threads() * 1024  # ~10-20 s per step at n = 4096 on the box's cores
     for i in range(args.warmup + args.steps):
         base = cpu_baseline(d, n, acq, X, Y, sample=args.ref_sample)
         if i >= args.warmup:
@@ -163,31 +192,104 @@ def run_reference(args, d, n, M, acq, desc):
     line = {"impl": "reference", "metric": "acq candidate-evals/sec", "value": v, "unit": "candidates/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * args.ref_sample / v, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": desc, "n_obs": n, "d": d, "candidates": M, "acq": acq,
-                       "note": f"each step scores a bounded sample of {args.ref_sample} candidates on the host CPU"},
+            "config": {"workload": desc, "n_obs": n, "d": d, "candidates": M, "acq": acq},
+            "details": {"note": f"each step scores a bounded sample of {args.ref_sample} candidates on the host CPU (all cores)"},
             "cpu_baseline": base, "e2e": {"value": v, "unit": "candidates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
 
-def measure_tf32_peak(torch, dev):
-    """Dense TF32 cuBLAS GEMM throughput, measured like MEASURED_PEAKS.json's bf16 entry (8192^3, best of 10)."""
-    old = torch.backends.cuda.matmul.allow_tf32
-    torch.backends.cuda.matmul.allow_tf32 = True
-    a = torch.randn(8192, 8192, device=dev)
-    b = torch.randn(8192, 8192, device=dev)
+def measure_ffma_peak(torch, dev, lib):
+    """fp32 SIMT peak of this GPU, measured like MEASURED_PEAKS.json's bf16 entry (best of 10 after warm-up, CUDA events):
+    an FFMA-only kernel, 8 independent chains per thread (bx_selftest_ffma).  Denominator of the fit path's roofline."""
+    import ctypes as C
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count
+    blocks, iters = sms * 32, 8192
+    out = torch.zeros(4, device=dev)
     best = 0.0
     for i in range(13):
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
-        a @ b
+        lib.bx_selftest_ffma(C.c_void_p(out.data_ptr()), blocks, iters, C.c_void_p(torch.cuda.current_stream().cuda_stream))
         e.record()
         e.synchronize()
         if i >= 3:
-            best = max(best, 2 * 8192.0 ** 3 / (s.elapsed_time(e) * 1e-3) / 1e12)
-    torch.backends.cuda.matmul.allow_tf32 = old
-    del a, b
+            best = max(best, blocks * 256.0 * iters * 16 / (s.elapsed_time(e) * 1e-3) / 1e12)
     return best
+
+
+def c5_problem(n, d=8, R=32):
+    """BASELINE config 5 inputs: d = 8 Real(0,1)^8, y = three RBF bumps + 0.01 N(0,1), R random restarts."""
+    rng = np.random.default_rng(5)
+    X = rng.uniform(0, 1, (n, d)).astype(np.float32)
+    centres = rng.uniform(0.2, 0.8, (3, d))
+    Y = (sum(np.exp(-np.sum((X - c) ** 2, axis=1) / 0.1) for c in centres) + 0.01 * rng.standard_normal(n)).astype(np.float32)
+    raws = np.concatenate([rng.uniform(-8, -2, (R, 1)), rng.uniform(-1, 1, (R, 1 + d))], axis=1).astype(np.float32)
+    return X, Y, raws
+
+
+def fit_step_flops(n, d):
+    """Cholesky n^3/3 + K^-1 through T 2n^3/3 + Gram and gradient contraction n^2 (3d + 4)."""
+    return float(n) ** 3 + float(n) * n * (3 * d + 4)
+
+
+def fit_records(args, torch, dist, bengine, fit_sweep, world, rank, dev, ffma_peak):
+    """The fit path in the driver's line: (1) `fit`: one 100-step posterior_fit at n = 4096, d = 8 on
+    one GPU (gp.py:90-110: Gram -> Cholesky -> T -> alpha, NLML -> gradient -> clip + AdamW per step); (2) `c5`: the 32-restart
+    sweep at n = 1024 / 4096 / 8192, restarts sharded over the ranks.  Roofline: algorithmic flops (n^3 per step) against the
+    FFMA peak measured in this run (north star: the fit path stays on the fp32 SIMT pipes)."""
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def tmax(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    out = {}
+    n, d, steps = 4096, 8, 100
+    X, Y, raws = c5_problem(n, d)
+    raw0 = np.concatenate([[-8.0], [0.0], np.zeros(d)]).astype(np.float32)
+    post = bengine.Posterior(X, Y, raw0, want_tc=False)
+    post.fit_hypers(steps=3)
+    sync_all()
+    t0 = time.perf_counter()
+    post.fit_hypers(steps=steps)  # synchronises its stream before it returns (include/bayex_b200.h)
+    torch.cuda.synchronize()
+    dt = tmax(time.perf_counter() - t0)
+    ach = fit_step_flops(n, d) * steps / dt / 1e12
+    out["fit"] = {"n_obs": n, "d": d, "steps": steps, "ms_per_step": 1e3 * dt / steps, "posterior_fit_ms": 1e3 * dt,
+                  "roofline": {"bound": "fp32 simt", "achieved": ach, "peak": ffma_peak, "unit": "TFLOP/s",
+                               "frac": ach / ffma_peak if ffma_peak else None,
+                               "peak_source": "FFMA-only kernel timed in this run (bx_selftest_ffma, best of 10)",
+                               "algorithmic_flops_per_step": fit_step_flops(n, d)},
+                  "note": "every rank runs the same fit (Gram + Cholesky stay on one GPU); max over ranks"}
+    del post
+    if not args.skip_c5:
+        c5 = {}
+        R = 32
+        for n in (1024, 4096, 8192):
+            X, Y, raws = c5_problem(n, d, R)
+            fit_sweep.fit_restarts(X, Y, raws[:max(world, 2)], trainsteps=2)  # warm-up: allocations, graph capture
+            sync_all()
+            t0 = time.perf_counter()
+            best, idx, table = fit_sweep.fit_restarts(X, Y, raws, trainsteps=steps)
+            sync_all()
+            dt = tmax(time.perf_counter() - t0)
+            ach = fit_step_flops(n, d) * steps * R / dt / 1e12
+            c5[f"n{n}"] = {"restarts": R, "steps": steps, "sweep_s": dt, "fit_steps_per_s": R * steps / dt,
+                           "achieved_tflops": ach, "frac_of_ffma_peak_all_gpus": ach / (ffma_peak * world) if ffma_peak else None,
+                           "best_restart": int(idx), "best_loss": float(table[idx, 0]),
+                           "finite_losses": int(np.isfinite(table[:, 0]).sum())}
+        out["c5"] = {"workload": "GP hyper-parameter fit sweep: RBF NLML + Cholesky, d = 8, 32 random restarts x 100 AdamW steps, "
+                                 "restarts sharded over the ranks (no data-path collective; one all-gather of (loss, hypers) rows)",
+                     "n_gpus": world, **c5}
+    return out
 
 
 def main():
@@ -198,9 +300,11 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--candidates", type=int, default=None)
-    ap.add_argument("--engine", default="auto", choices=["auto", "simt", "tcgen05", "tcgen05_pair", "tcgen05_f16", "tcgen05_f16_pair", "tcgen05_f16_shared"])
-    ap.add_argument("--ref-sample", type=int, default=32768)
+    ap.add_argument("--engine", default="auto", choices=["auto", "simt", "tcgen05_f16", "tcgen05_f16_raw"])
+    ap.add_argument("--ref-sample", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-fit", action="store_true", help="leave out the fit / c5 sub-records")
+    ap.add_argument("--skip-c5", action="store_true", help="leave out the 32-restart sweep (about 50 s on one GPU)")
     args = ap.parse_args()
     d, n, M, acq, desc = WORKLOADS[args.workload]
     if args.candidates:
@@ -218,20 +322,19 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     import bayex_b200 as bayex
-    from bayex_b200 import _lib, engine as bengine
+    from bayex_b200 import _lib, engine as bengine, fit_sweep
 
     P, X, Y = make_observations_device(d, n, bayex, bengine)
     dom = {f"x{i}": bayex.domain.Real(0.0, 1.0) for i in range(d)}
     opt = bayex.Optimizer(dom, acq=acq, maximize=False)
-    opt.engine = {"auto": _lib.ENGINE_AUTO, "simt": _lib.ENGINE_SIMT, "tcgen05": _lib.ENGINE_TCGEN05,
-                  "tcgen05_pair": _lib.ENGINE_TCGEN05_PAIR, "tcgen05_f16": _lib.ENGINE_TCGEN05_F16,
-                  "tcgen05_f16_pair": _lib.ENGINE_TCGEN05_F16_PAIR, "tcgen05_f16_shared": _lib.ENGINE_TCGEN05_F16_SHARED}[args.engine]
+    opt.engine = {"auto": _lib.ENGINE_AUTO, "simt": _lib.ENGINE_SIMT, "tcgen05_f16": _lib.ENGINE_TCGEN05_F16,
+                  "tcgen05_f16_raw": _lib.ENGINE_TCGEN05_F16_RAW}[args.engine]
     t0 = time.perf_counter()
     state = opt.init(Y, P)  # 100-step hyper-parameter fit + factor (untimed set-up)
     torch.cuda.synchronize()
     fit_s = time.perf_counter() - t0
     post = opt.posterior(state)
-    tf32_peak = measure_tf32_peak(torch, dev) if rank == 0 else 0.0
+    ffma_peak = measure_ffma_peak(torch, dev, _lib.lib)
     l2_flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
     def barrier():
@@ -258,8 +361,9 @@ def main():
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         with torch.cuda.stream(post.stream):
             s.record(post.stream)
-            post.score_generated(bayex.random.fold_in(key0, i), opt._dims, m_begin, m_count, acq, opt.acq_param, 0.0,
-                                 keep_acq=True, engine=opt.engine)
+            # the front half of sample(): fused generate -> score -> per-CTA top-k -> arg-max (+ hand-over pass, + merge)
+            post.sample_front(bayex.random.fold_in(key0, i), opt._dims, m_begin, m_count, acq, opt.acq_param, 0.0,
+                              opt.N_STARTS, engine=opt.engine)
             e.record(post.stream)
         e.synchronize()
         if i >= max(args.warmup, 3):
@@ -295,10 +399,10 @@ def main():
     barrier()
     t_e2e = max_over_ranks(time.perf_counter() - t0)
 
+    fit_rec = {} if args.skip_fit else fit_records(args, torch, dist, bengine, fit_sweep, world, rank, dev, ffma_peak)
+
     if rank == 0:
         hyp = opt.posterior(state).hyp()
-        used_tc = bool(opt.engine == _lib.ENGINE_TCGEN05 or (opt.engine == _lib.ENGINE_AUTO and post._bufs["Thi"] is not None
-                                                              and os.environ.get("BX_TC_READY", "1") == "1"))
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -307,7 +411,7 @@ def main():
         fl = flops_per_candidate(n, d) * m_count
         achieved = fl / (kern_ms_avg * 1e-3) / 1e12
         n_starts = opt.N_STARTS
-        f16 = args.engine in ("auto", "tcgen05_f16", "tcgen05_f16_pair", "tcgen05_f16_shared")
+        f16 = args.engine != "simt"
         if f16 and peaks.get("bf16_tflops_sustained"):
             # kind::f16 MMAs; the launch is ~1 s long under the 1000 W cap, so the sustained cuBLAS figure is the denominator
             peak, peak_src = float(peaks["bf16_tflops_sustained"]), (
@@ -317,33 +421,39 @@ def main():
         elif f16:
             peak, peak_src = 1400.0, "fallback of B200_PROFILING.md (sustained 1.4 PFLOP/s bf16; MEASURED_PEAKS.json absent)"
         else:
-            peak, peak_src = tf32_peak, ("dense TF32 cuBLAS 8192^3 measured in this run (MEASURED_PEAKS.json has 16-bit only); "
-                                         "the 3xTF32 split caps algorithmic flops at 1/3 of it")
+            peak, peak_src = ffma_peak, "fp32 SIMT engine: FFMA-only kernel timed in this run (bx_selftest_ffma)"
         roofline = {"bound": "tensor", "kernel": "score (generate -> K* -> T K* -> sum v^2 -> acquisition -> arg-max)",
                     "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
                     "frac_of_split_ceiling": 3 * achieved / peak if peak else None,
                     "traffic": TRAFFIC_BYTES.get((args.workload, M)), "kernel_ms": kern_ms_avg,
-                    "algorithmic_flops_per_launch": fl, "peak_source": peak_src, "tf32_peak_this_run": tf32_peak}
-        # scoring 1 + top-k 19 (init, 8 x hist, 8 x select, gather, sort) + start gather 1 + refinement 5 per round (K*, V chunks,
-        # reduce, W chunks, update); the conditional re-gather of a winning random candidate is not counted
-        launches_per_step = 1 + 19 + 1 + 5 * (opt.REFINE_ROUNDS + 1)
+                    "algorithmic_flops_per_launch": fl, "peak_source": peak_src, "ffma_peak_this_run": ffma_peak,
+                    "kernel_ms_covers": "front half of sample(): scoring kernel + hand-over pass (fp32 SIMT engine on the "
+                                        "cancellation-regime candidates) + top-k merge"}
+        # per sample(): scoring 1 + hand-over pass 1 + top-k merge 1 (+ 1 more merge at N > 1) + start gather 1 + refinement
+        # 5 per round (K*, V chunks, reduce, W chunks, update) + proposal 1; memsets / copies not counted
+        launches_per_step = 3 + (1 if world > 1 else 0) + 1 + 5 * (opt.REFINE_ROUNDS + 1) + 1
         line = {
             "metric": "acq candidate-evals/sec", "value": M * args.steps / t_res, "unit": "candidates/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_res / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": desc, "n_obs": n, "d": d, "candidates": M, "acq": acq, "n_starts": n_starts,
-                       "refine_rounds": opt.REFINE_ROUNDS, "engine": args.engine, "parallelism": f"candidate-shard x{world}",
-                       "l2": "256 MiB buffer rewritten between timed steps; T (hi+lo) is read from L2/HBM every step",
-                       "sample_latency_ms": 1e3 * t_res / args.steps, "fit_init_s": fit_s,
-                       "hyper": {"amp": float(hyp[0]), "noise": float(hyp[1])}},
+            "config": {"workload": desc, "n_obs": n, "d": d, "candidates": M, "acq": acq},  # same keys as the reference arm
+            "details": {"n_starts": n_starts, "refine_rounds": opt.REFINE_ROUNDS, "engine": args.engine,
+                        "parallelism": f"candidate shard x{world}, multi-start shard x{world}",
+                        "l2": "256 MiB buffer rewritten between timed steps; T (hi+lo) is read from L2/HBM every step",
+                        "sample_latency_ms": 1e3 * t_res / args.steps, "fit_init_s": fit_s,
+                        "hyper": {"amp": float(hyp[0]), "noise": float(hyp[1])}},
             "e2e": {"value": M * args.steps / t_e2e, "unit": "candidates/s", "ms_per_step": 1e3 * t_e2e / args.steps,
                     "h2d_bytes_per_step": int(X.nbytes + Y.nbytes + 4 * (d + 2) + 8),
-                    "d2h_bytes_per_step": int(4 * (d + 2) + 16 + 4 * n_starts * d + 4 * d)},
+                    "d2h_bytes_per_step": int(4 * (d + 2) + 4),
+                    "note": "cold cache every step: observations + raw hypers uploaded from host arrays, factor rebuilt on rank 0 "
+                            "(Gram + Cholesky + inverse) and broadcast (one NCCL broadcast of the flat factor buffer), the "
+                            "Cholesky status word and the proposal (d + 2 floats) read back"},
             "gpu_launches": launches_per_step * args.steps,
             "roofline": roofline,
             "clocks": clock_summary,
             "proposal": {k: float(v[0]) for k, v in list(proposal.items())[:3]},
         }
+        line.update(fit_rec)
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(d, n, acq, X, Y)
         print(json.dumps(line), flush=True)

@@ -34,7 +34,7 @@ extern "C" {
 #define BX_E_ARG (-1)       /* null pointer / non-positive size */
 #define BX_E_RANGE (-2)     /* size outside supported range (d > BX_MAX_D, k > BX_MAX_K ...) */
 #define BX_E_WORKSPACE (-3) /* workspace too small */
-#define BX_E_NOTPD (-4)     /* non-finite / non-positive Cholesky pivot (only from bx_check_status) */
+#define BX_E_NOTPD (-4)     /* non-finite / non-positive Cholesky pivot: returned by bx_check_status */
 #define BX_E_UNSUPPORTED (-5)
 
 #define BX_MAX_D 64   /* parameter-space dimensions */
@@ -43,12 +43,15 @@ extern "C" {
 
 /* acquisition ids - names follow bayex.acq (acq.py:8,53,90,124) */
 enum { BX_ACQ_EI = 0, BX_ACQ_PI = 1, BX_ACQ_UCB = 2, BX_ACQ_LCB = 3 };
-/* scoring engines: one production engine per regime, no zoo (the superseded experiments live in scripts/dev/engines) */
+/* scoring engines: one per regime, no zoo (superseded experiments, incl. the 3xTF32 engines, live in scripts/dev/engines) */
 enum {
-  BX_ENGINE_AUTO = 0,          /* fp16 tcgen05 engine when the factor has its fp16 copies and d <= 32, else SIMT */
-  BX_ENGINE_SIMT = 1,          /* fp32 FFMA pipes: explicit point sets, d > 32, and the on-GPU cross-check */
-  BX_ENGINE_TCGEN05_TF32 = 2,  /* 3xTF32, cta_group::2 (full fp32 exponent range of T; needs d_Thi / d_Tlo; opt-in) */
-  BX_ENGINE_TCGEN05_F16 = 3    /* fp16 head/tail split, cta_group::2, register-tiled K* producers: the production engine */
+  BX_ENGINE_AUTO = 0,           /* the production path when the factor has its fp16 copies and d <= 32, else SIMT */
+  BX_ENGINE_SIMT = 1,           /* fp32 FFMA pipes: explicit point sets, d > 32, cancellation-regime candidates */
+  BX_ENGINE_TCGEN05_F16 = 2,    /* the production path: tcgen05 with fp16 head/tail operands (3 MMAs per MAC, the same 22
+                                   operand bits as a 3xTF32 split at half the tensor work), cta_group::2, register-tiled K*
+                                   producers - and the fp32 SIMT engine on the candidates whose variance sits in the
+                                   cancellation regime */
+  BX_ENGINE_TCGEN05_F16_RAW = 3 /* the tensor engine alone, no hand-over (diagnostics: its own accuracy) */
 };
 
 /* One dimension of the parameter space - mirrors bayex.domain.Real / Integer (domain.py:22-131). */
@@ -69,8 +72,6 @@ typedef struct {
   int32_t d4;         /* row stride of d_U, multiple of 4 */
   const float* d_U;   /* [np x d4] observations * sqrt(log2 e) / lengthscale */
   const float* d_T;   /* [np x np] row-major, T = L^-1 (lower triangular), K = L L^T */
-  const float* d_Thi; /* [np x np] TF32-exact head of T (tcgen05 engine), may be NULL */
-  const float* d_Tlo; /* [np x np] tail T - Thi, may be NULL */
   const void* d_T16hi;  /* [np x np] fp16 head of T * 2^b (tcgen05 fp16 engine), may be NULL; 2^b is d_hyp[8] */
   const void* d_T16lo;  /* [np x np] fp16 tail, may be NULL */
   const float* d_alpha; /* [np] K^-1 (y - ymean) */
@@ -80,6 +81,11 @@ typedef struct {
 
 int32_t bx_version(void);
 const char* bx_last_error(void);
+
+/* Status of the last factorisation recorded in a factor's d_hyp[7] (a device read: synchronises `stream`).  Returns 0 or
+ * BX_E_NOTPD.  The reference's cholesky returns NaN silently; the Python layer calls this after every
+ * build and warns - it does not raise, the NaNs propagate exactly as they do upstream. */
+int32_t bx_check_status(const float* d_hyp, void* stream);
 
 /* Candidate generation - replaces: domain.py:159-161 (split), :74-75 (uniform+clip), :130-131 (randint+round/clip).
  * Writes candidates [m_begin, m_begin+m_count) of the draw `sample_params(key, (M,))` as float32 [m_count x d]. */
@@ -106,8 +112,10 @@ int32_t bx_nlml_grad(const float* d_X, const float* d_y, int32_t n, int32_t d, c
                      void* d_ws, size_t ws_bytes, void* stream);
 
 /* Hyper-parameter fit - replaces: gp.py:90-110 posterior_fit (clip_by_global_norm(10) + adamw(lr), fresh moments).
- * d_raw is updated in place; the whole loop runs on the device (CUDA graph replay, no host sync).
- * d_trace (optional) receives [steps x (2+d)] raw params before each step. */
+ * d_raw is updated in place; the whole loop runs on the device (one captured step replayed `steps` times: no host
+ * round-trip inside the loop).  EXCEPTION to the no-sync convention: with use_graph != 0 the call synchronises `stream`
+ * before it returns (the executable graph it created must outlive its queued launches; the library keeps no state that
+ * could own it).  d_trace (optional) receives [steps x (2+d)] raw params before each step (plain launches, no graph). */
 int32_t bx_fit_adamw(const float* d_X, const float* d_y, int32_t n, int32_t d, float* d_raw, float lr, int32_t steps,
                      float* d_trace, void* d_ws, size_t ws_bytes, int32_t use_graph, void* stream);
 
@@ -123,27 +131,34 @@ int32_t bx_fit_adamw_batch(const float* d_X, const float* d_y, int32_t n, int32_
                            int32_t steps, float* d_out, void* d_ws, size_t ws_bytes, void* stream);
 
 /* Posterior factor - replaces: gp.py:41-49 (softplus, centring, Gram, Cholesky, alpha) once per fit.
- * Outputs are the arrays referenced by bx_factor_t (caller allocates: U np*d4, T np*np, Thi/Tlo and T16hi/T16lo
+ * Outputs are the arrays referenced by bx_factor_t (caller allocates: U np*d4, T np*np, T16hi/T16lo
  * optional, alpha np, scale d4, hyp 16). */
 int32_t bx_factor_build(const float* d_X, const float* d_y, int32_t n, int32_t d, const float* d_raw, float* d_U,
-                        float* d_T, float* d_Thi, float* d_Tlo, void* d_T16hi, void* d_T16lo, float* d_alpha,
+                        float* d_T, void* d_T16hi, void* d_T16lo, float* d_alpha,
                         float* d_scale, float* d_hyp, void* d_ws, size_t ws_bytes, void* stream);
 
-#define BX_POINTS_TC_MIN 65536 /* bx_score_points: point sets at least this large use the tcgen05 engine if the factor has its fp16 copies */
+#define BX_POINTS_TC_MIN 65536 /* bx_score_points: point sets at least this large use the tcgen05 path if the factor has its fp16 copies */
+
+/* Hand-over workspace of the two-tier production path (bytes): the fp16 tcgen05 engine lists the candidates whose variance is
+ * below half the prior variance (where amp - sum v^2 cancels and the truncating fp32 accumulation of tcgen05.mma would
+ * show), the fp32 SIMT engine scores exactly those. */
+size_t bx_score_workspace_bytes(uint64_t M);
 
 /* Posterior + acquisition at explicit points - replaces: gp.py:59-71 predict, acq.py:45-50,84-87,120-121,155-156.
  * d_cand [M x d] raw (unscaled) points.  Any of d_mu / d_sigma / d_acq may be NULL.  d_best (optional) is a
- * uint64 packed arg-max accumulator (see bx_pack); index = index_base + row. */
+ * uint64 packed arg-max accumulator (see bx_pack); index = index_base + row.  d_ws (optional, bx_score_workspace_bytes(M)):
+ * without it every point is scored on the fp32 SIMT engine. */
 int32_t bx_score_points(const bx_factor_t* f, const float* d_cand, uint64_t M, int32_t acq_id, float acq_param,
                         float ystar, float* d_mu, float* d_sigma, float* d_acq, uint64_t* d_best,
-                        uint64_t index_base, void* stream);
+                        uint64_t index_base, void* d_ws, size_t ws_bytes, void* stream);
 
 /* Fused generate -> score -> arg-max over candidates [m_begin, m_begin+m_count) of sample_params(key, (M,)) -
  * replaces: optimizer.py:183-193 + :205.  No M x n intermediate is written; d_acq (optional, [m_count]) receives the
- * acquisition values for the top-k pass.  d_best must be zero-initialised by the caller (or hold a running max). */
+ * acquisition values.  d_best must be zero-initialised by the caller (or hold a running max).  d_ws:
+ * bx_score_workspace_bytes(m_count), needed by BX_ENGINE_AUTO / BX_ENGINE_TCGEN05_F16. */
 int32_t bx_score_generated(const bx_factor_t* f, const uint32_t key[2], const bx_dim_t* dims, uint64_t m_begin,
                            uint64_t m_count, int32_t acq_id, float acq_param, float ystar, float* d_acq,
-                           uint64_t* d_best, int32_t engine, void* stream);
+                           uint64_t* d_best, int32_t engine, void* d_ws, size_t ws_bytes, void* stream);
 
 /* Top-k by (value, index) ascending order, i.e. the last k of a stable argsort - replaces: optimizer.py:196.
  * NaN sorts last (largest).  Outputs ascending: d_out_idx[k-1] is the arg-max.  index = index_base + position. */
@@ -190,6 +205,10 @@ void bx_unpack(uint64_t key, float* value, uint32_t* index);
 /* 3xTF32 tcgen05 self-test: D[128 x N] = A[128 x K] * B[N x K]^T through the same descriptors/pipeline pieces the
  * scoring kernel uses.  Device pointers, row-major. */
 int32_t bx_selftest_umma(const float* d_A, const float* d_B, float* d_D, int32_t N, int32_t K, void* stream);
+
+/* fp32 SIMT peak probe: `blocks` CTAs of 256 threads, 8 independent FFMA chains of `iters` steps per thread
+ * (flops = blocks * 256 * iters * 16).  bench.py times it with CUDA events: the denominator of the fit path's roofline. */
+int32_t bx_selftest_ffma(float* d_out, int32_t blocks, int32_t iters, void* stream);
 
 #ifdef __cplusplus
 }

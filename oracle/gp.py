@@ -106,8 +106,12 @@ class Factor:
         logp += dt(-0.5 * np.log(2 * np.pi)) - np.log(self.amp) - np.log(self.amp) ** 2  # :56
         return dt(logp)
 
-    def predict(self, xt, chunk=8192, return_var=False):
-        """gp.py:59-71 with the diagonal of pred_var only (quirk Q8), chunked over candidates."""
+    def predict(self, xt, chunk=8192, return_var=False, threads=1):
+        """gp.py:59-71 with the diagonal of pred_var only (quirk Q8), chunked over candidates.
+
+        ``threads > 1`` (bench.py's CPU arm only): the chunks are independent, so they are spread over a thread pool -
+        NumPy releases the GIL inside the element-wise Gram build and inside BLAS; the caller limits BLAS itself to one
+        thread per call (threadpoolctl) so that ``threads`` cores are busy through both stages."""
         dt = self.dtype
         xt = _as2d(xt, dt)
         xt = (xt / self.ls).astype(dt)  # gp.py:60
@@ -115,12 +119,21 @@ class Factor:
         mean = np.empty((M,), dtype=dt)
         var = np.empty((M,), dtype=dt)
         am = (self.alpha * self.m).astype(dt)  # gp.py:66
-        for s in range(0, M, chunk):
+
+        def one(s):
             kc = self.amp * _cov_cols(self.xs, xt[s:s + chunk], self.m, dt)  # gp.py:64
             mean[s:s + chunk] = kc.T @ am + self.ymean  # gp.py:67
             v = solve_triangular(self.L, kc, lower=True, check_finite=False)  # gp.py:68
             # diag(amp*cov(xt,xt) - v.T@v): cov(xt,xt)_jj == 1  (gp.py:69-70)
             var[s:s + chunk] = self.amp - np.sum(v * v, axis=0, dtype=dt)
+
+        if threads > 1:
+            from concurrent.futures import ThreadPoolExecutor
+            with ThreadPoolExecutor(max_workers=threads) as pool:
+                list(pool.map(one, range(0, M, chunk)))
+        else:
+            for s in range(0, M, chunk):
+                one(s)
         std = np.sqrt(np.maximum(var, dt(1e-10))).astype(dt)  # gp.py:70
         return (mean, std, var) if return_var else (mean, std)
 

@@ -9,7 +9,7 @@ mkdir -p "$CS/build/variants"
 "$NVCC" -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC --expt-relaxed-constexpr $DEFS \
   -c "$CS/$UNIT.cu" -o "$CS/build/variants/${UNIT}_$NAME.o" 2>/dev/null
 OBJS=()
-for f in linalg fit score score_tc2 score_tc16p selftest topk refine; do
+for f in linalg fit score score_tc16p selftest topk refine; do
   if [ "$f" == "$UNIT" ]; then OBJS+=("$CS/build/variants/${UNIT}_$NAME.o"); else OBJS+=("$CS/build/$f.o"); fi
 done
 "$NVCC" -shared -o "$CS/build/variants/$NAME.so" "${OBJS[@]}"

@@ -18,13 +18,29 @@ from oracle import acq as oacq, domain as odom, gp as ogp, optimizer as oopt, pr
 RTOL = 1e-4
 
 
-def assert_close(got, ref64, ref32=None, rtol=RTOL, what=""):
-    """|got - ref64| <= max(rtol * max(|ref64|, floor), 4 * |ref32 - ref64|)."""
+def mean_sum_floor(f64, xt, chunk=8192):
+    """fp32 floor of the posterior mean as a SUM: mu = sum_j alpha_j k_j(x) + ymean evaluated in float32 cannot be better than
+    ~u sum_j |alpha_j k_j| whatever the order of summation (u = 2^-24; the textbook bound carries another factor n).  With
+    |alpha| ~ 1e2..1e3 and terms of both signs that is what limits the mean where 1e-4 |mu| is small; returned per point."""
+    xt = np.asarray(xt, np.float64)
+    xt = xt[:, None] if xt.ndim == 1 else xt
+    out = np.empty(xt.shape[0])
+    aa = np.abs(f64.alpha * f64.m)
+    for s0 in range(0, xt.shape[0], chunk):
+        kc = f64.amp * ogp._cov_cols(f64.xs, xt[s0:s0 + chunk] / f64.ls, f64.m, np.float64)
+        out[s0:s0 + chunk] = aa @ kc
+    return out * 2.0 ** -24
+
+
+def assert_close(got, ref64, ref32=None, rtol=RTOL, what="", floor=None):
+    """|got - ref64| <= max(rtol * max(|ref64|, mean |ref64|), 4 * |ref32 - ref64|, 8 * floor)."""
     got, ref64 = np.asarray(got, np.float64), np.asarray(ref64, np.float64)
     scale = np.maximum(np.abs(ref64), np.abs(ref64).mean() if ref64.size else 1.0)
     tol = rtol * scale
     if ref32 is not None:
         tol = np.maximum(tol, 4.0 * np.abs(np.asarray(ref32, np.float64) - ref64))
+    if floor is not None:
+        tol = np.maximum(tol, 8.0 * np.asarray(floor, np.float64))
     err = np.abs(got - ref64)
     bad = err > tol
     assert not bad.any(), (f"{what}: {bad.sum()}/{bad.size} outside tolerance; worst err {err.max():.3e} "
@@ -145,7 +161,7 @@ def test_acq1d_golden(golden, pad):
                    ("UCB", bayex.acq.upper_confidence_bounds), ("LCB", bayex.acq.lower_confidence_bounds)):
         got = fn(xt, xp, yp, mp, P)
         assert got.shape == xt.shape and np.all(np.isfinite(got))
-        assert_close(got, golden[f"acq1d_{nm}_pad{pad}_f64"], golden[f"acq1d_{nm}_pad{pad}"], rtol=2e-4, what=nm)
+        assert_close(got, golden[f"acq1d_{nm}_pad{pad}_f64"], golden[f"acq1d_{nm}_pad{pad}"], what=nm)
 
 
 def test_multidim_golden(golden):
@@ -244,7 +260,8 @@ def test_fused_generated_scoring_argmax_and_topk(space, n, M, acq):
     v, i = _lib.unpack(engine.to_unsigned(int(best.item())))
     assert i == oopt.jnp_argmax(got) and np.float32(v) == got[i]
     j = oopt.jnp_argmax(a64)
-    assert i == j or abs(a64[i] - a64[j]) <= 2e-4 * max(abs(a64[j]), 1e-30) + 4 * abs(a32[j] - a64[j])
+    # tie rule: the two leaders are indistinguishable when each may be off by the 1e-4 bar (or the fp32 oracle's own error)
+    assert i == j or abs(a64[i] - a64[j]) <= RTOL * (abs(a64[i]) + abs(a64[j])) + 4 * abs(a32[j] - a64[j]) + 4 * abs(a32[i] - a64[i])
     # top-50 (optimizer.py:196): exact w.r.t. the CUDA values incl. tie order
     tv, ti = post.topk(vals, 50)
     assert np.array_equal(ti.cpu().numpy().astype(np.int64), oopt.jnp_argsort(got)[-50:])
@@ -260,6 +277,45 @@ def test_fused_generated_scoring_argmax_and_topk(space, n, M, acq):
     mv, mi = bayex.optimizer.merge_topk(np.concatenate([t0.cpu().numpy(), t1.cpu().numpy()]),
                                         np.concatenate([i0.cpu().numpy(), i1.cpu().numpy()]), 50)
     assert np.array_equal(mi, ti.cpu().numpy())
+    # the fused path (per-CTA top-k inside the scoring kernels + merge) gives the same list, on both engines and
+    # for any shard split; the merged shard lists equal the unsharded list, entry [k] is the arg-max key
+    want_idx, want_val = oopt.jnp_argsort(got)[-50:], got[oopt.jnp_argsort(got)[-50:]]
+    for eng in (_lib.ENGINE_SIMT, _lib.ENGINE_AUTO):
+        lst, fv, fi, _ = post.sample_front(key, dims, 0, M, acq, param, ystar, 50, engine=eng)
+        if eng == _lib.ENGINE_SIMT:
+            assert np.array_equal(fi.cpu().numpy().astype(np.int64), want_idx) and np.array_equal(fv.cpu().numpy(), want_val)
+            assert engine.to_unsigned(int(lst[50].item())) == engine.to_unsigned(int(best.item()))
+        la, _, _, _ = post.sample_front(key, dims, 0, h, acq, param, ystar, 50, engine=eng)
+        lb, _, _, _ = post.sample_front(key, dims, h, M - h, acq, param, ystar, 50, engine=eng)
+        lm, mv2, mi2 = post.merge_lists(torch.cat([la, lb]), 2, 50)
+        assert torch.equal(lm, lst), "merged shard lists differ from the unsharded list"
+        assert torch.equal(mi2, fi) and torch.equal(mv2, fv)
+
+
+def test_fused_topk_mass_ties_and_small_counts():
+    """PI == 0 on (almost) the whole domain: millions of equal values, the reference's `argsort[-k:]` is then the LAST k
+    indices; k up to 1024; fewer candidates than k (the list is zero-padded at the front)."""
+    dom, odomn = both_spaces("mixed10")
+    d, n = 10, 64
+    ospace = odom.ParamSpace(odomn)
+    Xd = ospace.to_array(ospace.sample_params(prng.key(0), (n,)))
+    Y = (-np.sum(Xd ** 2, axis=1)).astype(np.float32)
+    raw = np.concatenate([[-5.0], [0.2], np.full(d, -1.0)]).astype(np.float32)  # short length scales: PI underflows to 0
+    key, dims = prng.key(4), engine.dims_array(dom)
+    post = engine.Posterior(Xd, Y, raw).build()
+    ystar = bayex.acq.ystar_for("PI", np.concatenate([Y, np.zeros(6, np.float32)]), np.concatenate([np.ones(n), np.zeros(6)]))
+    for M, k in ((300_000, 50), (70_001, 1024), (37, 50), (1, 50)):
+        vals, best = post.score_generated(key, dims, 0, M, "PI", 0.01, ystar)
+        got = vals.cpu().numpy()
+        lst, fv, fi, _ = post.sample_front(key, dims, 0, M, "PI", 0.01, ystar, k)
+        kk = min(k, M)
+        want = oopt.jnp_argsort(got)[-kk:]
+        assert np.array_equal(fi.cpu().numpy()[:kk].astype(np.int64), want), (M, k)
+        assert np.array_equal(fv.cpu().numpy()[:kk], got[want] + 0.0)
+        host = lst.cpu().numpy().astype(np.uint64)
+        assert np.all(host[:k - kk] == 0) and np.all(host[k - kk:k] != 0)
+        assert int(host[k]) == engine.to_unsigned(int(best.item()))
+    assert (got == 0.0).mean() > 0.5, "the fixture is meant to produce a mass of exact ties"
 
 
 def test_topk_ties_nan_and_signed_zero():
@@ -305,6 +361,44 @@ def test_posterior_fit_vs_oracle(n, d):
     assert np.all(np.abs(np.diff(tr, axis=0)) <= 1.2e-3), "Adam steps are bounded by ~lr"
 
 
+@pytest.mark.parametrize("n,scale_y,multi_kernel,expect_clipped", [(40, 1.0, False, True), (300, 1.0, False, True),
+                                                                   (5, 1.0, False, False), (12, 0.1, True, False)])
+def test_adamw_kernel_step_by_step(n, scale_y, multi_kernel, expect_clipped, monkeypatch):
+    """a12 / SURVEY 8.A4: clip_by_global_norm(10) + adamw(1e-3) on the device, step by step.  The trace gives the raw hypers
+    before every step; the gradient the device used at that point is re-read through bx_nlml_grad (same kernels), and the
+    oracle's AdamW restatement (oracle/gp.py:adamw_step, cross-checked against torch.optim.AdamW in test_oracle_golden)
+    is driven with exactly those gradients in float32: every one of the 100 updates must agree to 1e-6.  n <= 56 runs the
+    one-kernel fit (its own copy of the update) unless BX_NO_FIT_SMALL forces the multi-kernel loop; the gradient norm of
+    this objective is in the hundreds for any realistic n (every step clipped), n = 5 and n = 12 with small targets cover
+    the un-clipped branch on both code paths."""
+    if multi_kernel:
+        monkeypatch.setenv("BX_NO_FIT_SMALL", "1")
+    d, steps = 3, 100
+    X, Y, raw, P = make_problem(n, d, seed=5 * n, noise_raw=-8.0)
+    Y = (Y * scale_y).astype(np.float32)
+    raw[1], raw[2:] = 0.0, 0.0
+    post = engine.Posterior(X, Y, raw.copy(), want_tc=False)
+    tr = post.fit_hypers(steps=steps, trace=True, use_graph=False).cpu().numpy()
+    final = post.raw_host()
+    assert np.array_equal(tr[0], raw)
+    p = raw.copy()
+    m, v, t = np.zeros_like(p), np.zeros_like(p), 0
+    clipped = 0
+    probe = engine.Posterior(X, Y, raw.copy(), want_tc=False)
+    for i in range(steps):
+        assert np.allclose(tr[i], p, rtol=0, atol=1e-6), f"step {i}: device {tr[i]} oracle {p}"
+        probe.set_raw(tr[i])                       # the device's own iterate: errors do not compound across steps
+        _, _, g, _ = probe.nlml_grad()
+        clipped += float(np.sqrt(np.sum(g.astype(np.float64) ** 2))) >= 10.0
+        p, m, v, t = ogp.adamw_step(tr[i].astype(np.float32), g.astype(np.float32), m, v, t, 1e-3, np.float32)
+    assert np.allclose(final, p, rtol=0, atol=1e-6)
+    assert (clipped == steps) if expect_clipped else (clipped == 0), f"clipped steps: {clipped}"
+    # CUDA-graph replay gives the same bits as plain launches
+    again = engine.Posterior(X, Y, raw.copy(), want_tc=False)
+    again.fit_hypers(steps=steps, use_graph=True)
+    assert np.array_equal(again.raw_host(), final)
+
+
 @pytest.mark.parametrize("acq", ["EI", "PI", "UCB", "LCB"])
 def test_refinement_contract(acq):
     """Replacement of optimizer.py:39-73: monotone ascent - every refined value >= its start value, and the values
@@ -323,11 +417,20 @@ def test_refinement_contract(acq):
     v1 = post.score_points(xr, acq=acq, param=param, ystar=ystar, want=("acq",))["acq"].cpu().numpy()
     assert np.all(v1 >= v0 - 1e-5 * np.abs(v0) - 1e-7), f"refinement made a start worse: {np.min(v1 - v0)}"
     assert np.mean(v1 > v0) > 0.5, f"refinement did not move most starts: {np.mean(v1 > v0)}"
-    assert np.allclose(vr.cpu().numpy(), v1, rtol=2e-4, atol=1e-7)
+    assert np.allclose(vr.cpu().numpy(), v1, rtol=RTOL, atol=1e-7)
     # same algorithm restated in the oracle (fp64): reaches comparable values
     f64 = ogp.Factor(P, X, Y, np.ones(n), np.float64)
     _, fo = oopt.refine_ascent(acq, f64, Y.astype(np.float64), np.ones(n), starts.astype(np.float64), rounds=30)
     assert np.median(v1 - v0) >= 0.5 * np.median(fo - v0) - 1e-7
+    # SURVEY Q12 contract, judged by the ORACLE: every refined point's fp64 acquisition is at least its start's (up to the
+    # 1e-4 bar), so the proposal - the arg-max over refined + random - is never worse than the best random candidate
+    o0 = oacq.acq_from_moments(acq, *f64.predict(starts.astype(np.float64)), Y.astype(np.float64), np.ones(n))
+    o1 = oacq.acq_from_moments(acq, *f64.predict(xr.cpu().numpy().astype(np.float64)), Y.astype(np.float64), np.ones(n))
+    assert np.all(o1 >= o0 - RTOL * np.maximum(np.abs(o0), np.abs(o0).mean()) - 1e-9), np.min(o1 - o0)
+    assert o1.max() >= oacq.acq_from_moments(acq, *f64.predict(pool.astype(np.float64)), Y.astype(np.float64), np.ones(n)).max() * (1 - RTOL) - 1e-9
+    # the multi-start axis shards: refining a slice of the starts gives the bits of refining them all
+    xa, va = post.refine(torch.from_numpy(starts[7:20]).cuda(), 30, acq, param, ystar)
+    assert torch.equal(xa, xr[7:20]) and torch.equal(va, vr[7:20])
     # analytic gradient inside the kernel: one round from a start must not decrease and must move along +grad
     val, grad = oopt.acq_value_and_grad(acq, f64, Y.astype(np.float64), np.ones(n), starts[:4].astype(np.float64))
     x1, _ = post.refine(torch.from_numpy(starts[:4]).cuda(), 1, acq, param, ystar)
@@ -449,10 +552,30 @@ def test_umma_selftest_3xtf32(K):
     assert err.max() < 2e-6, f"3xTF32 error {err.max():.3e} (plain TF32 would be ~5e-4)"
 
 
+def acq_tolerance(acq, mu64, sd64, mu32, sd32, ys, mask):
+    """The bar every engine is held to: 1e-4 relative on the acquisition value, or - where fp32 itself cannot hold that - 4x
+    the fp32 oracle's own distance to the fp64 oracle at that point, or what the moments' own budget (1e-4 relative, same
+    fp32 escape) propagates to through the closed form (EI / PI amplify a relative sigma error by |z| phi(z))."""
+    ys64 = np.asarray(ys, np.float64)
+    a64 = oacq.acq_from_moments(acq, mu64, sd64, ys64, mask)
+    a32 = oacq.acq_from_moments(acq, mu32, sd32, np.asarray(ys, np.float32), mask)
+    tmu = np.maximum(RTOL * np.maximum(np.abs(mu64), np.abs(mu64).mean()), 4 * np.abs(mu32 - mu64))
+    tsd = np.maximum(RTOL * sd64, 4 * np.abs(sd32.astype(np.float64) - sd64))
+    prop = np.zeros_like(a64)
+    for smu in (-1, 1):
+        for ssd in (-1, 1):
+            prop = np.maximum(prop, np.abs(oacq.acq_from_moments(acq, mu64 + smu * tmu, np.maximum(sd64 + ssd * tsd, 1e-12), ys64, mask) - a64))
+    return a64, np.maximum.reduce([RTOL * np.maximum(np.abs(a64), np.abs(a64).mean()), 4 * np.abs(a32 - a64), 2 * prop])
+
+
 @pytest.mark.parametrize("n,d,M,acq", [(200, 3, 1000, "UCB"), (512, 6, 37965, "EI"), (1000, 10, 5000, "LCB"),
                                        (2048, 20, 4096, "LCB"), (1300, 20, 3000, "PI"), (700, 27, 2500, "EI"),
                                        (384, 32, 1111, "UCB"), (64, 1, 129, "PI"), (8192, 8, 700, "EI")])
-def test_tcgen05_engine_matches_simt_engine_and_oracle(n, d, M, acq):
+def test_production_path_matches_simt_engine_and_oracle(n, d, M, acq):
+    """The production path (AUTO = fp16 tcgen05 engine + fp32 SIMT engine on the candidates it hands over) is held to the
+    SAME bar as the fp32 SIMT engine: the oracle, pointwise.  The tensor engine alone (RAW, diagnostics) is looked at
+    separately: it must agree with the production path bit for bit where it keeps a candidate, and the candidates it
+    hands over must come back with the SIMT engine's bits."""
     X, Y, raw, P = make_problem(n, d, seed=n * 3 + d)
     dom = {f"x{i}": bayex.domain.Real(-0.1, 1.1) for i in range(d)}
     dims = engine.dims_array(dom)
@@ -461,46 +584,53 @@ def test_tcgen05_engine_matches_simt_engine_and_oracle(n, d, M, acq):
     param = bayex.acq.DEFAULT_PARAM[acq]
     key = prng.key(n)
     v_s, b_s = post.score_generated(key, dims, 5, M, acq, param, ystar, engine=_lib.ENGINE_SIMT)
-    v_t, b_t = post.score_generated(key, dims, 5, M, acq, param, ystar, engine=_lib.ENGINE_TCGEN05)
-    v_p, b_p = post.score_generated(key, dims, 5, M, acq, param, ystar, engine=_lib.ENGINE_TCGEN05_PAIR)
-    v_h, b_h = post.score_generated(key, dims, 5, M, acq, param, ystar, engine=_lib.ENGINE_TCGEN05_F16)
-    v_q, b_q = post.score_generated(key, dims, 5, M, acq, param, ystar, engine=_lib.ENGINE_TCGEN05_F16_PAIR)
-    v_r, b_r = post.score_generated(key, dims, 5, M, acq, param, ystar, engine=_lib.ENGINE_TCGEN05_F16_SHARED)
-    v_x, b_x = post.score_generated(key, dims, 5, M, acq, param, ystar, engine=_lib.ENGINE_TCGEN05_F16_T)
-    s, t, pr, hf, hp, hs, hx = (v.cpu().numpy().astype(np.float64) for v in (v_s, v_t, v_p, v_h, v_q, v_r, v_x))
-    assert np.all(np.isfinite(t)) and np.all(np.isfinite(pr)) and np.all(np.isfinite(hf)) and np.all(np.isfinite(hp)) and np.all(np.isfinite(hs))
-    assert np.all(np.isfinite(hx))
+    v_q, b_q = post.score_generated(key, dims, 5, M, acq, param, ystar, engine=_lib.ENGINE_AUTO)
+    v_r, b_r = post.score_generated(key, dims, 5, M, acq, param, ystar, engine=_lib.ENGINE_TCGEN05_F16_RAW)
+    s, q, r = (v.cpu().numpy() for v in (v_s, v_q, v_r))
+    assert np.all(np.isfinite(q)) and np.all(np.isfinite(r))
     cand = engine.threefry_fill(key, dims, d, 5, M).cpu().numpy()
     f64, f32 = ogp.Factor(P, X, Y, np.ones(n), np.float64), ogp.Factor(P, X, Y, np.ones(n), np.float32)
     mu64, sd64 = f64.predict(cand.astype(np.float64))
     mu32, sd32 = f32.predict(cand)
-    mom = post.score_points(cand, acq=acq, param=param, ystar=ystar, want=("mu", "sigma"))
-    # the tensor-core engine is held to the same bar as the SIMT engine: the oracle, not just its sibling
-    a64 = oacq.acq_from_moments(acq, mu64, sd64, Y.astype(np.float64), np.ones(n))
-    a32 = oacq.acq_from_moments(acq, mu32, sd32, Y, np.ones(n))
-    tmu = np.maximum(RTOL * np.maximum(np.abs(mu64), np.abs(mu64).mean()), 4 * np.abs(mu32 - mu64))
-    tsd = np.maximum(RTOL * sd64, 4 * np.abs(sd32.astype(np.float64) - sd64))
-    prop = np.zeros_like(a64)
-    for smu in (-1, 1):
-        for ssd in (-1, 1):
-            prop = np.maximum(prop, np.abs(oacq.acq_from_moments(acq, mu64 + smu * tmu, np.maximum(sd64 + ssd * tsd, 1e-12),
-                                                                 Y.astype(np.float64), np.ones(n)) - a64))
-    tol = np.maximum.reduce([RTOL * np.maximum(np.abs(a64), np.abs(a64).mean()), 4 * np.abs(a32 - a64), 2 * prop])
-    # The fp32 SIMT engine is held to the oracle bar as is.  The tensor engines read the SAME device-built fp32 factor
-    # (T, alpha), so where that factor itself sits at the fp32 floor (n = 8192: cond(K) ~ 1e5, every engine AND the fp32
-    # NumPy oracle are ~1e-4 off the fp64 oracle) they are allowed twice the SIMT engine's own distance to fp64.
-    # ... and never less than twice the WORST error the fp32 NumPy oracle itself makes on these inputs: the residual is the
-    # fp32 summation order of mu = sum alpha_j k_j (|alpha| ~ 1e3 at n = 8192), which differs from engine to engine.
-    tol_tc = np.maximum.reduce([tol, 2 * np.abs(s - a64), np.full_like(tol, 2 * np.abs(a32 - a64).max())])
-    for name, got, bar in (("simt", s, tol), ("tcgen05", t, tol_tc), ("tcgen05_pair", pr, tol_tc), ("tcgen05_f16", hf, tol_tc),
-                           ("tcgen05_f16_pair", hp, tol_tc), ("tcgen05_f16_shared", hs, tol_tc),
-                           ("tcgen05_f16_transposed", hx, tol_tc)):
-        err = np.abs(got - a64)
-        assert np.all(err <= bar), f"{name}: {np.sum(err > bar)}/{M} outside tolerance, worst {err.max():.3e} at {np.argmax(err)}"
-    assert np.abs(s - t).max() <= 2 * tol.max() and np.abs(s - pr).max() <= 2 * tol.max()
-    for vv, bb in ((v_t, b_t), (v_p, b_p), (v_h, b_h), (v_q, b_q), (v_r, b_r), (v_x, b_x)):
+    a64, tol = acq_tolerance(acq, mu64, sd64, mu32, sd32, Y, np.ones(n))
+    for name, got in (("simt", s), ("production", q)):
+        err = np.abs(got.astype(np.float64) - a64)
+        assert np.all(err <= tol), f"{name}: {np.sum(err > tol)}/{M} outside tolerance, worst {err.max():.3e} at {np.argmax(err)}"
+    # who scored what: variance from the SIMT engine's moments decides, with a margin around the hand-over threshold
+    mom = post.score_points(cand, acq=acq, param=param, ystar=ystar, want=("sigma",))
+    var_rel = mom["sigma"].cpu().numpy().astype(np.float64) ** 2 / float(post.hyp()[0])
+    handed, kept = var_rel < 0.45, var_rel > 0.55
+    assert np.array_equal(q[handed], s[handed]), "handed-over candidates must carry the SIMT engine's bits"
+    assert np.array_equal(q[kept], r[kept]), "kept candidates must carry the tensor engine's bits"
+    for vv, bb in ((v_q, b_q), (v_r, b_r), (v_s, b_s)):
         vt, it = _lib.unpack(engine.to_unsigned(int(bb.item())))
         assert it == 5 + oopt.jnp_argmax(vv.cpu().numpy()) and np.float32(vt) == vv.cpu().numpy()[it - 5]
+
+
+def test_tensor_engine_alone_variance_bias_is_what_the_handover_assumes():
+    """The reason for the hand-over, pinned: tcgen05.mma accumulates with truncation, so the tensor engine alone
+    over-estimates sum v^2 by up to ~6e-5 relative (scripts/dev/umma_probe.py, diag_bias_sign.py).  For a candidate it keeps
+    (var >= amp / 2) that is at most 6e-5 of var - inside the 1e-4 bar; this test measures the bias on a noise = softplus(-8)
+    factor (the worst case seen) and fails if it ever exceeds what the threshold was chosen for."""
+    n, d, M = 2048, 8, 8192
+    X, Y, raw, P = make_problem(n, d, seed=77, noise_raw=-8.0)
+    dom = {f"x{i}": bayex.domain.Real(-0.6, 1.6) for i in range(d)}  # wide enough for a far field around the observations
+    dims = engine.dims_array(dom)
+    post = engine.Posterior(X, Y, raw, want_tc=True).build()
+    key = prng.key(3)
+    amp = float(post.hyp()[0])
+    cand = engine.threefry_fill(key, dims, d, 0, M).cpu().numpy()
+    sd64 = ogp.Factor(P, X, Y, np.ones(n), np.float64).predict(cand.astype(np.float64))[1]
+    # LCB with kappa = 1, mu removed through UCB with kappa = 1: sigma = (ucb - lcb) / 2 of the RAW engine
+    u, _ = post.score_generated(key, dims, 0, M, "UCB", 1.0, 0.0, engine=_lib.ENGINE_TCGEN05_F16_RAW)
+    l, _ = post.score_generated(key, dims, 0, M, "LCB", 1.0, 0.0, engine=_lib.ENGINE_TCGEN05_F16_RAW)
+    sd_raw = 0.5 * (u.cpu().numpy().astype(np.float64) - l.cpu().numpy().astype(np.float64))
+    ssq64, ssq_raw = amp - sd64 ** 2, amp - sd_raw ** 2
+    far = sd64 ** 2 >= 0.5 * amp
+    rel = np.abs(ssq_raw - ssq64)[far] / np.maximum(sd64[far] ** 2, 1e-30)
+    print(f"tensor engine alone: {far.sum()} far candidates, worst bias of sum v^2 relative to var {rel.max():.3e}; "
+          f"all candidates: worst |sum v^2 error| / amp {np.abs(ssq_raw - ssq64).max() / amp:.3e}")
+    assert far.sum() > 100 and rel.max() <= 1e-4, (far.sum(), rel.max())
 
 
 @pytest.mark.parametrize("space,n,acq", [("mixed10", 2048, "PI"), ("mixed10", 130, "EI"), ("real6", 3, "UCB")])
@@ -525,7 +655,7 @@ def test_production_engine_mixed_domain_ragged_shards(space, n, acq):
     ref = ref.cpu().numpy().astype(np.float64)
     assert np.all(np.isfinite(full))
     scale = np.maximum(np.abs(ref), np.abs(ref).mean())
-    assert np.all(np.abs(full - ref) <= 5e-4 * scale + 1e-7), np.abs(full - ref).max()
+    assert np.all(np.abs(full - ref) <= 2e-4 * scale + 1e-7), np.abs(full - ref).max()  # two engines, each within 1e-4
     v, i = _lib.unpack(engine.to_unsigned(int(bfull.item())))
     assert i == oopt.jnp_argmax(full) and np.float32(v) == full[i]
     for cuts in ([1], [127, 128, 129], [255, 257, 600], [M - 1]):
@@ -574,15 +704,115 @@ def test_config3_full_size_properties():
     tv, ti = post.topk(vals, 50)
     t5, i5 = post.topk(v5, 50, index_base=b)
     assert set(i5.cpu().numpy().tolist()) >= set(int(x) for x in ti.cpu().numpy() if b <= x < b + c)
-    # oracle spot check on a strided sample of the same draw
+    # oracle spot check on a strided sample of the same draw, at the contract tolerance (1e-4, fp32-floor escape pointwise)
     sel = torch.arange(0, M, M // 4096, dtype=torch.int32, device="cuda")[:4096]
     cand = post.gather(key, dims, sel).cpu().numpy()
     P = ogp.GPParams(raw[0], raw[1], raw[2:])
-    f64 = ogp.Factor(P, X, Y, np.ones(n), np.float64)
+    f64, f32 = ogp.Factor(P, X, Y, np.ones(n), np.float64), ogp.Factor(P, X, Y, np.ones(n), np.float32)
     mu64, sd64 = f64.predict(cand.astype(np.float64))
-    want = mu64 + 0.01 * sd64
+    mu32, sd32 = f32.predict(cand)
+    a64, tol = acq_tolerance("UCB", mu64, sd64, mu32, sd32, Y, np.ones(n))
     got = vals[sel.long()].cpu().numpy()
-    assert_close(got, want, rtol=2e-4, what="UCB @ C3")
+    assert np.all(np.abs(got - a64) <= tol), np.abs(got - a64).max()
+    # sigma-sensitive acquisitions on the same 2^24 candidates: UCB's kappa = 0.01 hides sigma 100-fold
+    for acq, param in (("LCB", 2.576), ("EI", 0.01)):
+        ystar = bayex.acq.ystar_for(acq, Y, np.ones(n))
+        va, ba = post.score_generated(key, dims, 0, M, acq, param, ystar)
+        a64, tol = acq_tolerance(acq, mu64, sd64, mu32, sd32, Y, np.ones(n))
+        got = va[sel.long()].cpu().numpy()
+        err = np.abs(got - a64)
+        assert np.all(err <= tol), f"{acq} @ C3: {np.sum(err > tol)} outside tolerance, worst {err.max():.3e}"
+        v, i = _lib.unpack(engine.to_unsigned(int(ba.item())))
+        vmax, _ = torch.max(va, dim=0)
+        assert np.float32(v) == vmax.item() and i == int((va == vmax).nonzero()[0].item())
+        del va
+
+
+def _shortlist_argmax_check(vals, key, dims, post, f64, f32, acq, ys, mask, n_top=2000, n_rand=4096, seed=0):
+    """Full-size arg-max parity without an M-sized oracle run: the oracle scores the n_top best candidates by the CUDA
+    values plus a random sample.  The sample pins |cuda - oracle| <= tol pointwise; a candidate outside the shortlist
+    could only win if it were off by more than the gap between the shortlist's worst value and the winner."""
+    M = vals.numel()
+    tv, ti = torch.topk(vals, n_top)
+    rng = np.random.default_rng(seed)
+    ri = torch.from_numpy(rng.choice(M, n_rand, replace=False).astype(np.int32)).cuda()
+    idx = torch.cat([ti.to(torch.int32), ri])
+    cand = post.gather(key, dims, idx).cpu().numpy()
+    mu64, sd64 = f64.predict(cand.astype(np.float64))
+    mu32, sd32 = f32.predict(cand)
+    a64, tol = acq_tolerance(acq, mu64, sd64, mu32, sd32, ys, mask)
+    got = vals[idx.long()].cpu().numpy().astype(np.float64)
+    err = np.abs(got - a64)
+    assert np.all(err <= tol), f"{acq}: {np.sum(err > tol)} outside tolerance, worst {err.max():.3e}"
+    return idx.cpu().numpy(), cand, a64, tol, got
+
+
+def test_config4_mixed_domain_full_size_production_path():
+    """C4 on the production path (AUTO): 5 x Real(-5, 5) interleaved with 5 x Integer(-10, 10), PI, n = 2048; M = 10 000 against
+    the full oracle, M = 2^20 through the shortlist argument.  Integer columns bit-equal to the oracle's draws, arg-max
+    index equal to the oracle's (ties within tolerance excepted)."""
+    dom, odomn = both_spaces("mixed10")
+    d, n = 10, 2048
+    ospace = odom.ParamSpace(odomn)
+    Xd = ospace.to_array(ospace.sample_params(prng.key(0), (n,)))
+    Y = (-np.sum((Xd - np.array([1.0, 2, -1, 0, 0.5, -3, 2, 4, -2, 1], np.float32)) ** 2, axis=1)).astype(np.float32)
+    raw = np.concatenate([[-5.0], [3.0], np.full(d, 2.5)]).astype(np.float32)  # length scales ~2.6: the GP is non-trivial
+    P = ogp.GPParams(raw[0], raw[1], raw[2:])
+    mask = np.ones(n)
+    ypad = np.concatenate([Y, np.zeros(2, np.float32)])  # padded state (2050): PI's unmasked max sees the zeros (Q10)
+    mpad = np.concatenate([mask, np.zeros(2)])
+    ystar = bayex.acq.ystar_for("PI", ypad, mpad)
+    key, dims = prng.key(1), engine.dims_array(dom)
+    post = engine.Posterior(Xd, Y, raw).build()
+    f64, f32 = ogp.Factor(P, Xd, Y, mask, np.float64), ogp.Factor(P, Xd, Y, mask, np.float32)
+    # M = 10 000: everything against the oracle
+    M = 10_000
+    vals, best = post.score_generated(key, dims, 0, M, "PI", 0.01, ystar)
+    got = vals.cpu().numpy()
+    ocand = ospace.to_array(ospace.sample_params(key, (M,)))
+    cand = engine.threefry_fill(key, dims, d, 0, M).cpu().numpy()
+    assert np.array_equal(cand[:, 1::2], ocand[:, 1::2]) and np.all(cand[:, 1::2] == np.round(cand[:, 1::2]))
+    assert np.array_equal(cand.view(np.uint32), ocand.view(np.uint32))
+    mu64, sd64 = f64.predict(ocand.astype(np.float64))
+    mu32, sd32 = f32.predict(ocand)
+    a64, tol = acq_tolerance("PI", mu64, sd64, mu32, sd32, ypad, mpad)
+    assert np.all(np.abs(got - a64) <= tol), np.abs(got - a64).max()
+    v, i = _lib.unpack(engine.to_unsigned(int(best.item())))
+    j = oopt.jnp_argmax(a64)
+    assert i == oopt.jnp_argmax(got) and (i == j or abs(a64[i] - a64[j]) <= tol[i] + tol[j])
+    # M = 2^20
+    M = 1 << 20
+    vals, best = post.score_generated(key, dims, 0, M, "PI", 0.01, ystar)
+    v, i = _lib.unpack(engine.to_unsigned(int(best.item())))
+    vmax, _ = torch.max(vals, dim=0)
+    assert np.float32(v) == vmax.item() and i == int((vals == vmax).nonzero()[0].item())
+    idx, cand, a64, tol, got = _shortlist_argmax_check(vals, key, dims, post, f64, f32, "PI", ypad, mpad)
+    ocand = ospace.to_array(ospace.sample_params(key, (M,)))  # the draw itself is cheap on the CPU
+    assert np.array_equal(cand, ocand[idx]), "Integer and Real columns of the scored candidates differ from the oracle draw"
+    j = int(np.argmax(a64))  # oracle's winner inside the shortlist
+    assert idx[j] == i or abs(a64[j] - a64[list(idx).index(i)]) <= 2 * tol[j], (idx[j], i)
+    worst_short = float(torch.topk(vals, 2000)[0][-1].item())
+    assert worst_short + 4 * tol.max() < vmax.item() or got.max() == got.min(), "shortlist too short for the arg-max argument"
+
+
+def test_config2_values_full_size():
+    """C2: 6-D, EI, n = 512, 2^20 candidates - a regime where nearly every candidate's variance is far below the prior
+    variance (dense observations, long length scales), i.e. the SIMT engine carries the launch."""
+    d, n, M = 6, 512, 1 << 20
+    X, Y = _config_problem(d, n, seed=2)
+    raw = np.concatenate([[-8.0], [0.0], np.zeros(d)]).astype(np.float32)
+    P = ogp.GPParams(raw[0], raw[1], raw[2:])
+    dom = {f"x{i}": bayex.domain.Real(0.0, 1.0) for i in range(d)}
+    dims = engine.dims_array(dom)
+    post = engine.Posterior(X, Y, raw).build()
+    key = prng.key(1)
+    ystar = bayex.acq.ystar_for("EI", Y, np.ones(n))
+    vals, best = post.score_generated(key, dims, 0, M, "EI", 0.01, ystar)
+    f64, f32 = ogp.Factor(P, X, Y, np.ones(n), np.float64), ogp.Factor(P, X, Y, np.ones(n), np.float32)
+    _shortlist_argmax_check(vals, key, dims, post, f64, f32, "EI", Y, np.ones(n), n_top=512, n_rand=8192)
+    v, i = _lib.unpack(engine.to_unsigned(int(best.item())))
+    vmax, _ = torch.max(vals, dim=0)
+    assert np.float32(v) == vmax.item() and i == int((vals == vmax).nonzero()[0].item())
 
 
 def test_config2_sample_with_64_starts():
@@ -600,6 +830,54 @@ def test_config2_sample_with_64_starts():
     assert chosen_val >= best_random, "proposal must be at least as good as the best random candidate (Q12 contract)"
     assert np.all(info["opt_vals"] >= info["top_vals"] - 1e-5 * np.abs(info["top_vals"]) - 1e-7)
     assert all(0.0 <= new[k][0] <= 1.0 for k in dom)
+    # the same contract scored by the fp64 ORACLE at the fitted hypers: the chosen point's EI is at least the
+    # best random candidate's, and the CUDA values of the refined points are the oracle's
+    xs = opt.param_space.to_array({k: st.params[k] for k in dom})
+    f64 = ogp.Factor(ogp.GPParams(*st.gp_params), xs, st.ys, st.mask, np.float64)
+    f32 = ogp.Factor(ogp.GPParams(*st.gp_params), xs, st.ys, st.mask, np.float32)
+    pts = info["optimized"].astype(np.float64)
+    mu64, sd64 = f64.predict(pts)
+    mu32, sd32 = f32.predict(info["optimized"])
+    o_opt, tol = acq_tolerance("EI", mu64, sd64, mu32, sd32, st.ys, st.mask)
+    assert np.all(np.abs(info["opt_vals"] - o_opt) <= tol), np.abs(info["opt_vals"] - o_opt).max()
+    cand_best = engine.threefry_fill(bayex.random.key(1), opt._dims, d, int(np.argmax(info["acq_vals"])), 1).cpu().numpy()
+    o_rnd = oacq.acq_from_moments("EI", *f64.predict(cand_best.astype(np.float64)), st.ys.astype(np.float64), st.mask)[0]
+    assert o_opt.max() >= o_rnd * (1 - RTOL) - 1e-9, (o_opt.max(), o_rnd)
+    assert info["chosen"] < 64 and info["chosen"] == int(np.argmax(info["opt_vals"]))
+
+
+@pytest.mark.parametrize("acq,param", [("EI", 0.25), ("PI", 0.3), ("UCB", 1.7), ("LCB", 0.5)])
+def test_non_default_acq_param_reaches_the_kernels(acq, param):
+    """f3: Optimizer(..., acq_param=) and acq.<name>(..., xi= / kappa=) against the oracle with the same non-default value,
+    on both engines (n = 600, d = 4; 70 000 generated candidates on the production path, 3 000 explicit points on SIMT)."""
+    n, d = 600, 4
+    X, Y, raw, P = make_problem(n, d, seed=13)
+    dom = {f"x{i}": bayex.domain.Real(-0.2, 1.2) for i in range(d)}
+    opt = bayex.Optimizer(dom, acq=acq, maximize=True, acq_param=param)
+    assert opt.acq_param == param
+    gp_params = bayex.gp.GPParams(raw[0], raw[1], raw[2:])
+    st = bayex.optimizer.OptimizerState(params={f"x{i}": X[:, i].copy() for i in range(d)}, ys=Y, best_score=float(Y.max()),
+                                        best_params={}, mask=np.ones(n, bool), gp_params=gp_params)
+    key = bayex.random.key(9)
+    new, info = opt.sample(key, st, size=70_000, details=True)
+    cand = engine.threefry_fill(key, opt._dims, d, 0, 70_000).cpu().numpy()
+    f64, f32 = ogp.Factor(P, X, Y, np.ones(n), np.float64), ogp.Factor(P, X, Y, np.ones(n), np.float32)
+    mu64, sd64 = f64.predict(cand.astype(np.float64))
+    mu32, sd32 = f32.predict(cand)
+    kw = {"xi": param} if acq in ("EI", "PI") else {"kappa": param}
+    a64 = oacq.acq_from_moments(acq, mu64, sd64, Y.astype(np.float64), np.ones(n), param=param)
+    a32 = oacq.acq_from_moments(acq, mu32, sd32, Y, np.ones(n), param=param)
+    dflt = oacq.acq_from_moments(acq, mu64, sd64, Y.astype(np.float64), np.ones(n))
+    assert np.abs(a64 - dflt).max() > 100 * RTOL * np.abs(a64).mean(), "the non-default parameter must matter for this fixture"
+    tol = np.maximum(RTOL * np.maximum(np.abs(a64), np.abs(a64).mean()), 4 * np.abs(a32 - a64))
+    tsd = np.maximum(RTOL * sd64, 4 * np.abs(sd32.astype(np.float64) - sd64))
+    for ssd in (-1, 1):
+        tol = np.maximum(tol, 2 * np.abs(oacq.acq_from_moments(acq, mu64, np.maximum(sd64 + ssd * tsd, 1e-12), Y.astype(np.float64), np.ones(n), param=param) - a64))
+    assert np.all(np.abs(info["acq_vals"] - a64) <= tol), np.abs(info["acq_vals"] - a64).max()
+    fn = {"EI": bayex.acq.expected_improvement, "PI": bayex.acq.probability_improvement,
+          "UCB": bayex.acq.upper_confidence_bounds, "LCB": bayex.acq.lower_confidence_bounds}[acq]
+    got = fn(cand[:3000], X, Y, np.ones(n, bool), gp_params, **kw)
+    assert np.all(np.abs(got - a64[:3000]) <= tol[:3000])
 
 
 @pytest.mark.parametrize("n", [1024, 4096, 8192])
@@ -644,7 +922,7 @@ def test_config5_restart_sweep_single_rank():
         assert np.allclose(np.concatenate([np.ravel(v) for v in Pr]), table[r, 1:], rtol=0, atol=1e-6)
     want = float(ogp.neg_log_likelihood(ogp.GPParams(*[np.ravel(v) if i == 2 else float(np.ravel(v)[0]) for i, v in enumerate(best)]),
                                         X, Y, np.ones(n), dtype=np.float64))
-    assert abs(table[idx, 0] - want) <= 2e-4 * max(1.0, abs(want))
+    assert abs(table[idx, 0] - want) <= RTOL * max(1.0, abs(want))
 
 
 @pytest.mark.gpu
@@ -714,12 +992,12 @@ def test_more_than_32_dimensions_take_the_simt_engine():
     key = prng.key(2)
     v, b = post.score_generated(key, dims, 0, M, "UCB", 0.01, 0.0)  # AUTO
     cand = engine.threefry_fill(key, dims, d, 0, M).cpu().numpy()
-    f64 = ogp.Factor(P, X, Y, np.ones(n), np.float64)
+    f64, f32 = ogp.Factor(P, X, Y, np.ones(n), np.float64), ogp.Factor(P, X, Y, np.ones(n), np.float32)
     mu64, sd64 = f64.predict(cand.astype(np.float64))
-    want = mu64 + 0.01 * sd64
-    got = v.cpu().numpy().astype(np.float64)
-    assert np.all(np.abs(got - want) <= 2e-4 * np.maximum(np.abs(want), np.abs(want).mean()) + 1e-6)
-    for eng in (_lib.ENGINE_TCGEN05, _lib.ENGINE_TCGEN05_F16, _lib.ENGINE_TCGEN05_F16_PAIR):
+    mu32, sd32 = f32.predict(cand)
+    a64, tol = acq_tolerance("UCB", mu64, sd64, mu32, sd32, Y, np.ones(n))
+    assert np.all(np.abs(v.cpu().numpy().astype(np.float64) - a64) <= tol)
+    for eng in (_lib.ENGINE_TCGEN05_F16, _lib.ENGINE_TCGEN05_F16_RAW):
         with pytest.raises(RuntimeError, match="d <= 32"):
             post.score_generated(key, dims, 0, M, "UCB", 0.01, 0.0, engine=eng)
 
@@ -761,12 +1039,11 @@ def test_state_file_roundtrip_reproduces_the_proposal(tmp_path):
 
 
 @pytest.mark.gpu
-def test_large_explicit_point_sets_take_the_tcgen05_engine():
-    """gp.predict / acq.* on >= BX_POINTS_TC_MIN explicit points (rows a10, a13-a16) run on the production tensor-core engine
-    with the coordinates read from the caller's array.  Bars: the mean at the fp32 bar; the variance to 5e-5 of the
-    amplitude (tcgen05.mma accumulates in fp32 with truncation, one per MMA - scripts/dev/diag_umma_bias.py - which costs
-    ~1e-5 amp on a - sum v^2; the SIMT engine below the switch stays at the fp32 oracle's level); the acquisition through
-    the same propagated tolerance as every other engine test."""
+def test_large_explicit_point_sets_take_the_production_path():
+    """gp.predict / acq.* on >= BX_POINTS_TC_MIN explicit points (rows a10, a13-a16) run on the two-tier production path with
+    the coordinates read from the caller's array.  Same bars as the SIMT engine below the switch: mean and variance to 1e-4
+    relative or 4x the fp32 oracle's own error; the same point gives the same answer on either side of the switch whenever
+    the SIMT engine ends up scoring it (variance below half the prior variance)."""
     n, d, M = 700, 5, _lib.POINTS_TC_MIN + 777
     X, Y, raw, P = make_problem(n, d, seed=31)
     gp_params = bayex.gp.GPParams(raw[0], raw[1], raw[2:])
@@ -774,34 +1051,26 @@ def test_large_explicit_point_sets_take_the_tcgen05_engine():
     rng = np.random.default_rng(5)
     xt = rng.uniform(-0.1, 1.1, (M, d)).astype(np.float32)
     xt[:4] = X[:4] + 1e-3
-    mu, sd = bayex.gp.predict(gp_params, X, Y, mask, xt)                                    # tcgen05 engine
+    xt[4:2000] = rng.uniform(-3.0, 4.0, (1996, d)).astype(np.float32)  # far field: the tensor engine keeps these
+    mu, sd = bayex.gp.predict(gp_params, X, Y, mask, xt)                                    # production path
     k = _lib.POINTS_TC_MIN - 1
     mu_s, sd_s = bayex.gp.predict(gp_params, X, Y, mask, xt[:k])                             # SIMT engine
     assert mu.shape == sd.shape == (M,) and mu.dtype == np.float32 and np.all(np.isfinite(mu)) and np.all(np.isfinite(sd))
     f64, f32 = ogp.Factor(P, X, Y, np.ones(n), np.float64), ogp.Factor(P, X, Y, np.ones(n), np.float32)
-    mu64, sd64 = f64.predict(xt.astype(np.float64))
-    mu32, sd32 = f32.predict(xt)
+    mu64, sd64, var64 = f64.predict(xt.astype(np.float64), return_var=True)
+    mu32, sd32, var32 = f32.predict(xt, return_var=True)
+    floor = mean_sum_floor(f64, xt)
+    assert_close(mu, mu64, mu32, what="mean (production path)", floor=floor)
+    assert_close(mu_s, mu64[:k], mu32[:k], what="mean (SIMT)", floor=floor[:k])
+    assert_close(sd.astype(np.float64) ** 2, np.maximum(var64, 1e-10), np.maximum(var32, 1e-10), what="var (production path)")
+    assert_close(sd_s.astype(np.float64) ** 2, np.maximum(var64[:k], 1e-10), np.maximum(var32[:k], 1e-10), what="var (SIMT)")
     amp = float(np.logaddexp(np.float64(raw[1]), 0.0))
-    tmu = np.maximum(RTOL * np.maximum(np.abs(mu64), np.abs(mu64).mean()), 4 * np.abs(mu32 - mu64))
-    tmu = np.maximum(tmu, 2 * np.abs(mu32 - mu64).max())
-    assert np.all(np.abs(mu - mu64) <= tmu), np.abs(mu - mu64).max()
-    assert np.all(np.abs(mu_s - mu64[:k]) <= tmu[:k])
-    var_err = np.abs(sd.astype(np.float64) ** 2 - sd64 ** 2) / amp
-    var_err_s = np.abs(sd_s.astype(np.float64) ** 2 - sd64[:k] ** 2) / amp
-    var_err_32 = np.abs(sd32.astype(np.float64) ** 2 - sd64 ** 2) / amp
-    assert var_err.max() <= 5e-5, var_err.max()
-    assert var_err_s.max() <= max(1e-5, 4 * var_err_32.max()), (var_err_s.max(), var_err_32.max())
+    near = sd_s.astype(np.float64) ** 2 < 0.45 * amp
+    assert near.sum() > 1000 and (~near).sum() > 1000, (near.sum(), (~near).sum())
+    assert np.array_equal(sd[:k][near], sd_s[near]) and np.array_equal(mu[:k][near], mu_s[near]), \
+        "a point in the cancellation regime must get the same answer on either side of the BX_POINTS_TC_MIN switch"
     ei = bayex.acq.expected_improvement(xt, X, Y, mask, gp_params)
-    a64 = oacq.acq_from_moments("EI", mu64, sd64, Y.astype(np.float64), np.ones(n))
-    a32 = oacq.acq_from_moments("EI", mu32, sd32, Y, np.ones(n))
-    tsd = np.maximum(RTOL * sd64, 4 * np.abs(sd32.astype(np.float64) - sd64))
-    prop = np.zeros_like(a64)
-    for smu in (-1, 1):
-        for ssd in (-1, 1):
-            prop = np.maximum(prop, np.abs(oacq.acq_from_moments("EI", mu64 + smu * tmu, np.maximum(sd64 + ssd * tsd, 1e-12),
-                                                                 Y.astype(np.float64), np.ones(n)) - a64))
-    tol = np.maximum.reduce([RTOL * np.maximum(np.abs(a64), np.abs(a64).mean()), 4 * np.abs(a32 - a64), 2 * prop,
-                             np.full_like(a64, 2 * np.abs(a32 - a64).max())])
+    a64, tol = acq_tolerance("EI", mu64, sd64, mu32, sd32, Y, np.ones(n))
     assert ei.shape == (M,) and np.all(np.abs(ei - a64) <= tol), np.abs(ei - a64).max()
 
 
