@@ -3,8 +3,9 @@
 // The reference runs optax L-BFGS (unpinned dependency, mis-signed value_fn: SURVEY quirk Q12), so its trajectory is
 // not a parity target.  What is kept: the same place in sample(), unconstrained iterates clipped to +-1e6
 // (optimizer.py:68), scoring of the raw iterates (quirk Q11).  The iteration itself is a monotone ascent with
-// analytic gradients, batched over all starts: per round one K* build, two triangular GEMMs
-// (V = T K*, W = T^T V = K^-1 k) and one gradient/accept kernel; no host synchronisation anywhere.
+// analytic gradients, batched over all starts: per round one K* build, two skinny triangular products
+// (V = T K*, W = T^T V = K^-1 k; refine_blk_kernel + refine_partsum_kernel) and one gradient/accept kernel; no host
+// synchronisation anywhere.
 // The NumPy restatement is oracle/optimizer.py:refine_ascent.
 #include "internal.h"
 
@@ -13,29 +14,25 @@ namespace bx {
 constexpr float kLn2 = 0.6931471805599453f;
 
 struct RefineWs {
-  float *Kst, *V, *Vp, *Wp, *xt, *xb, *gb, *fb, *step;
-  int S64, ksplit, nsplit;  // the two skinny triangular products are split along K into nsplit chunks of ksplit
+  float *Kst, *V, *W, *P, *xt, *xb, *gb, *fb, *step;
+  int S16;  // starts rounded up to the group size of the skinny products
   size_t bytes;
 };
+constexpr int RG = 16;  // starts per group of the skinny triangular products
 static RefineWs carve_refine_ws(void* base, int np, int d, int S) {
   RefineWs w{};
-  w.S64 = round_up(S, 64);
-  // np/64 row tiles x 64 starts is too few CTAs and the last row tile carries the whole K range: split K into <= 8
-  // chunks (>= 128 long), partial products summed in a fixed order (deterministic: every rank must refine identically).
-  // CUPTI at n = 512 with one chunk: 20 us per product (8 CTAs, 32 k-steps each), 1.2 of the 2.8 ms of a C2 sample().
-  w.ksplit = max(128, round_up((np + 7) / 8, 64));  // (the products are computed transposed: [S64 x np] = starts x observations)
-  w.nsplit = (np + w.ksplit - 1) / w.ksplit;
+  w.S16 = round_up(S, RG);
   size_t off = 0;
   auto take = [&](size_t nfloat) {
     float* p = base ? reinterpret_cast<float*>(reinterpret_cast<char*>(base) + off) : nullptr;
     off += (nfloat * sizeof(float) + 255) / 256 * 256;
     return p;
   };
-  w.Kst = take((size_t)np * w.S64);
-  w.V = take((size_t)np * w.S64);
-  w.Vp = take((size_t)w.nsplit * np * w.S64);
-  w.Wp = take((size_t)w.nsplit * np * w.S64);
-  w.xt = take((size_t)w.S64 * d);
+  w.Kst = take((size_t)np * w.S16);
+  w.V = take((size_t)np * w.S16);
+  w.W = take((size_t)np * w.S16);
+  w.P = take((size_t)(np / 128) * np * w.S16);  // per-block partials of the triangular products
+  w.xt = take((size_t)w.S16 * d);
   w.xb = take((size_t)S * d);
   w.gb = take((size_t)S * d);
   w.fb = take(S);
@@ -44,12 +41,12 @@ static RefineWs carve_refine_ws(void* base, int np, int d, int S) {
   return w;
 }
 
-// Kst[s][j] = amp * exp(-|u_j - c_s|^2), START-major ([S64 x np]: every later kernel walks one start's row contiguously;
+// Kst[s][j] = amp * exp(-|u_j - c_s|^2), START-major ([S16 x np]: every later kernel walks one start's row contiguously;
 // the observation-major layout cost the update kernel a 32-byte sector per 4-byte read); zero for padded observations
 // and unused start slots.
-__global__ void __launch_bounds__(256) refine_kstar_kernel(bx_factor_t f, const float* __restrict__ xt, int S, int S64, float* Kst) {
+__global__ void __launch_bounds__(256) refine_kstar_kernel(bx_factor_t f, const float* __restrict__ xt, int S, int S16, float* Kst) {
   const int e = blockIdx.x * 256 + threadIdx.x;
-  if (e >= f.np * S64) return;
+  if (e >= f.np * S16) return;
   const int s = e / f.np, j = e % f.np;
   float v = 0.f;
   if (j < f.n && s < S) {
@@ -63,13 +60,90 @@ __global__ void __launch_bounds__(256) refine_kstar_kernel(bx_factor_t f, const 
   Kst[e] = v;
 }
 
-// V = sum of the K-chunk partials, in chunk order
-__global__ void __launch_bounds__(256) refine_reduce_kernel(const float* __restrict__ P, int nsplit, size_t stride, float* V) {
+// ---- the two triangular products of a round ----------------------------------------------------------------------------
+// V[s][i] = sum_{j <= i} T[i][j] K*[s][j]   and   W[s][j] = sum_{i >= j} T[i][j] V[s][i]   (W = T^T V = K^-1 k*) for up to
+// 50 starts (ceil(50 / N) per rank when the multi-start axis is sharded): skinny products, bound by the stream of T rather
+// than by the FMA pipe.  T is cut into 128 x 128 blocks; one CTA per lower block loads its block once (coalesced, from L2:
+// T stays resident across the 31 rounds), multiplies it with the 128-long slice of every group of RG = 16 starts and writes
+// the block's contribution to a partial buffer; refine_partsum_kernel adds the partials of a row (column) of blocks in
+// block order.  Nothing depends on how many starts ride along: a start's sums are formed in the same order whatever else
+// is in the batch, so sharding the starts cannot change a bit (test_refinement_contract), and every rank of a sharded
+// sample() refines exactly as one GPU would.
+constexpr int RBS = 128;         // block size
+constexpr int RLD = RBS + 1;     // padded row of the staged T block [k][out]: scalar accesses, conflict-free both ways
+
+__device__ __forceinline__ void lower_block(int b, int& I, int& J) {  // b-th block of the lower triangle, row-major
+  I = (int)((sqrtf(8.f * (float)b + 1.f) - 1.f) * 0.5f);
+  while ((I + 1) * (I + 2) / 2 <= b) ++I;
+  while (I * (I + 1) / 2 > b) --I;
+  J = b - I * (I + 1) / 2;
+}
+
+// TRANS = false: P[J][s][I rows] = T[I,J] In[s][J cols];   TRANS = true: P[I][s][J cols] = T[I,J]^T In[s][I rows]
+template <bool TRANS>
+__global__ void __launch_bounds__(256) refine_blk_kernel(const float* __restrict__ T, int np, const float* __restrict__ In, int S16,
+                                                         float* __restrict__ P) {
+  extern __shared__ float sm[];
+  float* Tb = sm;                  // [128 k][RLD out]
+  float* Ib = Tb + RBS * RLD;      // [128 k][RG]
+  float* Rb = Ib + RBS * RG;       // [2 k-halves][RG][128 out]
+  int I, J;
+  lower_block((int)blockIdx.x, I, J);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // stage the block k-major: k = column of T for V (out = row), k = row of T for W (out = column)
+  for (int e = tid; e < RBS * RBS; e += 256) {
+    const int r = e >> 7, c = e & 127;
+    const float v = T[(size_t)(I * RBS + r) * np + J * RBS + c];  // zero above the diagonal
+    if (TRANS) Tb[r * RLD + c] = v; else Tb[c * RLD + r] = v;
+  }
+  const int kblk = TRANS ? I : J, oblk = TRANS ? J : I, part = TRANS ? I : J;
+  const int q4 = (warp & 3) * 4, kh = warp >> 2;  // this warp: starts q4 .. q4 + 3 of the group, k half kh; lanes = out
+  for (int g = 0; g < S16 / RG; ++g) {
+    __syncthreads();  // Tb staged / the previous group's Ib and Rb consumed
+    for (int e = tid; e < RG * RBS; e += 256) {
+      const int sI = e >> 7, k = e & 127;
+      Ib[k * RG + sI] = In[(size_t)(g * RG + sI) * np + kblk * RBS + k];
+    }
+    __syncthreads();
+    float acc[4][4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
+#pragma unroll 4
+    for (int kk = 0; kk < RBS / 2; ++kk) {
+      const int k = kh * (RBS / 2) + kk;
+      const float4 in = *reinterpret_cast<const float4*>(&Ib[k * RG + q4]);  // warp-uniform address: one broadcast
+      const float iv[4] = {in.x, in.y, in.z, in.w};
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const float t = Tb[k * RLD + lane + 32 * r];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[r][c] = fmaf(t, iv[c], acc[r][c]);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) Rb[(kh * RG + q4 + c) * RBS + lane + 32 * r] = acc[r][c];
+    __syncthreads();
+    for (int e = tid; e < RG * RBS; e += 256) {  // the two k halves, in order
+      const int sI = e >> 7, o = e & 127;
+      P[((size_t)part * S16 + g * RG + sI) * np + oblk * RBS + o] = Rb[sI * RBS + o] + Rb[(RG + sI) * RBS + o];
+    }
+  }
+}
+
+// Out[s][x] = sum of the partials of x's block row (V: parts 0 .. I) or block column (W: parts J .. nb - 1), in part order
+template <bool TRANS>
+__global__ void __launch_bounds__(256) refine_partsum_kernel(const float* __restrict__ P, int np, int S16, float* __restrict__ Out) {
   const size_t e = (size_t)blockIdx.x * 256 + threadIdx.x;
-  if (e >= stride) return;
-  float acc = P[e];
-  for (int z = 1; z < nsplit; ++z) acc += P[(size_t)z * stride + e];
-  V[e] = acc;
+  if (e >= (size_t)S16 * np) return;
+  const int x = (int)(e % np), blk = x / RBS, nb = np / RBS;
+  const int p0 = TRANS ? blk : 0, p1 = TRANS ? nb : blk + 1;
+  float acc = 0.f;
+  for (int p = p0; p < p1; ++p) acc += P[(size_t)p * S16 * np + e];
+  Out[e] = acc;
 }
 
 // refine_update runs RU_T threads per start: 512 (4 j-iterations at n = 2048: the loops are global-latency bound) or, for
@@ -89,7 +163,7 @@ __device__ __forceinline__ float block_sum_128(float v, float* red) {
 // One block per start: value + gradient of the acquisition at the trial point, accept/reject, next trial point.
 template <int RU_T>
 __global__ void __launch_bounds__(RU_T) refine_update_kernel(bx_factor_t f, const float* __restrict__ Kst, const float* __restrict__ V,
-                                                            const float* __restrict__ Wp, int nsplit, int S64, int acq_id, float acq_param,
+                                                            const float* __restrict__ W, int acq_id, float acq_param,
                                                             float ystar, int first, float* xt, float* xb, float* gb,
                                                             float* fb, float* step) {
   extern __shared__ float sm[];
@@ -103,8 +177,7 @@ __global__ void __launch_bounds__(RU_T) refine_update_kernel(bx_factor_t f, cons
   float mu_p = 0.f, ss_p = 0.f;
   for (int j = tid; j < f.np; j += RU_T) {
     const float k = Kst[(size_t)s * f.np + j], v = V[(size_t)s * f.np + j];
-    float w = Wp[(size_t)s * f.np + j];  // W^T = V^T T: sum of the K-chunk partials, in chunk order
-    for (int z = 1; z < nsplit; ++z) w += Wp[((size_t)z * S64 + s) * f.np + j];
+    const float w = W[(size_t)s * f.np + j];  // (K^-1 k*)_j
     const float a = f.d_alpha[j] * k;
     ak[j] = a;
     wk[j] = w * k;
@@ -245,38 +318,33 @@ extern "C" int32_t bx_refine(const bx_factor_t* f, float* d_x, int32_t S, int32_
   BX_CHECK_ARG(usm <= 200 * 1024, BX_E_RANGE, "n=%d too large for the refinement kernel", f->n);
   cudaStream_t s = (cudaStream_t)stream;
   RefineWs w = carve_refine_ws(d_ws, f->np, f->d, S);
-  BX_CUDA(cudaMemsetAsync(w.xt, 0, sizeof(float) * (size_t)w.S64 * f->d, s));
+  BX_CUDA(cudaMemsetAsync(w.xt, 0, sizeof(float) * (size_t)w.S16 * f->d, s));
   BX_CUDA(cudaMemcpyAsync(w.xt, d_x, sizeof(float) * (size_t)S * f->d, cudaMemcpyDeviceToDevice, s));
   const bool wide = f->np > 256;
   BX_CUDA(cudaFuncSetAttribute(wide ? refine_update_kernel<512> : refine_update_kernel<128>,
                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)usm));
+  const int nb = f->np / RBS, nblk = nb * (nb + 1) / 2;
+  const size_t bsm = sizeof(float) * (RBS * RLD + RBS * RG + 2 * RG * RBS);
+  BX_CUDA(cudaFuncSetAttribute(refine_blk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsm));
+  BX_CUDA(cudaFuncSetAttribute(refine_blk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsm));
+  const unsigned gsum = (unsigned)(((size_t)w.S16 * f->np + 255) / 256);
   for (int r = 0; r <= rounds; ++r) {
-    refine_kstar_kernel<<<(f->np * w.S64 + 255) / 256, 256, 0, s>>>(*f, w.xt, S, w.S64, w.Kst);
+    refine_kstar_kernel<<<(f->np * w.S16 + 255) / 256, 256, 0, s>>>(*f, w.xt, S, w.S16, w.Kst);
     BX_LAUNCH_CHECK();
-    const size_t pstride = (size_t)f->np * w.S64;
-    GemmArgs g{};  // V^T [S64 x np] = Kst [S64 x np] * T^T   (T lower triangular: k <= i), K-chunk partials
-    g.A = w.Kst; g.lda = f->np; g.B = f->d_T; g.ldb = f->np; g.C = w.Vp; g.ldc = f->np;
-    g.M = w.S64; g.N = f->np; g.K = f->np; g.alpha = 1.f; g.beta = 0.f; g.kmode = KM_BT_LOWER;
-    g.ksplit = w.ksplit; g.csplit = pstride;
-    if (w.nsplit == 1) g.C = w.V;  // a single chunk is the product itself: no reduction launch
-    rc = gemm(s, false, true, g, w.nsplit);
-    if (rc) return rc;
-    if (w.nsplit > 1) {
-      refine_reduce_kernel<<<(unsigned)((pstride + 255) / 256), 256, 0, s>>>(w.Vp, w.nsplit, pstride, w.V);
-      BX_LAUNCH_CHECK();
-    }
-    GemmArgs h{};  // W^T [S64 x np] = V^T * T   (k >= j), K-chunk partials (summed by the update kernel)
-    h.A = w.V; h.lda = f->np; h.B = f->d_T; h.ldb = f->np; h.C = w.Wp; h.ldc = f->np;
-    h.M = w.S64; h.N = f->np; h.K = f->np; h.alpha = 1.f; h.beta = 0.f; h.kmode = KM_B_LOWER;
-    h.ksplit = w.ksplit; h.csplit = pstride;
-    rc = gemm(s, false, false, h, w.nsplit);
-    if (rc) return rc;
+    refine_blk_kernel<false><<<nblk, 256, bsm, s>>>(f->d_T, f->np, w.Kst, w.S16, w.P);  // V = T K*      (gp.py:68)
+    BX_LAUNCH_CHECK();
+    refine_partsum_kernel<false><<<gsum, 256, 0, s>>>(w.P, f->np, w.S16, w.V);
+    BX_LAUNCH_CHECK();
+    refine_blk_kernel<true><<<nblk, 256, bsm, s>>>(f->d_T, f->np, w.V, w.S16, w.P);     // W = T^T V = K^-1 k*
+    BX_LAUNCH_CHECK();
+    refine_partsum_kernel<true><<<gsum, 256, 0, s>>>(w.P, f->np, w.S16, w.W);
+    BX_LAUNCH_CHECK();
     if (wide)
-      refine_update_kernel<512><<<S, 512, usm, s>>>(*f, w.Kst, w.V, w.Wp, w.nsplit, w.S64, acq_id, acq_param, ystar, r == 0 ? 1 : 0,
-                                                    w.xt, w.xb, w.gb, w.fb, w.step);
+      refine_update_kernel<512><<<S, 512, usm, s>>>(*f, w.Kst, w.V, w.W, acq_id, acq_param, ystar, r == 0 ? 1 : 0, w.xt, w.xb, w.gb,
+                                                    w.fb, w.step);
     else
-      refine_update_kernel<128><<<S, 128, usm, s>>>(*f, w.Kst, w.V, w.Wp, w.nsplit, w.S64, acq_id, acq_param, ystar, r == 0 ? 1 : 0,
-                                                    w.xt, w.xb, w.gb, w.fb, w.step);
+      refine_update_kernel<128><<<S, 128, usm, s>>>(*f, w.Kst, w.V, w.W, acq_id, acq_param, ystar, r == 0 ? 1 : 0, w.xt, w.xb, w.gb,
+                                                    w.fb, w.step);
     BX_LAUNCH_CHECK();
   }
   BX_CUDA(cudaMemcpyAsync(d_x, w.xb, sizeof(float) * (size_t)S * f->d, cudaMemcpyDeviceToDevice, s));

@@ -57,8 +57,10 @@ __global__ void threefry_gather_kernel(const __grid_constant__ SamplerPack sp, c
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int CT = 64;   // candidates per block
 constexpr int RB = 64;   // T rows per accumulator tile
+constexpr int RP = 4;    // accumulator tiles (row blocks) per pass over the observations
 constexpr int KS = 16;   // observations per k-step
 constexpr int SP = CT + 4;
+constexpr int TSP = RP * RB + 4;
 
 
 // Persistent over 64-candidate tiles.  Two ways to name the candidates of a launch:
@@ -75,8 +77,8 @@ __global__ void __launch_bounds__(256) score_simt_kernel(const __grid_constant__
   const int d = a.f.d, d4 = a.f.d4, np = a.f.np, cs_ld = d4 + 1;
   float* cs = sm;                         // [CT][d4+1] scaled candidate coordinates
   float* us = cs + CT * cs_ld;            // [KS][d4]   scaled observation rows of the current k-step
-  float* Ts = us + KS * d4;               // [KS][SP]   T tile, k-major
-  float* Ks = Ts + KS * SP;               // [KS][SP]   K* tile, k-major
+  float* Ts = us + KS * d4;               // [KS][TSP]  T tiles of the pass, k-major
+  float* Ks = Ts + KS * TSP;              // [KS][SP]   K* tile, k-major
   float* red = Ks + KS * SP;              // [4][CT]    mean partials, then sum v^2
   const int tid = threadIdx.x;
   const uint64_t total = a.flag_list ? (uint64_t)*a.flag_count : a.m_count;
@@ -104,25 +106,32 @@ __global__ void __launch_bounds__(256) score_simt_kernel(const __grid_constant__
   }
   __syncthreads();
 
-  const int rg = tid & 15, cg = tid >> 4;    // accumulator mapping: rows 4rg.., candidates 4cg..
+  const int rg = tid & 15, cg = tid >> 4;    // accumulator mapping: rows 4rg.. of every row block, candidates 4cg..
   const int gc = tid & 63, gk = tid >> 6;    // generation mapping: candidate gc, observations gk + 4q
   float ss[4] = {0.f, 0.f, 0.f, 0.f};
   float mpart = 0.f;
   const int nI = np / RB;
-  for (int I = 0; I < nI; ++I) {
-    const bool last = (I == nI - 1);
-    float acc[4][4];
+  // RP row blocks (256 rows of T) ride on every generated K* tile: K* is regenerated once per pass, not once per row block
+  for (int I0 = 0; I0 < nI; I0 += RP) {
+    const int nr = min(RP, nI - I0);
+    const bool last = (I0 + RP >= nI);
+    float acc[RP][4][4];
 #pragma unroll
-    for (int r = 0; r < 4; ++r)
+    for (int p = 0; p < RP; ++p)
 #pragma unroll
-      for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
-    const int ksteps = (I + 1) * (RB / KS);
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[p][r][c] = 0.f;
+    const int ksteps = (I0 + nr) * (RB / KS);
     for (int ks = 0; ks < ksteps; ++ks) {
       const int k0 = ks * KS;
-      {  // T tile: rows I*64.., cols k0..k0+15 -> Ts[k][row]
-        const int r = tid >> 2, kk = (tid & 3) * 4;
-        const float4 v = *reinterpret_cast<const float4*>(a.f.d_T + (size_t)(I * RB + r) * np + k0 + kk);
-        Ts[(kk + 0) * SP + r] = v.x; Ts[(kk + 1) * SP + r] = v.y; Ts[(kk + 2) * SP + r] = v.z; Ts[(kk + 3) * SP + r] = v.w;
+      const int p_lo = max(0, k0 / RB - I0);  // row blocks entirely above the diagonal at this k-step are skipped
+      for (int e = tid; e < nr * RB * (KS / 4); e += 256) {  // T tiles: rows (I0 + p) * 64.., cols k0..k0+15 -> Ts[k][p * 64 + row]
+        const int r = e >> 2, kk = (e & 3) * 4;
+        if (r >= p_lo * RB) {
+          const float4 v = *reinterpret_cast<const float4*>(a.f.d_T + (size_t)(I0 * RB + r) * np + k0 + kk);
+          Ts[(kk + 0) * TSP + r] = v.x; Ts[(kk + 1) * TSP + r] = v.y; Ts[(kk + 2) * TSP + r] = v.z; Ts[(kk + 3) * TSP + r] = v.w;
+        }
       }
       for (int e = tid; e < KS * d4; e += 256) us[e] = a.f.d_U[(size_t)k0 * d4 + e];
       __syncthreads();
@@ -141,26 +150,37 @@ __global__ void __launch_bounds__(256) score_simt_kernel(const __grid_constant__
       __syncthreads();
 #pragma unroll
       for (int kk = 0; kk < KS; ++kk) {
-        const float4 tv = *reinterpret_cast<const float4*>(&Ts[kk * SP + rg * 4]);
         const float4 kv = *reinterpret_cast<const float4*>(&Ks[kk * SP + cg * 4]);
-        const float av[4] = {tv.x, tv.y, tv.z, tv.w}, bv[4] = {kv.x, kv.y, kv.z, kv.w};
+        const float bv[4] = {kv.x, kv.y, kv.z, kv.w};
 #pragma unroll
-        for (int r = 0; r < 4; ++r)
+        for (int p = 0; p < RP; ++p) {
+          if (p >= p_lo && p < nr) {
+            const float4 tv = *reinterpret_cast<const float4*>(&Ts[kk * TSP + p * RB + rg * 4]);
+            const float av[4] = {tv.x, tv.y, tv.z, tv.w};
 #pragma unroll
-          for (int c = 0; c < 4; ++c) acc[r][c] = fmaf(av[r], bv[c], acc[r][c]);
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+              for (int c = 0; c < 4; ++c) acc[p][r][c] = fmaf(av[r], bv[c], acc[p][r][c]);
+          }
+        }
       }
       __syncthreads();
     }
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {  // column sums of V^2 over this row block, reduced across the 16 row groups
-      float v = 0.f;
+    for (int p = 0; p < RP; ++p) {
+      if (p < nr) {
 #pragma unroll
-      for (int r = 0; r < 4; ++r) v = fmaf(acc[r][c], acc[r][c], v);
-      v += __shfl_xor_sync(0xffffffffu, v, 1);
-      v += __shfl_xor_sync(0xffffffffu, v, 2);
-      v += __shfl_xor_sync(0xffffffffu, v, 4);
-      v += __shfl_xor_sync(0xffffffffu, v, 8);
-      ss[c] += v;
+        for (int c = 0; c < 4; ++c) {  // column sums of V^2 over this row block, reduced across the 16 row groups
+          float v = 0.f;
+#pragma unroll
+          for (int r = 0; r < 4; ++r) v = fmaf(acc[p][r][c], acc[p][r][c], v);
+          v += __shfl_xor_sync(0xffffffffu, v, 1);
+          v += __shfl_xor_sync(0xffffffffu, v, 2);
+          v += __shfl_xor_sync(0xffffffffu, v, 4);
+          v += __shfl_xor_sync(0xffffffffu, v, 8);
+          ss[c] += v;
+        }
+      }
     }
   }
   red[gk * CT + gc] = mpart;
@@ -195,7 +215,7 @@ __global__ void __launch_bounds__(256) score_simt_kernel(const __grid_constant__
   }
 }
 
-static size_t score_simt_smem(int d4) { return sizeof(float) * (CT * (d4 + 1) + KS * d4 + 2 * KS * SP + 4 * CT); }
+static size_t score_simt_smem(int d4) { return sizeof(float) * (CT * (d4 + 1) + KS * d4 + KS * TSP + KS * SP + 4 * CT); }
 
 int32_t check_factor(const bx_factor_t* f) {
   BX_CHECK_ARG(f, BX_E_ARG, "null factor");
@@ -206,7 +226,7 @@ int32_t check_factor(const bx_factor_t* f) {
 }
 
 // CTAs the SIMT engine launches for up to `m_count` candidates: persistent, at most SIMT_CTAS_PER_SM per SM
-constexpr int SIMT_CTAS_PER_SM = 3;
+constexpr int SIMT_CTAS_PER_SM = 2;
 unsigned score_simt_grid(uint64_t m_count, int sms) {
   const uint64_t ntiles = (m_count + CT - 1) / CT, cap = (uint64_t)sms * SIMT_CTAS_PER_SM;
   return (unsigned)(ntiles < cap ? (ntiles ? ntiles : 1) : cap);
