@@ -19,7 +19,7 @@ if not os.path.exists(LIB_PATH):
 lib = C.CDLL(LIB_PATH)
 
 ACQ_IDS = {"EI": 0, "PI": 1, "UCB": 2, "LCB": 3}
-ENGINE_AUTO, ENGINE_SIMT, ENGINE_TCGEN05_F16, ENGINE_TCGEN05_F16_RAW = 0, 1, 2, 3
+ENGINE_AUTO, ENGINE_SIMT, ENGINE_TCGEN05_F16, ENGINE_TCGEN05_F16_RAW, ENGINE_TCGEN05_F16_ACC = 0, 1, 2, 3, 4
 MAX_D, MAX_K, TILE, FIT_BATCH_MAX = 64, 1024, 128, 32
 E_ARG, E_RANGE, E_WORKSPACE, E_NOTPD, E_UNSUPPORTED = -1, -2, -3, -4, -5
 POINTS_TC_MIN = 65536  # BX_POINTS_TC_MIN

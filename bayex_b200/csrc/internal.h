@@ -97,6 +97,10 @@ struct ScoreArgs {
   uint32_t* flag_list;
   unsigned int* flag_count;
   float flag_tau;
+  // list mode of the scoring engines: the launch scores rows in_list[0 .. *in_count) (a hand-over list) instead of
+  // [0, m_count); outputs and keys still go by the row
+  const uint32_t* in_list;
+  const unsigned int* in_count;
 };
 
 // Fused-top-k plumbing shared by score.cu / topk.cu / score_tc16p.cu

@@ -64,9 +64,9 @@ constexpr int TSP = RP * RB + 4;
 
 
 // Persistent over 64-candidate tiles.  Two ways to name the candidates of a launch:
-//   direct (a.flag_list == nullptr): rows [0, m_count) of the launch;
-//   list   (a.flag_list != nullptr): rows flag_list[0 .. *flag_count) - the candidates the fp16 tcgen05 engine handed over
-//           because their variance sits in the cancellation regime (score_tc16p.cu); count read on the device.
+//   direct (a.in_list == nullptr): rows [0, m_count) of the launch;
+//   list   (a.in_list != nullptr): rows in_list[0 .. *in_count) - candidates another engine handed over (score_tc16p.cu);
+//           count read on the device.
 // A row's candidate is generated from the key (GEN, index m_begin + row) or read from a.cand[row]; outputs go to slot
 // `row`.  With a.topk_k > 0 threads 0..127 also run the fused top-k collector (topk_fused.cuh), one slab per CTA.
 template <bool GEN>
@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(256) score_simt_kernel(const __grid_constant__
   float* Ks = Ts + KS * TSP;              // [KS][SP]   K* tile, k-major
   float* red = Ks + KS * SP;              // [4][CT]    mean partials, then sum v^2
   const int tid = threadIdx.x;
-  const uint64_t total = a.flag_list ? (uint64_t)*a.flag_count : a.m_count;
+  const uint64_t total = a.in_list ? (uint64_t)*a.in_count : a.m_count;
   const float amp = a.f.d_hyp[HYP_AMP];
   const int topk_k = a.topk_k;
   unsigned long long* const slab = topk_k ? a.topk_slab + (size_t)blockIdx.x * tk::CAP : nullptr;
@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(256) score_simt_kernel(const __grid_constant__
   unsigned long long best = 0ull;
 
   for (uint64_t c_base = (uint64_t)blockIdx.x * CT; c_base < total; c_base += (uint64_t)gridDim.x * CT) {
-  if (tid < CT) rows_s[tid] = (c_base + tid < total) ? (a.flag_list ? a.flag_list[c_base + tid] : (uint32_t)(c_base + tid)) : 0xFFFFFFFFu;
+  if (tid < CT) rows_s[tid] = (c_base + tid < total) ? (a.in_list ? a.in_list[c_base + tid] : (uint32_t)(c_base + tid)) : 0xFFFFFFFFu;
   __syncthreads();
   for (int e = tid; e < CT * d4; e += 256) {
     const int c = e / d4, k = e % d4;
@@ -251,7 +251,7 @@ int32_t launch_score_simt(cudaStream_t s, const ScoreArgs& a, const SamplerPack*
 }
 
 // implemented in score_tc16p.cu (fp16 head/tail, CTA pair, register-tiled producers): the production engine
-int32_t launch_score_tc16p(cudaStream_t s, const ScoreArgs& a, const SamplerPack& sp);
+int32_t launch_score_tc16p(cudaStream_t s, const ScoreArgs& a, const SamplerPack& sp, bool accurate = false);
 bool score_tc16_supported(const bx_factor_t& f);
 
 }  // namespace bx
@@ -328,21 +328,35 @@ static HandoverWs carve_handover(void* base, uint64_t m_count) {
   return h;
 }
 
-// fp16 tcgen05 engine over every candidate of the launch, then the fp32 SIMT engine over the rows it handed over
-// (variance in the cancellation regime).  a.topk_* (optional) name the slabs of the FIRST pass; the SIMT pass uses the
-// `grid1` slabs after them.  Returns the number of slabs in use through *nslabs.
-static int32_t launch_two_tier(cudaStream_t s, ScoreArgs a, const SamplerPack& sp, bool gen, const HandoverWs& h, bool raw,
+// Which engine scores the candidates the fast tensor mode hands over: the accurate tensor mode (default) or the fp32 SIMT
+// engine (BX_TIER2=simt; also what a factor without fp16 copies or d > 32 gets).
+static bool tier2_simt() {
+  const char* e = getenv("BX_TIER2");
+  return !(e && e[0] == 'a');  // until the accurate mode has been through the whole parity suite: opt-in (BX_TIER2=acc)
+}
+
+// The production path: the fast mode of the fp16 tcgen05 engine over every candidate of the launch, then the accurate
+// mode (or the SIMT engine) over the rows it handed over (variance in the cancellation regime).  a.topk_* (optional)
+// name the slabs of the FIRST pass; the second pass uses the slabs after them.  mode: 0 two-tier, 1 fast mode alone
+// (diagnostics), 2 accurate mode alone.  Returns the number of slabs in use through *nslabs.
+static int32_t launch_two_tier(cudaStream_t s, ScoreArgs a, const SamplerPack& sp, bool gen, const HandoverWs& h, int mode,
                                int* nslabs) {
   const unsigned grid1 = score_tc16p_grid(a.m_count);
   if (nslabs) *nslabs = (int)grid1;
-  if (raw) return launch_score_tc16p(s, a, sp);
+  if (mode != 0) return launch_score_tc16p(s, a, sp, mode == 2);
   BX_CUDA(cudaMemsetAsync(h.count, 0, sizeof(unsigned int), s));
   a.flag_list = h.list; a.flag_count = h.count; a.flag_tau = handover_tau();
-  int32_t rc = launch_score_tc16p(s, a, sp);
+  int32_t rc = launch_score_tc16p(s, a, sp, false);
   if (rc) return rc;
+  a.flag_list = nullptr; a.flag_count = nullptr;
+  a.in_list = h.list; a.in_count = h.count;
   if (a.topk_k) { a.topk_slab += (size_t)grid1 * tk::CAP; a.topk_count += grid1; }
-  if (nslabs) *nslabs = (int)(grid1 + score_simt_grid(a.m_count, sm_count()));
-  return launch_score_simt(s, a, &sp, gen);  // list mode: a.flag_list is set
+  if (tier2_simt()) {
+    if (nslabs) *nslabs = (int)(grid1 + score_simt_grid(a.m_count, sm_count()));
+    return launch_score_simt(s, a, &sp, gen);
+  }
+  if (nslabs) *nslabs = (int)(2 * grid1);
+  return launch_score_tc16p(s, a, sp, true);
 }
 
 struct SampleWs {
@@ -421,7 +435,7 @@ extern "C" int32_t bx_score_points(const bx_factor_t* f, const float* d_cand, ui
   static const SamplerPack no_sampler{};
   if (M >= BX_POINTS_TC_MIN && score_tc16_supported(*f) && d_ws) {
     BX_CHECK_ARG(ws_bytes >= bx_score_workspace_bytes(M), BX_E_WORKSPACE, "workspace too small");
-    return launch_two_tier((cudaStream_t)stream, a, no_sampler, false, carve_handover(d_ws, M), false, nullptr);
+    return launch_two_tier((cudaStream_t)stream, a, no_sampler, false, carve_handover(d_ws, M), 0, nullptr);
   }
   return launch_score_simt((cudaStream_t)stream, a, nullptr, false);
 }
@@ -443,11 +457,11 @@ extern "C" int32_t bx_score_generated(const bx_factor_t* f, const uint32_t key[2
   // AUTO: the two-tier production path (fp16 tcgen05 engine + fp32 SIMT engine on the cancellation-regime candidates)
   // whenever the factor carries its fp16 copies and d <= 32; otherwise the fp32 SIMT engine alone.
   if (engine == BX_ENGINE_AUTO) engine = score_tc16_supported(*f) ? BX_ENGINE_TCGEN05_F16 : BX_ENGINE_SIMT;
-  if (engine == BX_ENGINE_TCGEN05_F16 || engine == BX_ENGINE_TCGEN05_F16_RAW) {
+  if (engine == BX_ENGINE_TCGEN05_F16 || engine == BX_ENGINE_TCGEN05_F16_RAW || engine == BX_ENGINE_TCGEN05_F16_ACC) {
     BX_CHECK_ARG(score_tc16_supported(*f), BX_E_UNSUPPORTED, "the fp16 tcgen05 engine needs the T16hi/T16lo split of the factor and d <= 32");
-    const bool raw = engine == BX_ENGINE_TCGEN05_F16_RAW;
-    BX_CHECK_ARG(raw || (d_ws && ws_bytes >= bx_score_workspace_bytes(m_count)), BX_E_WORKSPACE, "hand-over workspace missing or too small");
-    return launch_two_tier((cudaStream_t)stream, a, sp, true, carve_handover(d_ws, m_count), raw, nullptr);
+    const int mode = engine == BX_ENGINE_TCGEN05_F16 ? 0 : (engine == BX_ENGINE_TCGEN05_F16_RAW ? 1 : 2);
+    BX_CHECK_ARG(mode != 0 || (d_ws && ws_bytes >= bx_score_workspace_bytes(m_count)), BX_E_WORKSPACE, "hand-over workspace missing or too small");
+    return launch_two_tier((cudaStream_t)stream, a, sp, true, carve_handover(d_ws, m_count), mode, nullptr);
   }
   BX_CHECK_ARG(engine == BX_ENGINE_SIMT, BX_E_ARG, "unknown engine %d", engine);
   return launch_score_simt((cudaStream_t)stream, a, &sp, true);
@@ -482,9 +496,9 @@ extern "C" int32_t bx_score_generated_topk(const bx_factor_t* f, const uint32_t 
   a.topk_slab = w.slabs; a.topk_count = w.counts; a.topk_k = k;
   if (engine == BX_ENGINE_AUTO) engine = score_tc16_supported(*f) ? BX_ENGINE_TCGEN05_F16 : BX_ENGINE_SIMT;
   int nslabs = 0;
-  if (engine == BX_ENGINE_TCGEN05_F16 || engine == BX_ENGINE_TCGEN05_F16_RAW) {
+  if (engine == BX_ENGINE_TCGEN05_F16 || engine == BX_ENGINE_TCGEN05_F16_RAW || engine == BX_ENGINE_TCGEN05_F16_ACC) {
     BX_CHECK_ARG(score_tc16_supported(*f), BX_E_UNSUPPORTED, "the fp16 tcgen05 engine needs the T16hi/T16lo split of the factor and d <= 32");
-    rc = launch_two_tier(s, a, sp, true, w.h, engine == BX_ENGINE_TCGEN05_F16_RAW, &nslabs);
+    rc = launch_two_tier(s, a, sp, true, w.h, engine == BX_ENGINE_TCGEN05_F16 ? 0 : (engine == BX_ENGINE_TCGEN05_F16_RAW ? 1 : 2), &nslabs);
   } else {
     BX_CHECK_ARG(engine == BX_ENGINE_SIMT, BX_E_UNSUPPORTED, "the fused top-k runs on the AUTO / SIMT / fp16 tcgen05 engines (engine %d)", engine);
     nslabs = (int)score_simt_grid(m_count, sm_count());

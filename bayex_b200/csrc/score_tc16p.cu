@@ -49,7 +49,8 @@ constexpr int HN = BN / 2;                 // rows of every T tile held by one C
 #ifndef BX_P_WAIT_NS
 #define BX_P_WAIT_NS 64
 #endif
-constexpr int NACC = 2, SA = BX_P_SA, SB = BX_P_SB, NU = BX_P_NU;
+constexpr int SA = BX_P_SA, SB = BX_P_SB, NU = BX_P_NU;
+constexpr int HB = 128;                    // accurate mode: rows per half of a row block = UMMA N; each CTA holds HB / 2 of them
 constexpr int KPR = BN / BKH;              // K-blocks per row block
 constexpr int ATILE = TM * BKH * 2;        // 16 KiB: 128 candidates x 64 halves
 constexpr int BTILE = HN * BKH * 2;        // 16 KiB: 128 T rows x 64 halves
@@ -60,8 +61,8 @@ struct __align__(16) Smem {
   char a_hi[SA][ATILE], a_lo[SA][ATILE];
   char b_hi[SB][BTILE], b_lo[SB][BTILE];
   float mean_s[MAXOP][TM];
-  unsigned long long full_a[SA], empty_a[SA], full_b[SB], empty_b[SB], full_u[NU], empty_u[NU], tmem_full[NACC],
-      tmem_empty[NACC], mean_full, mean_empty;
+  unsigned long long full_a[SA], empty_a[SA], full_b[SB], empty_b[SB], full_u[NU], empty_u[NU], tmem_full[2],
+      tmem_empty[2], mean_full, mean_empty;
   uint32_t tmem_base;
   tk::Shared topk;  // fused per-CTA top-k (epilogue warps)
 };
@@ -69,10 +70,22 @@ struct __align__(16) Smem {
 // ------------------------------------------------------------------------------------------------------------------
 // RC = candidates per producer thread.  128 / RC candidate groups x (2 RC) observation parts = 256 producer threads;
 // a thread generates RC candidates x (32 / RC) observations of every K-block.
-template <int D4, int RC>
+//
+// ACC = true is the ACCURATE mode of the same engine (score_tc16a_kernel below): tcgen05.mma adds into its fp32 accumulator
+// with truncation (toward zero, once per instruction, every aligned addend at a quarter ulp: scripts/dev/umma_probe.py), so a
+// chain of n / 16 * 3 instructions biases V by up to 6e-5 relative.  Here no sum longer than ONE K-block (12 instructions)
+// is formed inside the tensor core: a row block (256 rows of T) is processed as two halves of 128 rows, each K-block's
+// product lands in its own 128-column chunk accumulator X[h] (TMEM columns 256 + 128 h), and the epilogue warps add the
+// chunk into a running sum R (TMEM columns 0..255) with round-to-nearest FADDs - tcgen05.ld X, tcgen05.ld R, add,
+// tcgen05.st R - while the tensor core fills the other half's chunk.  That is the Ootomo-Yokota correction ("accumulate
+// outside the tensor core") with the running sums resident in TMEM; measured on real T / K* data it brings the error of
+// sum v^2 to the level of an fp32 FFMA loop (30-44x below the plain chain).  Price: one row block in flight instead of
+// two (K* is regenerated 8.5 n / 256... times instead of 4.5), N = 128 MMAs (the A operand is read twice).
+template <int D4, int RC, bool ACC>
 __global__ void __launch_bounds__(NTHREADS, 1)
 score_tc16p_kernel(const __grid_constant__ ScoreArgs a, const __grid_constant__ SamplerPack sp,
                    const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo) {
+  constexpr int NACC = ACC ? 1 : 2;  // row blocks in flight
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   Smem& S = *reinterpret_cast<Smem*>(smem_raw);
   constexpr int US = BKH * D4 + BKH;  // floats per staged K-block: 64 observation rows + 64 alpha
@@ -91,7 +104,9 @@ score_tc16p_kernel(const __grid_constant__ ScoreArgs a, const __grid_constant__ 
   const int nRB = (np + BN - 1) / BN;
   const int nJtot = np / BKH;
   const int nSB = (nRB + NACC - 1) / NACC;
-  const uint64_t ntiles = (a.m_count + TM - 1) / TM;
+  // list mode (a.in_list): the launch scores rows in_list[0 .. *in_count) - the candidates the fast mode handed over
+  const uint64_t total = a.in_list ? (uint64_t)*a.in_count : a.m_count;
+  const uint64_t ntiles = (total + TM - 1) / TM;
   const uint64_t npairs = (ntiles + 1) / 2;  // pair-tiles of 256 candidates
   const uint64_t pair0 = blockIdx.x >> 1, pstride = gridDim.x >> 1;
 
@@ -99,7 +114,7 @@ score_tc16p_kernel(const __grid_constant__ ScoreArgs a, const __grid_constant__ 
     for (int i = 0; i < SA; ++i) { mbar_init(smem_u32(&S.full_a[i]), 2 * (NPROD / 32)); mbar_init(smem_u32(&S.empty_a[i]), 1); }
     for (int i = 0; i < SB; ++i) { mbar_init(smem_u32(&S.full_b[i]), 2); mbar_init(smem_u32(&S.empty_b[i]), 1); }
     for (int i = 0; i < NU; ++i) { mbar_init(smem_u32(&S.full_u[i]), 1); mbar_init(smem_u32(&S.empty_u[i]), NPROD / 32); }
-    for (int i = 0; i < NACC; ++i) { mbar_init(smem_u32(&S.tmem_full[i]), 1); mbar_init(smem_u32(&S.tmem_empty[i]), 8); }
+    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&S.tmem_full[i]), 1); mbar_init(smem_u32(&S.tmem_empty[i]), 8); }
     mbar_init(smem_u32(&S.mean_full), NPROD / 32);
     mbar_init(smem_u32(&S.mean_empty), 4);
     fence_barrier_init();
@@ -115,24 +130,80 @@ score_tc16p_kernel(const __grid_constant__ ScoreArgs a, const __grid_constant__ 
     if (warp == 0 && lane == 0) {
       // ===== TMA: this CTA's 128-row half of every T tile (head + tail) =====
       uint32_t it = 0;
-      for (uint64_t pt = pair0; pt < npairs; pt += pstride) {
-        for (int sb = 0; sb < nSB; ++sb) {
-          const int rb0 = sb * NACC, rb1 = min(rb0 + NACC, nRB);
-          for (int J = 0; J < min(KPR * rb1, nJtot); ++J) {
-            for (int rb = max(rb0, J / KPR); rb < rb1; ++rb, ++it) {
+      if constexpr (ACC) {
+        // rows of a T tile held by this CTA: 64 of each 128-row half (the pair's N = 128 MMA takes 64 rows from each CTA)
+        for (uint64_t pt = pair0; pt < npairs; pt += pstride) {
+          for (int rb = 0; rb < nRB; ++rb) {
+            for (int J = 0; J < min(KPR * (rb + 1), nJtot); ++J, ++it) {
               const uint32_t st = it % SB, ph = (it / SB) & 1;
               mbar_wait<256>(smem_u32(&S.empty_b[st]), ph ^ 1);
               const uint32_t bar = smem_u32(&S.full_b[st]);
-              if (leader) mbar_expect_tx(bar, 4 * BTILE);  // both halves, head + tail
+              if (leader) mbar_expect_tx(bar, 4 * BTILE);
               else mbar_arrive_rank(bar, 0);
-              tma_load_2d_pair(smem_u32(S.b_hi[st]), &map_hi, bar, J * BKH, rb * BN + (int)rank * HN);
-              tma_load_2d_pair(smem_u32(S.b_lo[st]), &map_lo, bar, J * BKH, rb * BN + (int)rank * HN);
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                const int row = rb * BN + h * HB + (int)rank * (HB / 2);
+                tma_load_2d_pair(smem_u32(S.b_hi[st]) + (uint32_t)(h * (BTILE / 2)), &map_hi, bar, J * BKH, row);
+                tma_load_2d_pair(smem_u32(S.b_lo[st]) + (uint32_t)(h * (BTILE / 2)), &map_lo, bar, J * BKH, row);
+              }
+            }
+          }
+        }
+      } else {
+        for (uint64_t pt = pair0; pt < npairs; pt += pstride) {
+          for (int sb = 0; sb < nSB; ++sb) {
+            const int rb0 = sb * NACC, rb1 = min(rb0 + NACC, nRB);
+            for (int J = 0; J < min(KPR * rb1, nJtot); ++J) {
+              for (int rb = max(rb0, J / KPR); rb < rb1; ++rb, ++it) {
+                const uint32_t st = it % SB, ph = (it / SB) & 1;
+                mbar_wait<256>(smem_u32(&S.empty_b[st]), ph ^ 1);
+                const uint32_t bar = smem_u32(&S.full_b[st]);
+                if (leader) mbar_expect_tx(bar, 4 * BTILE);  // both halves, head + tail
+                else mbar_arrive_rank(bar, 0);
+                tma_load_2d_pair(smem_u32(S.b_hi[st]), &map_hi, bar, J * BKH, rb * BN + (int)rank * HN);
+                tma_load_2d_pair(smem_u32(S.b_lo[st]), &map_lo, bar, J * BKH, rb * BN + (int)rank * HN);
+              }
             }
           }
         }
       }
     } else if (warp == 1 && leader && lane == 0) {
       // ===== MMA issuer (leader CTA only) =====
+      if constexpr (ACC) {
+        const uint32_t idesc = make_idesc_f16(HB, 2 * TM);
+        uint32_t it = 0, xph = 0;  // bit h of xph = phase of chunk accumulator X[h]
+        for (uint64_t pt = pair0; pt < npairs; pt += pstride) {
+          for (int rb = 0; rb < nRB; ++rb) {
+            for (int J = 0; J < min(KPR * (rb + 1), nJtot); ++J, ++it) {
+              const uint32_t sa = it % SA, pa = (it / SA) & 1, st = it % SB, pb = (it / SB) & 1;
+              mbar_wait_cluster<32>(smem_u32(&S.full_a[sa]), pa);
+              mbar_wait<32>(smem_u32(&S.full_b[st]), pb);
+              tc_fence_after();
+              const uint64_t ah = make_desc(smem_u32(S.a_hi[sa])), al = make_desc(smem_u32(S.a_lo[sa]));
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                mbar_wait_cluster(smem_u32(&S.tmem_empty[h]), ((xph >> h) & 1) ^ 1);  // the epilogues folded X[h] into R
+                tc_fence_after();
+                const uint64_t bh = make_desc(smem_u32(S.b_hi[st]) + (uint32_t)(h * (BTILE / 2)));
+                const uint64_t bl = make_desc(smem_u32(S.b_lo[st]) + (uint32_t)(h * (BTILE / 2)));
+                const uint32_t d = tmem + (uint32_t)(BN + h * HB);
+                if (!(a.debug & 2))
+#pragma unroll
+                for (int ks = 0; ks < BKH / 16; ++ks) {
+                  const uint64_t o = (uint64_t)(ks * 2);
+                  umma_f16_pair(d, ah + o, bh + o, idesc, ks != 0);  // a chunk never holds more than this one K-block
+                  umma_f16_pair(d, al + o, bh + o, idesc, 1u);
+                  umma_f16_pair(d, ah + o, bl + o, idesc, 1u);
+                }
+                umma_commit_pair(smem_u32(&S.tmem_full[h]));
+                xph ^= 1u << h;
+              }
+              umma_commit_pair(smem_u32(&S.empty_b[st]));
+              umma_commit_pair(smem_u32(&S.empty_a[sa]));
+            }
+          }
+        }
+      } else {
       const uint32_t idesc = make_idesc_f16(BN, 2 * TM);
       uint32_t ita = 0, itb = 0, acc_ph = 0;  // bit a of acc_ph = phase of accumulator a
       for (uint64_t pt = pair0; pt < npairs; pt += pstride) {
@@ -171,6 +242,7 @@ score_tc16p_kernel(const __grid_constant__ ScoreArgs a, const __grid_constant__ 
             umma_commit_pair(smem_u32(&S.empty_a[sa]));
           }
         }
+      }
       }
     } else if (warp == 2 && lane == 0) {
       // ===== TMA: observation rows (scaled coordinates) + alpha of every K-block, NU-deep ring =====
@@ -212,6 +284,43 @@ score_tc16p_kernel(const __grid_constant__ ScoreArgs a, const __grid_constant__ 
     for (uint64_t pt = pair0; pt < npairs; pt += pstride, ++tiles_done) {
       const uint64_t tile = 2 * pt + rank;
       float ss = 0.f;
+      if constexpr (ACC) {
+        // fold every K-block's chunk X[h] into the running sum R with round-to-nearest adds; the last chunk of a row
+        // block is squared and summed instead of stored (its running sum is complete: V for 128 rows of T)
+        for (int rb = 0; rb < nRB; ++rb) {
+          const int nJ = min(KPR * (rb + 1), nJtot);
+          for (int J = 0; J < nJ; ++J) {
+            const bool first = (J == 0), last = (J == nJ - 1);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              mbar_wait<64>(smem_u32(&S.tmem_full[h]), (acc_ph >> h) & 1);
+              acc_ph ^= 1u << h;
+              tc_fence_after();
+#pragma unroll
+              for (int c0 = 0; c0 < HB; c0 += 32) {
+                uint32_t x[32], r[32];
+                tmem_ld32_nowait(lane_addr + (uint32_t)(BN + h * HB + c0), x);
+                if (!first) tmem_ld32_nowait(lane_addr + (uint32_t)(h * HB + c0), r);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                  const float v = first ? __uint_as_float(x[i]) : __uint_as_float(r[i]) + __uint_as_float(x[i]);
+                  if (last) ss = fmaf(v, v, ss);
+                  else x[i] = __float_as_uint(v);
+                }
+                if (!last) tmem_st32(lane_addr + (uint32_t)(h * HB + c0), x);
+              }
+              if (!last) tmem_st_wait();
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) {
+                if (leader) mbar_arrive(smem_u32(&S.tmem_empty[h]));
+                else mbar_arrive_rank(smem_u32(&S.tmem_empty[h]), 0);
+              }
+            }
+          }
+        }
+      } else
       for (int sb = 0; sb < nSB; ++sb) {
         const int rb0 = sb * NACC, rb1 = min(rb0 + NACC, nRB);
         for (int acc = 0; acc < rb1 - rb0; ++acc) {
@@ -243,8 +352,9 @@ score_tc16p_kernel(const __grid_constant__ ScoreArgs a, const __grid_constant__ 
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&S.mean_empty));
       const float mu = msum * mean_unscale + ymean;  // gp.py:67
-      const uint64_t row = tile * TM + cl;
-      const bool valid = row < a.m_count;
+      const uint64_t lrow = tile * TM + cl;  // position in this launch; list mode: the row it stands for
+      const bool valid = lrow < total;
+      const uint64_t row = (a.in_list && valid) ? (uint64_t)a.in_list[lrow] : lrow;
       const float var = amp - ss * unscale2;       // gp.py:69 (diagonal only)
       // tcgen05.mma adds into its fp32 accumulator with truncation (toward zero, once per instruction, and every aligned
       // addend at a quarter ulp: scripts/dev/umma_probe.py), which biases sum v^2 by 1e-6 .. 6e-5 relative.  That is
@@ -408,14 +518,14 @@ static unsigned pair_grid(uint64_t m_count, int sms) {
   return 2u * (unsigned)(npairs < max_pairs ? npairs : max_pairs);
 }
 
-template <int D4, int RC>
+template <int D4, int RC, bool ACC>
 static int32_t launch_d4(cudaStream_t s, const ScoreArgs& a, const SamplerPack& sp, const CUtensorMap& mh, const CUtensorMap& ml) {
   const size_t smem = sizeof(Smem) + sizeof(float) * NU * (BKH * D4 + BKH) + (D4 <= 28 ? sizeof(float) * TM * D4 : 0);
-  BX_CUDA(cudaFuncSetAttribute(score_tc16p_kernel<D4, RC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  BX_CUDA(cudaFuncSetAttribute(score_tc16p_kernel<D4, RC, ACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int dev = 0, sms = 0;
   BX_CUDA(cudaGetDevice(&dev));
   BX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  const unsigned grid = pair_grid(a.m_count, sms);
+  const unsigned grid = pair_grid(a.m_count, sms);  // list mode: sized for the whole launch, CTAs beyond the list idle
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(NTHREADS);
@@ -428,8 +538,25 @@ static int32_t launch_d4(cudaStream_t s, const ScoreArgs& a, const SamplerPack& 
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  BX_CUDA(cudaLaunchKernelEx(&cfg, score_tc16p_kernel<D4, RC>, a, sp, mh, ml));
+  BX_CUDA(cudaLaunchKernelEx(&cfg, score_tc16p_kernel<D4, RC, ACC>, a, sp, mh, ml));
   return 0;
+}
+
+template <bool ACC>
+static int32_t launch_any(cudaStream_t s, const ScoreArgs& a, const SamplerPack& sp, const CUtensorMap& mh, const CUtensorMap& ml) {
+  // RC = 4 candidates per producer thread while their coordinates fit the 176-register budget (d <= 20), else 2
+  switch (a.f.d4) {
+    case 4: return launch_d4<4, 4, ACC>(s, a, sp, mh, ml);
+    case 8: return launch_d4<8, 4, ACC>(s, a, sp, mh, ml);
+    case 12: return launch_d4<12, 4, ACC>(s, a, sp, mh, ml);
+    case 16: return launch_d4<16, 4, ACC>(s, a, sp, mh, ml);
+    case 20: return launch_d4<20, 4, ACC>(s, a, sp, mh, ml);
+    case 24: return launch_d4<24, 2, ACC>(s, a, sp, mh, ml);
+    case 28: return launch_d4<28, 2, ACC>(s, a, sp, mh, ml);
+    case 32: return launch_d4<32, 2, ACC>(s, a, sp, mh, ml);
+  }
+  set_error("tcgen05 engines support d <= 32 (d4=%d)", a.f.d4);
+  return BX_E_UNSUPPORTED;
 }
 
 }  // namespace tc16p
@@ -442,27 +569,18 @@ unsigned score_tc16p_grid(uint64_t m_count) {
 
 bool score_tc16_supported(const bx_factor_t& f) { return f.d_T16hi && f.d_T16lo && f.d4 <= 32; }
 
-int32_t launch_score_tc16p(cudaStream_t s, const ScoreArgs& a_in, const SamplerPack& sp) {
+// accurate = false: the fast mode (two row blocks in flight, sums over whole rows inside the tensor core);
+// accurate = true: chunk accumulators folded into TMEM-resident running sums by the epilogue (fp32-level accuracy)
+int32_t launch_score_tc16p(cudaStream_t s, const ScoreArgs& a_in, const SamplerPack& sp, bool accurate) {
   ScoreArgs a = a_in;
   if (const char* e = getenv("BX_TC_ABLATE")) a.debug = atoi(e);
   CUtensorMap mh, ml;
-  int32_t rc = tc::make_map_f16(&mh, a.f.d_T16hi, a.f.np, a.f.np, tc16p::HN);
+  const uint32_t box_rows = accurate ? tc16p::HB / 2 : tc16p::HN;
+  int32_t rc = tc::make_map_f16(&mh, a.f.d_T16hi, a.f.np, a.f.np, box_rows);
   if (rc) return rc;
-  rc = tc::make_map_f16(&ml, a.f.d_T16lo, a.f.np, a.f.np, tc16p::HN);
+  rc = tc::make_map_f16(&ml, a.f.d_T16lo, a.f.np, a.f.np, box_rows);
   if (rc) return rc;
-  // RC = 4 candidates per producer thread while their coordinates fit the 176-register budget (d <= 20), else 2
-  switch (a.f.d4) {
-    case 4: return tc16p::launch_d4<4, 4>(s, a, sp, mh, ml);
-    case 8: return tc16p::launch_d4<8, 4>(s, a, sp, mh, ml);
-    case 12: return tc16p::launch_d4<12, 4>(s, a, sp, mh, ml);
-    case 16: return tc16p::launch_d4<16, 4>(s, a, sp, mh, ml);
-    case 20: return tc16p::launch_d4<20, 4>(s, a, sp, mh, ml);
-    case 24: return tc16p::launch_d4<24, 2>(s, a, sp, mh, ml);
-    case 28: return tc16p::launch_d4<28, 2>(s, a, sp, mh, ml);
-    case 32: return tc16p::launch_d4<32, 2>(s, a, sp, mh, ml);
-  }
-  set_error("tcgen05 engines support d <= 32 (d4=%d)", a.f.d4);
-  return BX_E_UNSUPPORTED;
+  return accurate ? tc16p::launch_any<true>(s, a, sp, mh, ml) : tc16p::launch_any<false>(s, a, sp, mh, ml);
 }
 
 }  // namespace bx

@@ -49,9 +49,12 @@ enum {
   BX_ENGINE_SIMT = 1,           /* fp32 FFMA pipes: explicit point sets, d > 32, cancellation-regime candidates */
   BX_ENGINE_TCGEN05_F16 = 2,    /* the production path: tcgen05 with fp16 head/tail operands (3 MMAs per MAC, the same 22
                                    operand bits as a 3xTF32 split at half the tensor work), cta_group::2, register-tiled K*
-                                   producers - and the fp32 SIMT engine on the candidates whose variance sits in the
-                                   cancellation regime */
-  BX_ENGINE_TCGEN05_F16_RAW = 3 /* the tensor engine alone, no hand-over (diagnostics: its own accuracy) */
+                                   producers.  Fast mode over every candidate (whole-row sums inside the tensor core);
+                                   the candidates whose variance sits in the cancellation regime (var < amp / 2) are
+                                   re-scored in the accurate mode (per-K-block chunks folded into TMEM-resident fp32
+                                   running sums with round-to-nearest adds) */
+  BX_ENGINE_TCGEN05_F16_RAW = 3, /* the fast mode alone, no hand-over (diagnostics: its own accuracy) */
+  BX_ENGINE_TCGEN05_F16_ACC = 4  /* the accurate mode alone over every candidate */
 };
 
 /* One dimension of the parameter space - mirrors bayex.domain.Real / Integer (domain.py:22-131). */
