@@ -90,19 +90,41 @@ __global__ void __launch_bounds__(256) refine_blk_kernel(const float* __restrict
   int I, J;
   lower_block((int)blockIdx.x, I, J);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  // stage the block k-major: k = column of T for V (out = row), k = row of T for W (out = column)
-  for (int e = tid; e < RBS * RBS; e += 256) {
-    const int r = e >> 7, c = e & 127;
-    const float v = T[(size_t)(I * RBS + r) * np + J * RBS + c];  // zero above the diagonal
-    if (TRANS) Tb[r * RLD + c] = v; else Tb[c * RLD + r] = v;
+  // stage the block k-major: k = column of T for V (out = row), k = row of T for W (out = column).  8 loads in flight per
+  // thread before the first store (one load per iteration left the staging latency-bound: 64 x an L2 round trip per CTA)
+  {
+    const float* Tblk = T + (size_t)(I * RBS) * np + J * RBS;
+#pragma unroll 1
+    for (int b = 0; b < RBS * RBS / 256; b += 8) {
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int e = tid + 256 * (b + u);
+        v[u] = Tblk[(size_t)(e >> 7) * np + (e & 127)];  // zero above the diagonal
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int e = tid + 256 * (b + u), r = e >> 7, c = e & 127;
+        if (TRANS) Tb[r * RLD + c] = v[u]; else Tb[c * RLD + r] = v[u];
+      }
+    }
   }
   const int kblk = TRANS ? I : J, oblk = TRANS ? J : I, part = TRANS ? I : J;
   const int q4 = (warp & 3) * 4, kh = warp >> 2;  // this warp: starts q4 .. q4 + 3 of the group, k half kh; lanes = out
   for (int g = 0; g < S16 / RG; ++g) {
     __syncthreads();  // Tb staged / the previous group's Ib and Rb consumed
-    for (int e = tid; e < RG * RBS; e += 256) {
-      const int sI = e >> 7, k = e & 127;
-      Ib[k * RG + sI] = In[(size_t)(g * RG + sI) * np + kblk * RBS + k];
+    {
+      float v[RG * RBS / 256];
+#pragma unroll
+      for (int u = 0; u < RG * RBS / 256; ++u) {
+        const int e = tid + 256 * u;
+        v[u] = In[(size_t)(g * RG + (e >> 7)) * np + kblk * RBS + (e & 127)];
+      }
+#pragma unroll
+      for (int u = 0; u < RG * RBS / 256; ++u) {
+        const int e = tid + 256 * u;
+        Ib[(e & 127) * RG + (e >> 7)] = v[u];
+      }
     }
     __syncthreads();
     float acc[4][4];

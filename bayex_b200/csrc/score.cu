@@ -332,7 +332,7 @@ static HandoverWs carve_handover(void* base, uint64_t m_count) {
 // engine (BX_TIER2=simt; also what a factor without fp16 copies or d > 32 gets).
 static bool tier2_simt() {
   const char* e = getenv("BX_TIER2");
-  return !(e && e[0] == 'a');  // until the accurate mode has been through the whole parity suite: opt-in (BX_TIER2=acc)
+  return e && e[0] == 's';
 }
 
 // The production path: the fast mode of the fp16 tcgen05 engine over every candidate of the launch, then the accurate

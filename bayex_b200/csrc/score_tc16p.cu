@@ -51,6 +51,10 @@ constexpr int HN = BN / 2;                 // rows of every T tile held by one C
 #endif
 constexpr int SA = BX_P_SA, SB = BX_P_SB, NU = BX_P_NU;
 constexpr int HB = 128;                    // accurate mode: rows per half of a row block = UMMA N; each CTA holds HB / 2 of them
+#ifndef BX_ACC_CHJ
+#define BX_ACC_CHJ 1
+#endif
+constexpr int CHJ = BX_ACC_CHJ;            // accurate mode: K-blocks summed inside the tensor core before a chunk is folded
 constexpr int KPR = BN / BKH;              // K-blocks per row block
 constexpr int ATILE = TM * BKH * 2;        // 16 KiB: 128 candidates x 64 halves
 constexpr int BTILE = HN * BKH * 2;        // 16 KiB: 128 T rows x 64 halves
@@ -180,10 +184,13 @@ score_tc16p_kernel(const __grid_constant__ ScoreArgs a, const __grid_constant__ 
               mbar_wait<32>(smem_u32(&S.full_b[st]), pb);
               tc_fence_after();
               const uint64_t ah = make_desc(smem_u32(S.a_hi[sa])), al = make_desc(smem_u32(S.a_lo[sa]));
+              const bool c_first = (J % CHJ == 0), c_last = (J % CHJ == CHJ - 1) || (J == min(KPR * (rb + 1), nJtot) - 1);
 #pragma unroll
               for (int h = 0; h < 2; ++h) {
-                mbar_wait_cluster(smem_u32(&S.tmem_empty[h]), ((xph >> h) & 1) ^ 1);  // the epilogues folded X[h] into R
-                tc_fence_after();
+                if (c_first) {
+                  mbar_wait_cluster(smem_u32(&S.tmem_empty[h]), ((xph >> h) & 1) ^ 1);  // the epilogues folded X[h] into R
+                  tc_fence_after();
+                }
                 const uint64_t bh = make_desc(smem_u32(S.b_hi[st]) + (uint32_t)(h * (BTILE / 2)));
                 const uint64_t bl = make_desc(smem_u32(S.b_lo[st]) + (uint32_t)(h * (BTILE / 2)));
                 const uint32_t d = tmem + (uint32_t)(BN + h * HB);
@@ -191,12 +198,14 @@ score_tc16p_kernel(const __grid_constant__ ScoreArgs a, const __grid_constant__ 
 #pragma unroll
                 for (int ks = 0; ks < BKH / 16; ++ks) {
                   const uint64_t o = (uint64_t)(ks * 2);
-                  umma_f16_pair(d, ah + o, bh + o, idesc, ks != 0);  // a chunk never holds more than this one K-block
+                  umma_f16_pair(d, ah + o, bh + o, idesc, !(c_first && ks == 0));  // a chunk holds at most CHJ K-blocks
                   umma_f16_pair(d, al + o, bh + o, idesc, 1u);
                   umma_f16_pair(d, ah + o, bl + o, idesc, 1u);
                 }
-                umma_commit_pair(smem_u32(&S.tmem_full[h]));
-                xph ^= 1u << h;
+                if (c_last) {
+                  umma_commit_pair(smem_u32(&S.tmem_full[h]));
+                  xph ^= 1u << h;
+                }
               }
               umma_commit_pair(smem_u32(&S.empty_b[st]));
               umma_commit_pair(smem_u32(&S.empty_a[sa]));
@@ -288,12 +297,12 @@ score_tc16p_kernel(const __grid_constant__ ScoreArgs a, const __grid_constant__ 
         // fold every K-block's chunk X[h] into the running sum R with round-to-nearest adds; the last chunk of a row
         // block is squared and summed instead of stored (its running sum is complete: V for 128 rows of T)
         for (int rb = 0; rb < nRB; ++rb) {
-          const int nJ = min(KPR * (rb + 1), nJtot);
-          for (int J = 0; J < nJ; ++J) {
-            const bool first = (J == 0), last = (J == nJ - 1);
+          const int nCh = (min(KPR * (rb + 1), nJtot) + CHJ - 1) / CHJ;
+          for (int ch = 0; ch < nCh; ++ch) {
+            const bool first = (ch == 0), last = (ch == nCh - 1);
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-              mbar_wait<64>(smem_u32(&S.tmem_full[h]), (acc_ph >> h) & 1);
+              mbar_wait(smem_u32(&S.tmem_full[h]), (acc_ph >> h) & 1);  // hot: one wait per 768 CHJ clocks of MMAs, no back-off
               acc_ph ^= 1u << h;
               tc_fence_after();
 #pragma unroll
@@ -314,8 +323,10 @@ score_tc16p_kernel(const __grid_constant__ ScoreArgs a, const __grid_constant__ 
               tc_fence_before();
               __syncwarp();
               if (lane == 0) {
+                // what the MMA issuer must see is ordered by the tcgen05 fences (TMEM only): the remote arrive needs no
+                // cluster-scope release (that form compiles to MEMBAR.ALL.GPU - once per 768 clocks here)
                 if (leader) mbar_arrive(smem_u32(&S.tmem_empty[h]));
-                else mbar_arrive_rank(smem_u32(&S.tmem_empty[h]), 0);
+                else mbar_arrive_rank_relaxed(smem_u32(&S.tmem_empty[h]), 0);
               }
             }
           }

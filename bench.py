@@ -369,6 +369,15 @@ def main():
         if i >= max(args.warmup, 3):
             kern_ms.append(s.elapsed_time(e))
     kern_ms_avg = float(np.mean(kern_ms))
+    # every rank's own front-half time: the GPUs of a box settle at different power-capped clocks, and a step ends when the
+    # slowest rank arrives at the all-gather - the spread is reported so that it is not mistaken for a serial fraction
+    if world > 1:
+        kt = torch.tensor([kern_ms_avg], dtype=torch.float64, device=dev)
+        kall = [torch.empty_like(kt) for _ in range(world)]
+        dist.all_gather(kall, kt)
+        kern_ms_ranks = [float(t.item()) for t in kall]
+    else:
+        kern_ms_ranks = [kern_ms_avg]
 
     # -- resident-factor steps (value)
     for i in range(args.warmup):
@@ -426,6 +435,7 @@ def main():
                     "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
                     "frac_of_split_ceiling": 3 * achieved / peak if peak else None,
                     "traffic": TRAFFIC_BYTES.get((args.workload, M)), "kernel_ms": kern_ms_avg,
+                    "kernel_ms_per_rank": kern_ms_ranks,
                     "algorithmic_flops_per_launch": fl, "peak_source": peak_src, "ffma_peak_this_run": ffma_peak,
                     "kernel_ms_covers": "front half of sample(): scoring kernel + hand-over pass (fp32 SIMT engine on the "
                                         "cancellation-regime candidates) + top-k merge"}
