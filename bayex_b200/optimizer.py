@@ -89,6 +89,9 @@ class Optimizer:
         self.engine = _lib.ENGINE_AUTO
         self._dims = engine.dims_array(domain)
         self._cache = {}
+        # multi-GPU load balance: candidates per millisecond every rank sustained in its last front half (None: equal shards)
+        self._rates = None
+        self._pending = None
 
     # ------------------------------------------------------------------------------------------------------
     def _dist(self):
@@ -188,7 +191,12 @@ class Optimizer:
         post = self.posterior(state)
         ystar = boacq.ystar_for(self.acq_name, self.sign * np.asarray(state.ys, dtype=np.float32), state.mask)
         dist, rank, world = self._dist()
-        m_begin, m_count = shard_range(size, rank, world)
+        # The GPUs of a box settle at different power-capped clocks (a few per cent apart), and a sharded step ends when the
+        # slowest rank reaches the all-gather: the candidate shards are therefore sized by the throughput every rank
+        # sustained in its previous front half.  The result does not depend on the shard boundaries (candidate i is a
+        # function of (key, i); the merged top-k and arg-max are those of the whole draw), only the time does.
+        self._collect_rates(world)
+        m_begin, m_count = shard_range(size, rank, world, self._rates)
         name, param = self.acq_name, self.acq_param
         d = len(self.domain)
         k = max(1, min(n_starts, size))  # optimizer.py:196 takes what exists when size < 50
@@ -198,9 +206,17 @@ class Optimizer:
         # is the read-back of the proposal (d + 2 floats).
         with engine.on_stream(post.stream, post.dev):
             # optimizer.py:183-197, :205 on this rank's candidate shard: fused generate -> score -> top-k -> arg-max
+            if world > 1:
+                ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                ev0.record(post.stream)
             lst, tv, ti, vals = post.sample_front(key, self._dims, m_begin, m_count, name, param, ystar, k,
                                                   engine=self.engine, keep_acq=details)
             if world > 1:
+                ev1.record(post.stream)
+                # what this rank sustained LAST time travels with this call (its events are long complete: no sync)
+                mine = torch.tensor([self._pending[2] if self._pending and self._pending[2] else 0.0], dtype=torch.float64)
+                rates_dev = torch.empty(world, dtype=torch.float64, device=post.dev)
+                dist.all_gather_into_tensor(rates_dev, mine.to(post.dev, non_blocking=True))
                 # one packed all-gather (k top keys + the arg-max key per rank), merged identically on every rank
                 lists = torch.empty(world * (k + 1), dtype=torch.int64, device=post.dev)
                 dist.all_gather_into_tensor(lists, lst)
@@ -224,6 +240,8 @@ class Optimizer:
             # optimizer.py:203-207: arg-max over concat(optimised, random), first occurrence => optimised points win ties
             out = post.propose(key, self._dims, optimized, opt_vals, S, lst[k:])
             out_host = out.cpu().numpy()
+            if world > 1:
+                self._pending = (ev0, ev1, None, m_count, rates_dev.cpu().numpy())
         point = out_host[:d].astype(np.float32)
         chosen = int(out_host[d + 1:d + 2].view(np.uint32)[0])
         if q > 1 or details:
@@ -246,6 +264,20 @@ class Optimizer:
                             best_opt=_lib.unpack(b_opt), best_rnd=_lib.unpack(b_rnd), m_begin=m_begin, m_count=m_count)
             return best_params, info
         return best_params
+
+    def _collect_rates(self, world):
+        """Turn the previous call's front-half timing into this rank's rate, and the rates every rank reported last time into
+        the shard weights.  Everything here is host arithmetic on values that are identical on all ranks (the gathered
+        vector), so every rank derives the same shard boundaries."""
+        if world == 1 or self._pending is None:
+            return
+        ev0, ev1, _, m_count, gathered = self._pending
+        ms = ev0.elapsed_time(ev1)  # the events completed before the previous call returned
+        rate = (m_count / ms) if (ms > 0 and m_count >= MIN_BALANCED_SHARD) else 0.0
+        self._pending = (ev0, ev1, rate, m_count, gathered)
+        if gathered is not None and np.all(gathered > 0):
+            new = gathered / gathered.sum()
+            self._rates = new if self._rates is None else 0.5 * (self._rates + new)  # damped: one noisy sample moves it half way
 
     def _batch_points(self, post, key, first, opt_host, ov_host, tv, ti, q):
         """The q best distinct points of concat(refined starts, top random candidates) by acquisition value; row 0 = ``first``."""
@@ -308,11 +340,26 @@ def argmax_first(v: np.ndarray) -> int:
     return int(np.argmax(nan)) if nan.any() else int(np.argmax(v))
 
 
-def shard_range(size: int, rank: int, world: int):
-    """Contiguous slice [begin, begin+count) of the candidate axis owned by ``rank``."""
-    per = (size + world - 1) // world
-    begin = min(rank * per, size)
-    return begin, min(per, size - begin)
+MIN_BALANCED_SHARD = 1 << 16   # shards below this are latency-, not throughput-bound: keep them equal
+SHARD_GRANULE = 256             # candidates per pair-tile of the scoring kernel
+
+
+def shard_range(size: int, rank: int, world: int, weights=None):
+    """Contiguous slice [begin, begin+count) of the candidate axis owned by ``rank``.  ``weights`` (optional,
+    one positive number per rank, identical on every rank): shares proportional to them, boundaries on multiples of the
+    scoring kernel's pair-tile; None, or a draw too small to matter, gives equal shards."""
+    if weights is None or world == 1 or size < world * MIN_BALANCED_SHARD:
+        per = (size + world - 1) // world
+        begin = min(rank * per, size)
+        return begin, min(per, size - begin)
+    w = np.asarray(weights, dtype=np.float64)
+    cuts = np.concatenate([[0.0], np.cumsum(w / w.sum())]) * size
+    edges = [int(round(c / SHARD_GRANULE)) * SHARD_GRANULE for c in cuts]
+    edges[0], edges[-1] = 0, size
+    edges = [min(max(e, 0), size) for e in edges]
+    for i in range(1, len(edges)):
+        edges[i] = max(edges[i], edges[i - 1])
+    return edges[rank], edges[rank + 1] - edges[rank]
 
 
 def allreduce_packed_max(best: torch.Tensor, dist, group=None) -> torch.Tensor:

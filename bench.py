@@ -98,8 +98,9 @@ class ClockSampler(threading.Thread):
         sm = sorted(float(r[0]) for r in self.rows)
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [nm for j, nm in enumerate(names) if any(r[3 + j].lower().startswith("active") for r in self.rows)]
+        pw = [float(r[2]) for r in self.rows]
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons, "samples": len(sm),
-                "power_w_max": max(float(r[2]) for r in self.rows)}
+                "power_w_max": max(pw), "power_w_mean": float(np.mean(pw))}
 
 
 def host_threads():
@@ -461,6 +462,11 @@ def main():
             "gpu_launches": launches_per_step * args.steps,
             "roofline": roofline,
             "clocks": clock_summary,
+            # the scoring kernel runs against the 1000 W cap (sw_power_cap, ~1.45 of 1.965 GHz): its time is joules per
+            # candidate / the cap.  Mean board power of rank 0 over the timed region x step time / candidates per rank
+            "energy": ({"board_power_w_mean": clock_summary["power_w_mean"],
+                        "microjoules_per_candidate": 1e6 * clock_summary["power_w_mean"] * (t_res / args.steps) / (M / world)}
+                       if clock_summary and clock_summary.get("power_w_mean") else None),
             "proposal": {k: float(v[0]) for k, v in list(proposal.items())[:3]},
         }
         line.update(fit_rec)

@@ -170,3 +170,20 @@ def test_restart_sweep_concurrency_policy_and_validation():
             fit_sweep.fit_restarts(x, y, raws, concurrent=bad)
     with pytest.raises(AssertionError):
         fit_sweep.fit_restarts(x, y, np.zeros((3, 5), np.float32))
+
+
+def test_weighted_shards_cover_the_draw_exactly():
+    """Throughput-weighted candidate shards (multi-GPU load balance): contiguous, ordered, exact cover, on pair-tile
+    boundaries; equal shards for small draws or without weights; a faster rank gets more."""
+    size, world = (1 << 24) + 12345, 8
+    w = [1.0, 1.05, 0.95, 1.0, 1.02, 0.98, 1.0, 1.0]
+    r = [bopt.shard_range(size, k, world, w) for k in range(world)]
+    assert r[0][0] == 0 and r[-1][0] + r[-1][1] == size
+    assert all(r[i][0] + r[i][1] == r[i + 1][0] for i in range(world - 1))
+    assert all(b % bopt.SHARD_GRANULE == 0 for b, _ in r)
+    assert r[1][1] > r[0][1] > r[2][1]
+    assert [bopt.shard_range(size, k, world) for k in range(world)] == [bopt.shard_range(size, k, world, None) for k in range(world)]
+    small = [bopt.shard_range(1000, k, world, w) for k in range(world)]
+    assert small == [bopt.shard_range(1000, k, world) for k in range(world)]
+    lop = [bopt.shard_range(1 << 20, k, 2, [1e-9, 1.0]) for k in range(2)]  # a rank may end up with (almost) nothing
+    assert lop[0][1] + lop[1][1] == 1 << 20 and lop[0][1] <= bopt.SHARD_GRANULE
