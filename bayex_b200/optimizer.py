@@ -131,8 +131,24 @@ class Optimizer:
         self._cache[self._digest(xs, ys_signed, mask, raw)] = post
         return raw
 
+    @staticmethod
+    def _identity(state: OptimizerState):
+        """Cheap key of a state: the identities of its arrays plus sums that a change of their contents would move.  States
+        are immutable value objects upstream (JAX arrays); this is the fast path of the cache look-up - a miss falls back
+        to the content digest, so a state that came from elsewhere (a file, another process) still finds its factor."""
+        parts = [id(state.ys), id(state.mask), float(np.sum(state.ys)), int(np.sum(state.mask))]
+        for k, v in state.params.items():
+            parts += [k, id(v), float(np.sum(v))]
+        for v in state.gp_params:
+            parts.append(np.asarray(v, dtype=np.float32).tobytes())
+        return tuple(parts)
+
     def posterior(self, state: OptimizerState) -> engine.Posterior:
         """The GPU-resident factor for ``state`` (cached; rebuilt if the state came from elsewhere)."""
+        ident = self._identity(state)
+        hit = self._cache.get("ident")
+        if hit is not None and hit[0] == ident:
+            return hit[1]
         xs, ys_signed, mask = self._arrays(state.params, state.ys, state.mask)
         raw = engine.raw_vector(state.gp_params, xs.shape[1])
         key = self._digest(xs, ys_signed, mask, raw)
@@ -141,6 +157,7 @@ class Optimizer:
             post = self._make_posterior(xs, ys_signed, mask, raw, fit_steps=0)
             self._cache.clear()
             self._cache[key] = post
+        self._cache["ident"] = (ident, post)
         return post
 
     # ------------------------------------------------------------------------------------------------------
@@ -204,7 +221,17 @@ class Optimizer:
 
         # Everything up to the proposal is enqueued on the library stream; the only host synchronisation of a sample()
         # is the read-back of the proposal (d + 2 floats).
+        import os
+        trace = [] if os.environ.get("BX_TRACE_SAMPLE") else None
+
+        def mark(label):
+            if trace is not None:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record(post.stream)
+                trace.append((label, ev))
+
         with engine.on_stream(post.stream, post.dev):
+            mark("start")
             # optimizer.py:183-197, :205 on this rank's candidate shard: fused generate -> score -> top-k -> arg-max
             if world > 1:
                 ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -221,6 +248,7 @@ class Optimizer:
                 lists = torch.empty(world * (k + 1), dtype=torch.int64, device=post.dev)
                 dist.all_gather_into_tensor(lists, lst)
                 lst, tv, ti = post.merge_lists(lists, world, k)
+            mark("all-gather of the key lists + merge")
             # optimizer.py:197-200: the multi-start axis is sharded too: rank r refines starts
             # [r c, (r + 1) c) of the merged list; a start's refinement does not depend on its neighbours in the batch
             c = (S + world - 1) // world if S else 0
@@ -231,6 +259,7 @@ class Optimizer:
                 x_mine, v_mine = post.refine(starts, refine_rounds, name, param, ystar)
                 rows[:b - a, :d] = x_mine
                 rows[:b - a, d] = v_mine
+            mark("gather of the starts + refinement of this rank's share")
             if world > 1 and S:
                 allrows = torch.empty((world * c, d + 1), dtype=torch.float32, device=post.dev)
                 dist.all_gather_into_tensor(allrows, rows)
@@ -238,8 +267,13 @@ class Optimizer:
             optimized = rows[:S, :d].contiguous()
             opt_vals = rows[:S, d].contiguous()
             # optimizer.py:203-207: arg-max over concat(optimised, random), first occurrence => optimised points win ties
+            mark("all-gather of the refined rows")
             out = post.propose(key, self._dims, optimized, opt_vals, S, lst[k:])
+            mark("proposal")
             out_host = out.cpu().numpy()
+            if trace is not None and rank == 0:
+                print("sample() device timeline, ms: " + "; ".join(f"{b[0]} {a[1].elapsed_time(b[1]):.3f}" for a, b in zip(trace[:-1], trace[1:])),
+                      flush=True)
             if world > 1:
                 self._pending = (ev0, ev1, None, m_count, rates_dev.cpu().numpy())
         point = out_host[:d].astype(np.float32)
