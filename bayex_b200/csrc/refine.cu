@@ -14,7 +14,7 @@ namespace bx {
 constexpr float kLn2 = 0.6931471805599453f;
 
 struct RefineWs {
-  float *Kst, *V, *W, *P, *xt, *xb, *gb, *fb, *step;
+  float *Kst, *Kst2, *V, *W, *P, *xt, *xb, *gb, *fb, *step;
   int S16;  // starts rounded up to the group size of the skinny products
   size_t bytes;
 };
@@ -29,6 +29,7 @@ static RefineWs carve_refine_ws(void* base, int np, int d, int S) {
     return p;
   };
   w.Kst = take((size_t)np * w.S16);
+  w.Kst2 = take((size_t)np * w.S16);  // K* of the next trial point, written by the update kernel
   w.V = take((size_t)np * w.S16);
   w.W = take((size_t)np * w.S16);
   w.P = take((size_t)(np / 128) * np * w.S16);  // per-block partials of the triangular products
@@ -187,7 +188,7 @@ template <int RU_T>
 __global__ void __launch_bounds__(RU_T) refine_update_kernel(bx_factor_t f, const float* __restrict__ Kst, const float* __restrict__ V,
                                                             const float* __restrict__ W, int acq_id, float acq_param,
                                                             float ystar, int first, float* xt, float* xb, float* gb,
-                                                            float* fb, float* step) {
+                                                            float* fb, float* step, float* Kst_next) {
   extern __shared__ float sm[];
   float* ak = sm;              // [np] alpha_j k_j
   float* wk = sm + f.np;       // [np] w_j k_j
@@ -313,7 +314,23 @@ __global__ void __launch_bounds__(RU_T) refine_update_kernel(bx_factor_t f, cons
     nrm = sqrtf(nrm);
     const bool ok = (nrm > 0.f) && (nrm < CUDART_INF_F);
     const float dir = ok ? gk * ls * ls / nrm : 0.f;
-    xt[(size_t)s * d + tid] = fminf(fmaxf(xbk + st * dir, -1e6f), 1e6f);  // optimizer.py:68
+    const float xn = fminf(fmaxf(xbk + st * dir, -1e6f), 1e6f);  // optimizer.py:68
+    xt[(size_t)s * d + tid] = xn;
+    ct[tid] = xn * f.d_scale[tid];
+  }
+  // K* of the next trial point, for the next round's products (saves the separate K* launch of every round but the first)
+  __syncthreads();
+  for (int j = tid; j < f.np; j += RU_T) {
+    float v = 0.f;
+    if (j < f.n) {
+      float acc = 0.f;
+      for (int k = 0; k < d; ++k) {
+        const float df = f.d_U[(size_t)j * f.d4 + k] - ct[k];
+        acc = fmaf(df, df, acc);
+      }
+      v = f.d_hyp[HYP_AMP] * ex2_approx(-acc);
+    }
+    Kst_next[(size_t)s * f.np + j] = v;
   }
 }
 
@@ -350,24 +367,34 @@ extern "C" int32_t bx_refine(const bx_factor_t* f, float* d_x, int32_t S, int32_
   BX_CUDA(cudaFuncSetAttribute(refine_blk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsm));
   BX_CUDA(cudaFuncSetAttribute(refine_blk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsm));
   const unsigned gsum = (unsigned)(((size_t)w.S16 * f->np + 255) / 256);
+  BX_CUDA(cudaMemsetAsync(w.Kst2, 0, sizeof(float) * (size_t)w.S16 * f->np, s));  // unused start slots stay zero
+  refine_kstar_kernel<<<(f->np * w.S16 + 255) / 256, 256, 0, s>>>(*f, w.xt, S, w.S16, w.Kst);
+  BX_LAUNCH_CHECK();
+  float *kcur = w.Kst, *knext = w.Kst2;
   for (int r = 0; r <= rounds; ++r) {
-    refine_kstar_kernel<<<(f->np * w.S16 + 255) / 256, 256, 0, s>>>(*f, w.xt, S, w.S16, w.Kst);
-    BX_LAUNCH_CHECK();
-    refine_blk_kernel<false><<<nblk, 256, bsm, s>>>(f->d_T, f->np, w.Kst, w.S16, w.P);  // V = T K*      (gp.py:68)
-    BX_LAUNCH_CHECK();
-    refine_partsum_kernel<false><<<gsum, 256, 0, s>>>(w.P, f->np, w.S16, w.V);
-    BX_LAUNCH_CHECK();
-    refine_blk_kernel<true><<<nblk, 256, bsm, s>>>(f->d_T, f->np, w.V, w.S16, w.P);     // W = T^T V = K^-1 k*
-    BX_LAUNCH_CHECK();
-    refine_partsum_kernel<true><<<gsum, 256, 0, s>>>(w.P, f->np, w.S16, w.W);
-    BX_LAUNCH_CHECK();
+    if (nb == 1) {  // a single block: its partial product is the product
+      refine_blk_kernel<false><<<nblk, 256, bsm, s>>>(f->d_T, f->np, kcur, w.S16, w.V);   // V = T K*      (gp.py:68)
+      BX_LAUNCH_CHECK();
+      refine_blk_kernel<true><<<nblk, 256, bsm, s>>>(f->d_T, f->np, w.V, w.S16, w.W);     // W = T^T V = K^-1 k*
+      BX_LAUNCH_CHECK();
+    } else {
+      refine_blk_kernel<false><<<nblk, 256, bsm, s>>>(f->d_T, f->np, kcur, w.S16, w.P);
+      BX_LAUNCH_CHECK();
+      refine_partsum_kernel<false><<<gsum, 256, 0, s>>>(w.P, f->np, w.S16, w.V);
+      BX_LAUNCH_CHECK();
+      refine_blk_kernel<true><<<nblk, 256, bsm, s>>>(f->d_T, f->np, w.V, w.S16, w.P);
+      BX_LAUNCH_CHECK();
+      refine_partsum_kernel<true><<<gsum, 256, 0, s>>>(w.P, f->np, w.S16, w.W);
+      BX_LAUNCH_CHECK();
+    }
     if (wide)
-      refine_update_kernel<512><<<S, 512, usm, s>>>(*f, w.Kst, w.V, w.W, acq_id, acq_param, ystar, r == 0 ? 1 : 0, w.xt, w.xb, w.gb,
-                                                    w.fb, w.step);
+      refine_update_kernel<512><<<S, 512, usm, s>>>(*f, kcur, w.V, w.W, acq_id, acq_param, ystar, r == 0 ? 1 : 0, w.xt, w.xb, w.gb,
+                                                    w.fb, w.step, knext);
     else
-      refine_update_kernel<128><<<S, 128, usm, s>>>(*f, w.Kst, w.V, w.W, acq_id, acq_param, ystar, r == 0 ? 1 : 0, w.xt, w.xb, w.gb,
-                                                    w.fb, w.step);
+      refine_update_kernel<128><<<S, 128, usm, s>>>(*f, kcur, w.V, w.W, acq_id, acq_param, ystar, r == 0 ? 1 : 0, w.xt, w.xb, w.gb,
+                                                    w.fb, w.step, knext);
     BX_LAUNCH_CHECK();
+    float* t = kcur; kcur = knext; knext = t;
   }
   BX_CUDA(cudaMemcpyAsync(d_x, w.xb, sizeof(float) * (size_t)S * f->d, cudaMemcpyDeviceToDevice, s));
   BX_CUDA(cudaMemcpyAsync(d_val, w.fb, sizeof(float) * S, cudaMemcpyDeviceToDevice, s));
