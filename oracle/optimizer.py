@@ -8,7 +8,9 @@ line.  Two documented differences, both from SURVEY quirks:
   diagonal is mathematically identical).
 * The L-BFGS refinement (``optimizer.py:39-73``) lives in optax (unpinned, and
   fed a mis-signed ``value_fn`` - quirk Q12), so its trajectory is PARITY
-  UNPINNED.  ``refine="identity"`` skips it (what the golden vectors made from
+  UNPINNED.  ``refine="lbfgs"`` / ``"lbfgs_quirk"`` run a restatement of the
+  published algorithm (``oracle/lbfgs.py``: L-BFGS two-loop recursion + strong-
+  Wolfe zoom search, not optax's code); ``refine="identity"`` skips it (what the golden vectors made from
   the reference source under the shim use, where ``optax.lbfgs`` is stubbed to
   a zero update); ``refine="ascent"`` restates the monotone multi-start ascent
   the CUDA path runs (``bayex_b200/csrc/refine.cu``) so the contract
@@ -179,6 +181,18 @@ class Optimizer:
             optimized = init_points.astype(self.dtype)
         elif refine == "ascent":
             optimized, _ = refine_ascent(self.acq_name, f, ys, state.mask, init_points)
+        elif refine in ("lbfgs", "lbfgs_quirk"):
+            # optimizer.py:198-199: vmap(_optimize_suggestion)(init_points) with max_iter = 10 - L-BFGS restated from the
+            # published algorithm (oracle/lbfgs.py, PARITY UNPINNED); "lbfgs_quirk" wires the signs as the reference does (Q12)
+            from . import lbfgs as olbfgs
+            f64 = Factor(state.gp_params, xs, ys, state.mask, np.float64)
+
+            def fg(x):
+                v, g = acq_value_and_grad(self.acq_name, f64, ys.astype(np.float64), state.mask, x[None, :])
+                return float(v[0]), g[0].astype(np.float64)
+
+            optimized = np.stack([olbfgs.optimize_suggestion(p0.astype(np.float64), fg, 10, sign_quirk=(refine == "lbfgs_quirk"))
+                                  for p0 in init_points]).astype(self.dtype)
         else:
             raise ValueError(refine)
         opt_vals = self.acq(optimized, xs, ys, state.mask, state.gp_params, dtype=self.dtype, factor=f)  # :200

@@ -228,3 +228,43 @@ def test_adamw_restatement_matches_an_independent_implementation():
         p, m, v, t = ogp.adamw_step(p, g, m, v, t, 1e-3, np.float64)
         assert np.allclose(p, tp.detach().numpy(), rtol=0, atol=5e-9), (step, np.abs(p - tp.detach().numpy()).max())
     assert 0 < clipped < 60
+
+
+def test_lbfgs_restatement_on_a_quadratic_and_in_the_reference_call_pattern():
+    """oracle-only restatement of the refinement's optimiser (PARITY UNPINNED: optax's source is not
+    available; this is Nocedal & Wright's L-BFGS + strong-Wolfe zoom).  Checks the algorithm itself (exact minimum of an
+    ill-conditioned quadratic in <= d + 2 steps, Rosenbrock progress) and its use through the oracle's sample(): refined
+    points never score below their starts, the proposal never below the best random candidate (the Q12 contract)."""
+    from oracle import lbfgs as olbfgs, optimizer as oopt, domain as odom, prng
+    rng = np.random.default_rng(0)
+    d = 6
+    A = rng.standard_normal((d, d))
+    H = A @ A.T + np.diag(np.logspace(0, 3, d))
+    b = rng.standard_normal(d)
+    xs_true = np.linalg.solve(H, b)
+    x, trace = olbfgs.lbfgs_minimize(lambda x: (0.5 * x @ H @ x - b @ x, H @ x - b), np.zeros(d), max_iter=40)
+    assert np.allclose(x, xs_true, rtol=1e-6, atol=1e-8)
+    assert all(t1[1] <= t0[1] + 1e-12 for t0, t1 in zip(trace[:-1], trace[1:])), "the Wolfe search must not increase f"
+
+    def rosen(x):
+        return (100.0 * (x[1] - x[0] ** 2) ** 2 + (1 - x[0]) ** 2,
+                np.array([-400.0 * x[0] * (x[1] - x[0] ** 2) - 2 * (1 - x[0]), 200.0 * (x[1] - x[0] ** 2)]))
+    x, trace = olbfgs.lbfgs_minimize(rosen, np.array([-1.2, 1.0]), max_iter=60)
+    assert trace[-1][1] < 1e-10 and np.allclose(x, [1.0, 1.0], atol=1e-4)
+
+    dom = {"a": odom.Real(0.0, 1.0), "b": odom.Real(0.0, 1.0), "c": odom.Real(0.0, 1.0)}
+    P0 = {k: rng.uniform(0, 1, 30).astype(np.float32) for k in dom}
+    Y0 = (np.sin(4 * P0["a"]) + P0["b"] ** 2 - P0["c"]).astype(np.float32)
+    opt = oopt.Optimizer(dom, acq="EI", maximize=True)
+    st = opt.init(Y0, P0, fit=False)
+    key = prng.key(3)
+    _, ident = opt.sample(key, st, size=2000, refine="identity", n_starts=8, details=True)
+    _, lb = opt.sample(key, st, size=2000, refine="lbfgs", n_starts=8, details=True)
+    assert np.all(lb["opt_vals"] >= ident["opt_vals"] - 1e-6 * np.abs(ident["opt_vals"]) - 1e-9)
+    assert np.any(lb["opt_vals"] > ident["opt_vals"] * (1 + 1e-4)), "L-BFGS should improve at least one start"
+    assert lb["all_vals"][lb["chosen"]] >= ident["acq_vals"].max() - 1e-9
+    # the reference's wiring (mis-signed value_fn): finite, clipped, and the arg-max over optimised + random still
+    # guarantees the proposal is at least the best random candidate - the contract the CUDA path is held to
+    _, qk = opt.sample(key, st, size=2000, refine="lbfgs_quirk", n_starts=8, details=True)
+    assert np.all(np.isfinite(qk["optimized"])) and np.all(np.abs(qk["optimized"]) <= 1e6)
+    assert qk["all_vals"][qk["chosen"]] >= ident["acq_vals"].max() - 1e-9
