@@ -505,8 +505,14 @@ extern "C" int32_t bx_score_generated_topk(const bx_factor_t* f, const uint32_t 
     rc = launch_score_simt(s, a, &sp, true);
   }
   if (rc) return rc;
-  return launch_topk_merge(s, w.slabs, w.counts, nslabs, tk::CAP, k, w.scratch, reinterpret_cast<unsigned long long*>(d_list), w.best, 1,
-                           1, d_vals, d_idx, d_count);
+  rc = launch_topk_merge(s, w.slabs, w.counts, nslabs, tk::CAP, k, w.scratch, reinterpret_cast<unsigned long long*>(d_list), w.best, 1,
+                         1, d_vals, d_idx, d_count);
+  if (rc) return rc;
+  if (d_count) {  // d_count[1]: candidates the fast mode handed to the second tier (0 for single-engine launches)
+    if (engine == BX_ENGINE_TCGEN05_F16) BX_CUDA(cudaMemcpyAsync(d_count + 1, w.h.count, sizeof(int32_t), cudaMemcpyDeviceToDevice, s));
+    else BX_CUDA(cudaMemsetAsync(d_count + 1, 0, sizeof(int32_t), s));
+  }
+  return 0;
 }
 
 extern "C" int32_t bx_propose(const uint32_t key[2], const bx_dim_t* dims, int32_t d, const float* d_opt_x, const float* d_opt_val,

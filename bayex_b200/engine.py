@@ -288,12 +288,14 @@ class Posterior:
             vals = torch.empty(k, dtype=torch.float32, device=self.dev)
             idx = torch.empty(k, dtype=torch.int32, device=self.dev)
             acq_out = torch.empty(m_count, dtype=torch.float32, device=self.dev) if keep_acq else None
+            self.last_counts = torch.zeros(2, dtype=torch.int32, device=self.dev)  # [valid list entries, handed over]
+            self.last_m_count = int(m_count)
             if m_count > 0:
                 nbytes = lib.bx_score_topk_workspace_bytes(int(m_count), int(k))
                 ws = _workspace(self.dev, nbytes)
                 check(lib.bx_score_generated_topk(C.byref(self.factor), _lib.key_words(key), dims, int(m_begin), int(m_count),
                                                   _lib.ACQ_IDS[acq], float(param), float(ystar), int(k), _ptr(lst), _ptr(vals),
-                                                  _ptr(idx), None, _ptr(acq_out), int(engine), _ptr(ws), nbytes,
+                                                  _ptr(idx), _ptr(self.last_counts), _ptr(acq_out), int(engine), _ptr(ws), nbytes,
                                                   C.c_void_p(self.stream.cuda_stream)), "bx_score_generated_topk")
         return lst, vals, idx, acq_out
 

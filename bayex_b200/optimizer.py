@@ -92,6 +92,10 @@ class Optimizer:
         # multi-GPU load balance: candidates per millisecond every rank sustained in its last front half (None: equal shards)
         self._rates = None
         self._pending = None
+        # share of the last two-tier launch (over ALL ranks) that the fast tensor mode handed to the second tier, and the
+        # number of sample() calls since it was measured
+        self._handover_frac = 0.0
+        self._since_probe = 0
 
     # ------------------------------------------------------------------------------------------------------
     def _dist(self):
@@ -236,14 +240,24 @@ class Optimizer:
             if world > 1:
                 ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 ev0.record(post.stream)
+            # A posterior whose candidates nearly all sit in the cancellation regime (dense observations, long length scales)
+            # gets the accurate mode directly - the fast pass would only produce the hand-over list.  The decision is a
+            # function of the GLOBAL hand-over count of the last two-tier call (identical on every rank and for any number
+            # of ranks), re-measured every 8th call.
+            eng = self.engine
+            two_tier = eng in (_lib.ENGINE_AUTO, _lib.ENGINE_TCGEN05_F16) and post.want_tc and d <= 32
+            if eng == _lib.ENGINE_AUTO and two_tier and self._handover_frac > 0.5 and self._since_probe < 8:
+                eng, two_tier = _lib.ENGINE_TCGEN05_F16_ACC, False
             lst, tv, ti, vals = post.sample_front(key, self._dims, m_begin, m_count, name, param, ystar, k,
-                                                  engine=self.engine, keep_acq=details)
+                                                  engine=eng, keep_acq=details)
+            stats = post.last_counts.to(torch.float64)  # [valid list entries, handed over] of this rank's shard
             if world > 1:
                 ev1.record(post.stream)
                 # what this rank sustained LAST time travels with this call (its events are long complete: no sync)
                 mine = torch.tensor([self._pending[2] if self._pending and self._pending[2] else 0.0], dtype=torch.float64)
-                rates_dev = torch.empty(world, dtype=torch.float64, device=post.dev)
-                dist.all_gather_into_tensor(rates_dev, mine.to(post.dev, non_blocking=True))
+                mine = torch.cat([mine.to(post.dev, non_blocking=True), stats[1:2]])
+                gathered_dev = torch.empty(2 * world, dtype=torch.float64, device=post.dev)
+                dist.all_gather_into_tensor(gathered_dev, mine)
                 # one packed all-gather (k top keys + the arg-max key per rank), merged identically on every rank
                 lists = torch.empty(world * (k + 1), dtype=torch.int64, device=post.dev)
                 dist.all_gather_into_tensor(lists, lst)
@@ -271,11 +285,19 @@ class Optimizer:
             out = post.propose(key, self._dims, optimized, opt_vals, S, lst[k:])
             mark("proposal")
             out_host = out.cpu().numpy()
+            if world > 1:
+                g = gathered_dev.cpu().numpy().reshape(world, 2)
+                self._pending = (ev0, ev1, None, m_count, g[:, 0].copy())
+                handed = float(g[:, 1].sum())
+            else:
+                handed = float(stats.cpu().numpy()[1])
+            if two_tier and size >= 4096:
+                self._handover_frac, self._since_probe = handed / size, 0
+            else:
+                self._since_probe += 1
             if trace is not None and rank == 0:
                 print("sample() device timeline, ms: " + "; ".join(f"{b[0]} {a[1].elapsed_time(b[1]):.3f}" for a, b in zip(trace[:-1], trace[1:])),
                       flush=True)
-            if world > 1:
-                self._pending = (ev0, ev1, None, m_count, rates_dev.cpu().numpy())
         point = out_host[:d].astype(np.float32)
         chosen = int(out_host[d + 1:d + 2].view(np.uint32)[0])
         if q > 1 or details:

@@ -177,8 +177,10 @@ int32_t bx_topk(const float* d_vals, uint64_t M, int32_t k, uint64_t index_base,
 /* Fused generate -> score -> top-k -> arg-max over candidates [m_begin, m_begin + m_count) of sample_params(key, (M,)) -
  * replaces: optimizer.py:183-197 + :205.  On the fp16 tcgen05 engine the top-k is kept per CTA
  * inside the scoring epilogue and nothing per candidate is written to HBM (d_acq == NULL); d_acq (optional, [m_count])
- * additionally receives every acquisition value.  d_vals / d_idx / d_count (optional): the valid entries of the list
- * unpacked, ascending, at the front of d_vals [k] / d_idx [k]. */
+ * additionally receives every acquisition value.  d_vals / d_idx (optional): the valid entries of the list unpacked,
+ * ascending, at the front of d_vals [k] / d_idx [k].  d_count (optional, int32 [2]): their number, and the number of
+ * candidates the fast mode handed to the second tier (a caller that sees most of a launch handed over can ask for
+ * BX_ENGINE_TCGEN05_F16_ACC next time and save the first pass). */
 size_t bx_score_topk_workspace_bytes(uint64_t m_count, int32_t k);
 int32_t bx_score_generated_topk(const bx_factor_t* f, const uint32_t key[2], const bx_dim_t* dims, uint64_t m_begin,
                                 uint64_t m_count, int32_t acq_id, float acq_param, float ystar, int32_t k, uint64_t* d_list,
