@@ -305,22 +305,52 @@ score_tc16p_kernel(const __grid_constant__ ScoreArgs a, const __grid_constant__ 
               mbar_wait(smem_u32(&S.tmem_full[h]), (acc_ph >> h) & 1);  // hot: one wait per 768 CHJ clocks of MMAs, no back-off
               acc_ph ^= 1u << h;
               tc_fence_after();
+              // The three cases are separate straight-line loops: with `first` / `last` tested per element the fold ran to
+              // ~930 SASS instructions per warp (SEL / FSEL around every add: ncu source page, profiles/r2q) - five times
+              // the work - and the fold, not the tensor pipe (18 % active), set the pace of the accurate mode.
+              // (A software-pipelined version on 16-column groups was measured slower: more TMEM instructions.)
+              const uint32_t xa = lane_addr + (uint32_t)(BN + h * HB), ra = lane_addr + (uint32_t)(h * HB);
+              if (first && !last) {         // R = X
 #pragma unroll
-              for (int c0 = 0; c0 < HB; c0 += 32) {
-                // (a software-pipelined version on 16-column groups - next group's loads in flight during the adds - was
-                // measured SLOWER, 37.4 against 34.8 ms per 2^18 candidates at n = 4096: the fold is bound by the number of
-                // TMEM instructions and by the cross-CTA round trip per chunk, not by load latency; profiles/r2j_*)
-                uint32_t x[32], r[32];
-                tmem_ld32_nowait(lane_addr + (uint32_t)(BN + h * HB + c0), x);
-                if (!first) tmem_ld32_nowait(lane_addr + (uint32_t)(h * HB + c0), r);
-                tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                  const float v = first ? __uint_as_float(x[i]) : __uint_as_float(r[i]) + __uint_as_float(x[i]);
-                  if (last) ss = fmaf(v, v, ss);
-                  else x[i] = __float_as_uint(v);
+                for (int c0 = 0; c0 < HB; c0 += 32) {
+                  uint32_t x[32];
+                  tmem_ld32_nowait(xa + (uint32_t)c0, x);
+                  tmem_ld_wait();
+                  tmem_st32(ra + (uint32_t)c0, x);
                 }
-                if (!last) tmem_st32(lane_addr + (uint32_t)(h * HB + c0), x);
+              } else if (!last) {           // R += X   (round to nearest)
+#pragma unroll
+                for (int c0 = 0; c0 < HB; c0 += 32) {
+                  uint32_t x[32], r[32];
+                  tmem_ld32_nowait(xa + (uint32_t)c0, x);
+                  tmem_ld32_nowait(ra + (uint32_t)c0, r);
+                  tmem_ld_wait();
+#pragma unroll
+                  for (int i = 0; i < 32; ++i) x[i] = __float_as_uint(__uint_as_float(r[i]) + __uint_as_float(x[i]));
+                  tmem_st32(ra + (uint32_t)c0, x);
+                }
+              } else if (!first) {          // V = R + X complete for these 128 rows: square and sum
+#pragma unroll
+                for (int c0 = 0; c0 < HB; c0 += 32) {
+                  uint32_t x[32], r[32];
+                  tmem_ld32_nowait(xa + (uint32_t)c0, x);
+                  tmem_ld32_nowait(ra + (uint32_t)c0, r);
+                  tmem_ld_wait();
+#pragma unroll
+                  for (int i = 0; i < 32; ++i) {
+                    const float v = __uint_as_float(r[i]) + __uint_as_float(x[i]);
+                    ss = fmaf(v, v, ss);
+                  }
+                }
+              } else {                      // a row block with a single chunk
+#pragma unroll
+                for (int c0 = 0; c0 < HB; c0 += 32) {
+                  uint32_t x[32];
+                  tmem_ld32_nowait(xa + (uint32_t)c0, x);
+                  tmem_ld_wait();
+#pragma unroll
+                  for (int i = 0; i < 32; ++i) ss = fmaf(__uint_as_float(x[i]), __uint_as_float(x[i]), ss);
+                }
               }
               if (!last) tmem_st_wait();
               tc_fence_before();
