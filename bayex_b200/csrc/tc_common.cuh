@@ -24,21 +24,32 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
 // Bounded wait: a protocol bug must trap (process dies with a launch failure) instead of hanging the GPU.
-// SLEEP_NS > 0 backs off between probes so long waits (epilogue, TMA) do not steal issue slots from the producers.
+// The wait itself is the hardware's: mbarrier.try_wait with a suspend-time hint parks the warp until the phase completes or
+// the hint expires, so a waiting warp issues (almost) nothing.  Round 1 polled - try_wait without a hint returns after
+// ~35 ns, and `nanosleep` between probes does not sleep much longer - and ncu's source page of the scoring kernel showed
+// what that costs: 13.3 G iterations of the epilogue warps' wait alone, 52 % of ALL executed warp instructions of the
+// launch were barrier polling (profiles/r2l_score_tc16p_ncu_full_c3.csv, README).  SLEEP_NS > 0 marks the long waits
+// (epilogue, TMA): a longer hint.
+#ifndef BX_WAIT_HINT_HOT
+#define BX_WAIT_HINT_HOT 2000
+#endif
+#ifndef BX_WAIT_HINT_LONG
+#define BX_WAIT_HINT_LONG 20000
+#endif
 template <int SLEEP_NS = 0>
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done = 0, spins = 0;
   long long t0 = 0;
+  constexpr uint32_t hint = SLEEP_NS > 0 ? BX_WAIT_HINT_LONG : BX_WAIT_HINT_HOT;
   while (true) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done)
-        : "r"(bar), "r"(parity)
+        : "r"(bar), "r"(parity), "r"(hint)
         : "memory");
     if (done) return;
-    if (SLEEP_NS > 0) __nanosleep(SLEEP_NS);
     if ((++spins & 0xFFFu) == 0) {
       const long long now = clock64();
       if (t0 == 0) t0 = now;
@@ -196,16 +207,16 @@ template <int SLEEP_NS = 0>
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
   uint32_t done = 0, spins = 0;
   long long t0 = 0;
+  constexpr uint32_t hint = SLEEP_NS > 0 ? BX_WAIT_HINT_LONG : BX_WAIT_HINT_HOT;
   while (true) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done)
-        : "r"(bar), "r"(parity)
+        : "r"(bar), "r"(parity), "r"(hint)
         : "memory");
     if (done) return;
-    if (SLEEP_NS > 0) __nanosleep(SLEEP_NS);
     if ((++spins & 0xFFFu) == 0) {
       const long long now = clock64();
       if (t0 == 0) t0 = now;
