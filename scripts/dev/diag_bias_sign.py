@@ -1,4 +1,7 @@
+"""Signed relative error of sum v^2 from the tcgen05 fast mode ALONE (BX_HANDOVER_TAU=0 switches the hand-over to the
+accurate mode off, so nothing is re-scored) against the fp64 oracle: the truncation bias of DESIGN.md section 3.  Dev tool."""
 import os, sys
+os.environ["BX_HANDOVER_TAU"] = "0"  # read once by the library at its first scoring call
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np, torch
