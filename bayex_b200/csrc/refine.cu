@@ -73,6 +73,14 @@ __global__ void __launch_bounds__(256) refine_kstar_kernel(bx_factor_t f, const 
 constexpr int RBS = 128;         // block size
 constexpr int RLD = RBS + 1;     // padded row of the staged T block [k][out]: scalar accesses, conflict-free both ways
 
+// Programmatic dependent launch: the ~155 kernels of a refinement are each a few microseconds long, so the gaps between
+// them (drain + launch latency, ~5 us each) were a third of its time.  Every kernel of the loop lets its successor
+// start at once (launch_dependents) and waits for its predecessor's results (wait: predecessor grid complete and its
+// writes visible) before it reads or writes anything a predecessor touches; the block kernels stage their T block, which
+// no kernel of the loop writes, ahead of that wait.  Launched without the attribute (BX_NO_PDL), both are no-ops.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ void lower_block(int b, int& I, int& J) {  // b-th block of the lower triangle, row-major
   I = (int)((sqrtf(8.f * (float)b + 1.f) - 1.f) * 0.5f);
   while ((I + 1) * (I + 2) / 2 <= b) ++I;
@@ -91,8 +99,10 @@ __global__ void __launch_bounds__(256) refine_blk_kernel(const float* __restrict
   int I, J;
   lower_block((int)blockIdx.x, I, J);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  pdl_launch_dependents();
   // stage the block k-major: k = column of T for V (out = row), k = row of T for W (out = column).  8 loads in flight per
-  // thread before the first store (one load per iteration left the staging latency-bound: 64 x an L2 round trip per CTA)
+  // thread before the first store (one load per iteration left the staging latency-bound: 64 x an L2 round trip per CTA;
+  // 16-byte loads with the block kept [row][col] measured 15 % slower end to end, r2v)
   {
     const float* Tblk = T + (size_t)(I * RBS) * np + J * RBS;
 #pragma unroll 1
@@ -112,6 +122,7 @@ __global__ void __launch_bounds__(256) refine_blk_kernel(const float* __restrict
   }
   const int kblk = TRANS ? I : J, oblk = TRANS ? J : I, part = TRANS ? I : J;
   const int q4 = (warp & 3) * 4, kh = warp >> 2;  // this warp: starts q4 .. q4 + 3 of the group, k half kh; lanes = out
+  pdl_wait();  // In is the predecessor's output, P was read by the kernel before it
   for (int g = 0; g < S16 / RG; ++g) {
     __syncthreads();  // Tb staged / the previous group's Ib and Rb consumed
     {
@@ -161,6 +172,8 @@ __global__ void __launch_bounds__(256) refine_blk_kernel(const float* __restrict
 template <bool TRANS>
 __global__ void __launch_bounds__(256) refine_partsum_kernel(const float* __restrict__ P, int np, int S16, float* __restrict__ Out) {
   const size_t e = (size_t)blockIdx.x * 256 + threadIdx.x;
+  pdl_launch_dependents();
+  pdl_wait();
   if (e >= (size_t)S16 * np) return;
   const int x = (int)(e % np), blk = x / RBS, nb = np / RBS;
   const int p0 = TRANS ? blk : 0, p1 = TRANS ? nb : blk + 1;
@@ -196,6 +209,8 @@ __global__ void __launch_bounds__(RU_T) refine_update_kernel(bx_factor_t f, cons
   __shared__ float red[RU_W];
   __shared__ float dmu[BX_MAX_D], dvar[BX_MAX_D], ct[BX_MAX_D];
   const int s = blockIdx.x, tid = threadIdx.x, d = f.d;
+  pdl_launch_dependents();  // the next round's block kernel stages its T blocks under this kernel
+  pdl_wait();
   if (tid < BX_MAX_D) ct[tid] = (tid < d) ? xt[(size_t)s * d + tid] * f.d_scale[tid] : 0.f;
   float mu_p = 0.f, ss_p = 0.f;
   for (int j = tid; j < f.np; j += RU_T) {
@@ -340,6 +355,25 @@ int32_t check_factor(const bx_factor_t* f);
 
 using namespace bx;
 
+namespace {
+// launch with programmatic stream serialisation (see pdl_wait above); plain stream order with BX_NO_PDL set
+template <typename... KArgs, typename... Args>
+cudaError_t launch_chain(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
+  static const bool no_pdl = getenv("BX_NO_PDL") != nullptr;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = no_pdl ? 0 : 1;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+}  // namespace
+
 extern "C" size_t bx_refine_workspace_bytes(const bx_factor_t* f, int32_t S) {
   if (!f || S <= 0 || f->np <= 0) return 0;
   return carve_refine_ws(nullptr, f->np, f->d, S).bytes;
@@ -373,27 +407,20 @@ extern "C" int32_t bx_refine(const bx_factor_t* f, float* d_x, int32_t S, int32_
   float *kcur = w.Kst, *knext = w.Kst2;
   for (int r = 0; r <= rounds; ++r) {
     if (nb == 1) {  // a single block: its partial product is the product
-      refine_blk_kernel<false><<<nblk, 256, bsm, s>>>(f->d_T, f->np, kcur, w.S16, w.V);   // V = T K*      (gp.py:68)
-      BX_LAUNCH_CHECK();
-      refine_blk_kernel<true><<<nblk, 256, bsm, s>>>(f->d_T, f->np, w.V, w.S16, w.W);     // W = T^T V = K^-1 k*
-      BX_LAUNCH_CHECK();
+      BX_CUDA(launch_chain(refine_blk_kernel<false>, nblk, 256, bsm, s, f->d_T, f->np, kcur, w.S16, w.V));   // V = T K*  (gp.py:68)
+      BX_CUDA(launch_chain(refine_blk_kernel<true>, nblk, 256, bsm, s, f->d_T, f->np, w.V, w.S16, w.W));     // W = T^T V = K^-1 k*
     } else {
-      refine_blk_kernel<false><<<nblk, 256, bsm, s>>>(f->d_T, f->np, kcur, w.S16, w.P);
-      BX_LAUNCH_CHECK();
-      refine_partsum_kernel<false><<<gsum, 256, 0, s>>>(w.P, f->np, w.S16, w.V);
-      BX_LAUNCH_CHECK();
-      refine_blk_kernel<true><<<nblk, 256, bsm, s>>>(f->d_T, f->np, w.V, w.S16, w.P);
-      BX_LAUNCH_CHECK();
-      refine_partsum_kernel<true><<<gsum, 256, 0, s>>>(w.P, f->np, w.S16, w.W);
-      BX_LAUNCH_CHECK();
+      BX_CUDA(launch_chain(refine_blk_kernel<false>, nblk, 256, bsm, s, f->d_T, f->np, kcur, w.S16, w.P));
+      BX_CUDA(launch_chain(refine_partsum_kernel<false>, gsum, 256, 0, s, w.P, f->np, w.S16, w.V));
+      BX_CUDA(launch_chain(refine_blk_kernel<true>, nblk, 256, bsm, s, f->d_T, f->np, w.V, w.S16, w.P));
+      BX_CUDA(launch_chain(refine_partsum_kernel<true>, gsum, 256, 0, s, w.P, f->np, w.S16, w.W));
     }
     if (wide)
-      refine_update_kernel<512><<<S, 512, usm, s>>>(*f, kcur, w.V, w.W, acq_id, acq_param, ystar, r == 0 ? 1 : 0, w.xt, w.xb, w.gb,
-                                                    w.fb, w.step, knext);
+      BX_CUDA(launch_chain(refine_update_kernel<512>, S, 512, usm, s, *f, kcur, w.V, w.W, acq_id, acq_param, ystar, r == 0 ? 1 : 0,
+                           w.xt, w.xb, w.gb, w.fb, w.step, knext));
     else
-      refine_update_kernel<128><<<S, 128, usm, s>>>(*f, kcur, w.V, w.W, acq_id, acq_param, ystar, r == 0 ? 1 : 0, w.xt, w.xb, w.gb,
-                                                    w.fb, w.step, knext);
-    BX_LAUNCH_CHECK();
+      BX_CUDA(launch_chain(refine_update_kernel<128>, S, 128, usm, s, *f, kcur, w.V, w.W, acq_id, acq_param, ystar, r == 0 ? 1 : 0,
+                           w.xt, w.xb, w.gb, w.fb, w.step, knext));
     float* t = kcur; kcur = knext; knext = t;
   }
   BX_CUDA(cudaMemcpyAsync(d_x, w.xb, sizeof(float) * (size_t)S * f->d, cudaMemcpyDeviceToDevice, s));
