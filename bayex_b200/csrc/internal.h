@@ -101,7 +101,14 @@ struct ScoreArgs {
   // [0, m_count); outputs and keys still go by the row
   const uint32_t* in_list;
   const unsigned int* in_count;
+  // fast mode of the fp16 tcgen05 engine: its centred copy of the observation rows, rebuilt in the caller's workspace by
+  // every fast-mode launch (score_tc16p.cu: ux_rows_kernel), and the norm bound below which it expands the squared distance
+  float* ux;
+  float expand_smax;
 };
+
+constexpr int BX_UX_MAX_NP = 32768;  // largest padded n the fp16 tcgen05 engine takes (sizes the ux part of the workspaces)
+size_t score_tc16_ux_bytes();
 
 // Fused-top-k plumbing shared by score.cu / topk.cu / score_tc16p.cu
 unsigned score_tc16p_grid(uint64_t m_count);  // CTAs the fp16 engine launches for m_count candidates (slabs to merge)

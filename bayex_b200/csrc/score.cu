@@ -318,13 +318,17 @@ static float handover_tau() {
 struct HandoverWs {
   unsigned int* count;
   uint32_t* list;
+  float* ux;  // the fast mode's copy of the observation rows (ScoreArgs::ux)
   size_t bytes;
 };
 static HandoverWs carve_handover(void* base, uint64_t m_count) {
   HandoverWs h{};
+  char* b = reinterpret_cast<char*>(base);
+  const size_t list_bytes = align256(4 * (size_t)m_count);
   h.count = reinterpret_cast<unsigned int*>(base);
-  h.list = base ? reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(base) + 256) : nullptr;
-  h.bytes = 256 + align256(4 * (size_t)m_count);
+  h.list = base ? reinterpret_cast<uint32_t*>(b + 256) : nullptr;
+  h.ux = base ? reinterpret_cast<float*>(b + 256 + list_bytes) : nullptr;
+  h.bytes = 256 + list_bytes + align256(score_tc16_ux_bytes());
   return h;
 }
 
@@ -343,6 +347,7 @@ static int32_t launch_two_tier(cudaStream_t s, ScoreArgs a, const SamplerPack& s
                                int* nslabs) {
   const unsigned grid1 = score_tc16p_grid(a.m_count);
   if (nslabs) *nslabs = (int)grid1;
+  a.ux = h.ux;
   if (mode != 0) return launch_score_tc16p(s, a, sp, mode == 2);
   BX_CUDA(cudaMemsetAsync(h.count, 0, sizeof(unsigned int), s));
   a.flag_list = h.list; a.flag_count = h.count; a.flag_tau = handover_tau();
@@ -460,7 +465,7 @@ extern "C" int32_t bx_score_generated(const bx_factor_t* f, const uint32_t key[2
   if (engine == BX_ENGINE_TCGEN05_F16 || engine == BX_ENGINE_TCGEN05_F16_RAW || engine == BX_ENGINE_TCGEN05_F16_ACC) {
     BX_CHECK_ARG(score_tc16_supported(*f), BX_E_UNSUPPORTED, "the fp16 tcgen05 engine needs the T16hi/T16lo split of the factor and d <= 32");
     const int mode = engine == BX_ENGINE_TCGEN05_F16 ? 0 : (engine == BX_ENGINE_TCGEN05_F16_RAW ? 1 : 2);
-    BX_CHECK_ARG(mode != 0 || (d_ws && ws_bytes >= bx_score_workspace_bytes(m_count)), BX_E_WORKSPACE, "hand-over workspace missing or too small");
+    BX_CHECK_ARG(mode == 2 || (d_ws && ws_bytes >= bx_score_workspace_bytes(m_count)), BX_E_WORKSPACE, "scoring workspace missing or too small");
     return launch_two_tier((cudaStream_t)stream, a, sp, true, carve_handover(d_ws, m_count), mode, nullptr);
   }
   BX_CHECK_ARG(engine == BX_ENGINE_SIMT, BX_E_ARG, "unknown engine %d", engine);

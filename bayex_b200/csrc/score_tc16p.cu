@@ -60,6 +60,9 @@ constexpr int ATILE = TM * BKH * 2;        // 16 KiB: 128 candidates x 64 halves
 constexpr int BTILE = HN * BKH * 2;        // 16 KiB: 128 T rows x 64 halves
 constexpr int NTHREADS = 512, PROD0 = 8 * 32, NPROD = 256;
 constexpr int MAXOP = 8;                   // most observation parts (producer threads per candidate group)
+constexpr int UXP = 4;                     // fast mode: floats appended to a staged observation row (-|u'|^2, alpha, 2 pad)
+
+constexpr bool share_coords(int d4, bool acc) { return acc ? d4 <= 28 : d4 <= 24; }
 
 struct __align__(16) Smem {
   char a_hi[SA][ATILE], a_lo[SA][ATILE];
@@ -92,12 +95,15 @@ score_tc16p_kernel(const __grid_constant__ ScoreArgs a, const __grid_constant__ 
   constexpr int NACC = ACC ? 1 : 2;  // row blocks in flight
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   Smem& S = *reinterpret_cast<Smem*>(smem_raw);
-  constexpr int US = BKH * D4 + BKH;  // floats per staged K-block: 64 observation rows + 64 alpha
+  // Staged K-block of observations.  Accurate mode: 64 rows of U + 64 alpha (two bulk copies).  Fast mode: 64 rows of the
+  // centred copy built per launch by ux_rows_kernel - [D4 coordinates u' = u - mid | -|u'|^2 | alpha | 2 pad] - one copy.
+  constexpr int UR = ACC ? D4 : D4 + UXP;                 // floats per staged row
+  constexpr int US = ACC ? BKH * D4 + BKH : BKH * UR;     // floats per staged K-block
   const uint32_t us_addr = smem_u32(smem_raw) + (uint32_t)sizeof(Smem);  // [NU][US]
   // scaled candidate coordinates of the current tile [TM][D4], drawn ONCE per tile by the 256 producer threads together:
   // a producer thread needs the RC x D4 coordinates of its candidates, and the 2 RC threads that share a candidate group
   // used to draw them redundantly - at n = 512 those Threefry calls were half of the producers' instructions
-  constexpr bool SHARE_COORDS = (D4 <= 28);  // D4 = 32 does not leave room for the buffer
+  constexpr bool SHARE_COORDS = share_coords(D4, ACC);  // the widest rows do not leave room for the buffer
   const uint32_t cs_addr = us_addr + (uint32_t)(NU * US * 4);
   if ((smem_u32(smem_raw) & 1023u) != 0u) __trap();
 
@@ -264,8 +270,12 @@ score_tc16p_kernel(const __grid_constant__ ScoreArgs a, const __grid_constant__ 
             mbar_wait<256>(smem_u32(&S.empty_u[su]), ph ^ 1);
             const uint32_t bar = smem_u32(&S.full_u[su]), dst = us_addr + su * (uint32_t)(US * 4);
             mbar_expect_tx(bar, (uint32_t)(US * 4));
-            bulk_load_1d(dst, a.f.d_U + (size_t)J * BKH * D4, (uint32_t)(BKH * D4 * 4), bar);
-            bulk_load_1d(dst + (uint32_t)(BKH * D4 * 4), a.f.d_alpha + (size_t)J * BKH, (uint32_t)(BKH * 4), bar);
+            if constexpr (ACC) {
+              bulk_load_1d(dst, a.f.d_U + (size_t)J * BKH * D4, (uint32_t)(BKH * D4 * 4), bar);
+              bulk_load_1d(dst + (uint32_t)(BKH * D4 * 4), a.f.d_alpha + (size_t)J * BKH, (uint32_t)(BKH * 4), bar);
+            } else {
+              bulk_load_1d(dst, a.ux + (size_t)J * BKH * UR, (uint32_t)(US * 4), bar);
+            }
           }
         }
       }
@@ -438,6 +448,27 @@ score_tc16p_kernel(const __grid_constant__ ScoreArgs a, const __grid_constant__ 
     const int pth = tid - PROD0, cg = pth % NCG, op = pth / NCG;  // op is warp-uniform
     const float amp = a.f.d_hyp[HYP_AMP];
     const float ampk = amp * kstar_scale(amp);  // exact (power-of-two scale): entries land near 2^14
+    // Fast mode: coordinates are centred on the midpoint of the observations' bounding box (tail of a.ux), and when the
+    // norms are small the squared distance is formed as |c'|^2 + |u'|^2 - 2 c'.u' - one packed FMA per two dimensions
+    // instead of an add and an FMA (the producers, not the tensor pipe, set the kernel's pace).  The price is rounding at
+    // the magnitude of the norms instead of the distance: an absolute error of ~2^-24 (|c'|^2 + |u'|^2) in the exponent,
+    // i.e. a relative one in K*; so the form is used only while the largest possible |c'|^2 + |u'|^2 (from the domain box
+    // and the largest |u'|^2) stays below a.expand_smax (64: error below 4e-6, 1e-6 typical, against the 2^-22 the
+    // head/tail split itself carries).  Generated candidates only: explicit points have no box.
+    const float* ux_tail = ACC ? nullptr : a.ux + (size_t)np * UR;  // [D4] mid, then max |u'|^2
+    bool expand = false;
+    if constexpr (!ACC) {
+      if (!a.cand && a.expand_smax > 0.f) {
+        float cb = 0.f;
+        for (int k = 0; k < a.f.d; ++k) {
+          const DimSampler& ds = sp.dim[k];
+          const float lo = ds.kind == 0 ? ds.lo : (float)ds.ilo, hi = ds.kind == 0 ? ds.hi : (float)ds.ilo + (float)(ds.span - 1u);
+          const float a0 = lo * a.f.d_scale[k] - ux_tail[k], a1 = hi * a.f.d_scale[k] - ux_tail[k];
+          cb += fmaxf(a0 * a0, a1 * a1);
+        }
+        expand = (cb + ux_tail[D4] <= a.expand_smax);  // the same on every thread of the grid
+      }
+    }
     uint32_t ita = 0, itu = 0, tiles_done = 0;
     for (uint64_t pt = pair0; pt < npairs; pt += pstride, ++tiles_done) {
       const uint64_t tile = 2 * pt + rank;
@@ -445,7 +476,11 @@ score_tc16p_kernel(const __grid_constant__ ScoreArgs a, const __grid_constant__ 
       if constexpr (SHARE_COORDS) {
         for (int e = pth; e < TM * D4; e += NPROD) {
           const int c = e / D4, k = e % D4;
-          const float v = (k < a.f.d) ? cand_coord(a, sp, tile * TM + c, k) * a.f.d_scale[k] : 0.f;
+          float v = 0.f;
+          if (k < a.f.d) {
+            v = cand_coord(a, sp, tile * TM + c, k) * a.f.d_scale[k];
+            if constexpr (!ACC) v -= ux_tail[k];
+          }
           sts32(cs_addr + 4u * (uint32_t)e, -v);
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");  // producers only; the K loop below keeps tiles apart
@@ -464,8 +499,12 @@ score_tc16p_kernel(const __grid_constant__ ScoreArgs a, const __grid_constant__ 
           const uint64_t grow = tile * TM + cg + j * NCG;
 #pragma unroll
           for (int k = 0; k < D4; k += 2) {
-            const float c0 = (k < a.f.d) ? cand_coord(a, sp, grow, k) * a.f.d_scale[k] : 0.f;
-            const float c1 = (k + 1 < a.f.d) ? cand_coord(a, sp, grow, k + 1) * a.f.d_scale[k + 1] : 0.f;
+            float c0 = (k < a.f.d) ? cand_coord(a, sp, grow, k) * a.f.d_scale[k] : 0.f;
+            float c1 = (k + 1 < a.f.d) ? cand_coord(a, sp, grow, k + 1) * a.f.d_scale[k + 1] : 0.f;
+            if constexpr (!ACC) {
+              if (k < a.f.d) c0 -= ux_tail[k];
+              if (k + 1 < a.f.d) c1 -= ux_tail[k + 1];
+            }
             ncr[j][k / 2] = pack2(-c0, -c1);
           }
         }
@@ -473,13 +512,25 @@ score_tc16p_kernel(const __grid_constant__ ScoreArgs a, const __grid_constant__ 
       float mpart[RC];
 #pragma unroll
       for (int j = 0; j < RC; ++j) mpart[j] = 0.f;
+      float ncn[RC];  // -|c'_j|^2 (expanded form)
+#pragma unroll
+      for (int j = 0; j < RC; ++j) {
+        uint64_t q = 0ull;
+        if (expand) {
+#pragma unroll
+          for (int k = 0; k < D4 / 2; ++k) q = fma2(ncr[j][k], ncr[j][k], q);
+        }
+        float qx, qy;
+        unpack2(q, qx, qy);
+        ncn[j] = -(qx + qy);
+      }
       for (int sb = 0; sb < nSB; ++sb) {
         const bool last_sb = (sb == nSB - 1);
         const int nJ = min(KPR * min(sb * NACC + NACC, nRB), nJtot);
         for (int J = 0; J < nJ; ++J, ++ita, ++itu) {
           const uint32_t su = itu % NU, pu = (itu / NU) & 1;
-          const uint32_t u = us_addr + su * (uint32_t)(US * 4) + (uint32_t)(op * OPT * D4 * 4);  // this thread's rows
-          const uint32_t al_addr = us_addr + su * (uint32_t)(US * 4) + (uint32_t)((BKH * D4 + op * OPT) * 4);
+          const uint32_t u = us_addr + su * (uint32_t)(US * 4) + (uint32_t)(op * OPT * UR * 4);  // this thread's rows
+          const uint32_t al_addr = us_addr + su * (uint32_t)(US * 4) + (uint32_t)((BKH * D4 + op * OPT) * 4);  // accurate mode
           mbar_wait(smem_u32(&S.full_u[su]), pu);
           const uint32_t sa = ita % SA, pa = (ita / SA) & 1;
           // under the power cap the producers run ahead of the tensor pipe and wait here ~10 % of the time: back off
@@ -490,6 +541,7 @@ score_tc16p_kernel(const __grid_constant__ ScoreArgs a, const __grid_constant__ 
 #pragma unroll
           for (int g = 0; g < OPT / 8; ++g) {  // 8 observations -> one 16-byte chunk (8 halves) of RC rows of the A tile
             float kv[RC][8];
+            float al[8];  // alpha of these 8 observations (the mean rides along in the last super-block)
 #pragma unroll
             for (int b = 0; b < 8 / OB; ++b) {
               uint64_t sq[RC][OB];  // one packed accumulator per (candidate, observation): lanes = even / odd dimensions
@@ -497,32 +549,69 @@ score_tc16p_kernel(const __grid_constant__ ScoreArgs a, const __grid_constant__ 
               for (int j = 0; j < RC; ++j)
 #pragma unroll
                 for (int i = 0; i < OB; ++i) sq[j][i] = 0ull;
+              if (!ACC && expand) {
 #pragma unroll
-              for (int k4 = 0; k4 < D4; k4 += 4) {
+                for (int k4 = 0; k4 < D4; k4 += 4) {
+#pragma unroll
+                  for (int i = 0; i < OB; ++i) {
+                    uint64_t u01, u23;
+                    lds_2x64(u + (uint32_t)(((g * 8 + b * OB + i) * UR + k4) * 4), u01, u23);
+#pragma unroll
+                    for (int j = 0; j < RC; ++j) {
+                      sq[j][i] = fma2(u01, ncr[j][k4 / 2], sq[j][i]);  // -c'.u'
+                      sq[j][i] = fma2(u23, ncr[j][k4 / 2 + 1], sq[j][i]);
+                    }
+                  }
+                }
 #pragma unroll
                 for (int i = 0; i < OB; ++i) {
-                  uint64_t u01, u23;
-                  lds_2x64(u + (uint32_t)(((g * 8 + b * OB + i) * D4 + k4) * 4), u01, u23);
+                  uint64_t na;
+                  asm volatile("ld.shared.b64 %0, [%1];" : "=l"(na) : "r"(u + (uint32_t)(((g * 8 + b * OB + i) * UR + D4) * 4)));
+                  float nun;
+                  unpack2(na, nun, al[b * OB + i]);
 #pragma unroll
                   for (int j = 0; j < RC; ++j) {
-                    const uint64_t d01 = add2(u01, ncr[j][k4 / 2]), d23 = add2(u23, ncr[j][k4 / 2 + 1]);
-                    sq[j][i] = fma2(d01, d01, sq[j][i]);
-                    sq[j][i] = fma2(d23, d23, sq[j][i]);
+                    float sx, sy;
+                    unpack2(sq[j][i], sx, sy);
+                    kv[j][b * OB + i] = ampk * ex2_approx(fmaf(-2.f, sx + sy, ncn[j] + nun));  // gp.py:64, times 2^a
+                  }
+                }
+              } else {
+#pragma unroll
+                for (int k4 = 0; k4 < D4; k4 += 4) {
+#pragma unroll
+                  for (int i = 0; i < OB; ++i) {
+                    uint64_t u01, u23;
+                    lds_2x64(u + (uint32_t)(((g * 8 + b * OB + i) * UR + k4) * 4), u01, u23);
+#pragma unroll
+                    for (int j = 0; j < RC; ++j) {
+                      const uint64_t d01 = add2(u01, ncr[j][k4 / 2]), d23 = add2(u23, ncr[j][k4 / 2 + 1]);
+                      sq[j][i] = fma2(d01, d01, sq[j][i]);
+                      sq[j][i] = fma2(d23, d23, sq[j][i]);
+                    }
+                  }
+                }
+#pragma unroll
+                for (int j = 0; j < RC; ++j)
+#pragma unroll
+                  for (int i = 0; i < OB; ++i) {
+                    float sx, sy;
+                    unpack2(sq[j][i], sx, sy);
+                    kv[j][b * OB + i] = ampk * ex2_approx(-sx - sy);  // gp.py:64, times 2^a
+                  }
+                if constexpr (!ACC) {
+                  if (last_sb) {
+#pragma unroll
+                    for (int i = 0; i < OB; ++i) al[b * OB + i] = lds32(u + (uint32_t)(((g * 8 + b * OB + i) * UR + D4 + 1) * 4));
                   }
                 }
               }
-#pragma unroll
-              for (int j = 0; j < RC; ++j)
-#pragma unroll
-                for (int i = 0; i < OB; ++i) {
-                  float sx, sy;
-                  unpack2(sq[j][i], sx, sy);
-                  kv[j][b * OB + i] = ampk * ex2_approx(-sx - sy);  // gp.py:64, times 2^a
-                }
             }
             if (last_sb) {  // gp.py:66-67: the last super-block visits every K-block, so the mean rides along there
-              const float4 a0 = lds128(al_addr + (uint32_t)(g * 32)), a1 = lds128(al_addr + (uint32_t)(g * 32 + 16));
-              const float al[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+              if constexpr (ACC) {
+                const float4 a0 = lds128(al_addr + (uint32_t)(g * 32)), a1 = lds128(al_addr + (uint32_t)(g * 32 + 16));
+                al[0] = a0.x; al[1] = a0.y; al[2] = a0.z; al[3] = a0.w; al[4] = a1.x; al[5] = a1.y; al[6] = a1.z; al[7] = a1.w;
+              }
 #pragma unroll
               for (int j = 0; j < RC; ++j)
 #pragma unroll
@@ -556,6 +645,52 @@ score_tc16p_kernel(const __grid_constant__ ScoreArgs a, const __grid_constant__ 
   }
 }
 
+// ---- the fast mode's copy of the observations, rebuilt in the caller's workspace by every fast-mode launch (two launches
+// of a few microseconds): rows [d4 coordinates u' = u - mid | -|u'|^2 | alpha | 0 | 0], then mid[d4], then max |u'|^2.
+// mid = midpoint of the observations' bounding box in scaled units: centring keeps the norms - and with them the
+// rounding of the expanded squared distance - as small as a translation can make them.
+__global__ void __launch_bounds__(256) ux_mid_kernel(const bx_factor_t f, float* __restrict__ ux) {
+  __shared__ float smin[8], smax[8];
+  const int k = blockIdx.x, tid = threadIdx.x;
+  float mn = CUDART_INF_F, mx = -CUDART_INF_F;
+  for (int i = tid; i < f.n; i += 256) {
+    const float v = f.d_U[(size_t)i * f.d4 + k];
+    mn = fminf(mn, v);
+    mx = fmaxf(mx, v);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  }
+  if ((tid & 31) == 0) { smin[tid >> 5] = mn; smax[tid >> 5] = mx; }
+  __syncthreads();
+  if (tid == 0) {
+    for (int w = 1; w < 8; ++w) { mn = fminf(mn, smin[w]); mx = fmaxf(mx, smax[w]); }
+    float* tail = ux + (size_t)f.np * (f.d4 + UXP);
+    tail[k] = (k < f.d) ? 0.5f * (mn + mx) : 0.f;
+    if (k == 0) tail[f.d4] = 0.f;  // max |u'|^2, raised by ux_rows_kernel
+  }
+}
+
+__global__ void __launch_bounds__(256) ux_rows_kernel(const bx_factor_t f, float* __restrict__ ux) {
+  const int i = blockIdx.x * 256 + threadIdx.x, ur = f.d4 + UXP;
+  if (i >= f.np) return;
+  float* tail = ux + (size_t)f.np * ur;
+  float* row = ux + (size_t)i * ur;
+  float un = 0.f;
+  for (int k = 0; k < f.d4; ++k) {
+    const float c = (i < f.n && k < f.d) ? f.d_U[(size_t)i * f.d4 + k] - tail[k] : 0.f;  // padding rows meet zero columns of T
+    row[k] = c;
+    un = fmaf(c, c, un);
+  }
+  row[f.d4] = -un;
+  row[f.d4 + 1] = (i < f.n) ? f.d_alpha[i] : 0.f;
+  row[f.d4 + 2] = 0.f;
+  row[f.d4 + 3] = 0.f;
+  atomicMax(reinterpret_cast<unsigned int*>(tail + f.d4), __float_as_uint(un));  // un >= 0: the bit patterns order like the values
+}
+
 static unsigned pair_grid(uint64_t m_count, int sms) {
   const uint64_t ntiles = (m_count + TM - 1) / TM, npairs = (ntiles + 1) / 2;
   const uint64_t max_pairs = (uint64_t)(sms / 2);
@@ -564,7 +699,8 @@ static unsigned pair_grid(uint64_t m_count, int sms) {
 
 template <int D4, int RC, bool ACC>
 static int32_t launch_d4(cudaStream_t s, const ScoreArgs& a, const SamplerPack& sp, const CUtensorMap& mh, const CUtensorMap& ml) {
-  const size_t smem = sizeof(Smem) + sizeof(float) * NU * (BKH * D4 + BKH) + (D4 <= 28 ? sizeof(float) * TM * D4 : 0);
+  const size_t us = ACC ? BKH * D4 + BKH : BKH * (D4 + UXP);  // floats per staged K-block of observations (see the kernel)
+  const size_t smem = sizeof(Smem) + sizeof(float) * NU * us + (share_coords(D4, ACC) ? sizeof(float) * TM * D4 : 0);
   BX_CUDA(cudaFuncSetAttribute(score_tc16p_kernel<D4, RC, ACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int dev = 0, sms = 0;
   BX_CUDA(cudaGetDevice(&dev));
@@ -611,7 +747,9 @@ unsigned score_tc16p_grid(uint64_t m_count) {
   return tc16p::pair_grid(m_count, sms);
 }
 
-bool score_tc16_supported(const bx_factor_t& f) { return f.d_T16hi && f.d_T16lo && f.d4 <= 32; }
+bool score_tc16_supported(const bx_factor_t& f) { return f.d_T16hi && f.d_T16lo && f.d4 <= 32 && f.np <= BX_UX_MAX_NP; }
+
+size_t score_tc16_ux_bytes() { return sizeof(float) * ((size_t)BX_UX_MAX_NP * (32 + tc16p::UXP) + 32 + 4); }
 
 // accurate = false: the fast mode (two row blocks in flight, sums over whole rows inside the tensor core);
 // accurate = true: chunk accumulators folded into TMEM-resident running sums by the epilogue (fp32-level accuracy)
@@ -624,7 +762,19 @@ int32_t launch_score_tc16p(cudaStream_t s, const ScoreArgs& a_in, const SamplerP
   if (rc) return rc;
   rc = tc::make_map_f16(&ml, a.f.d_T16lo, a.f.np, a.f.np, box_rows);
   if (rc) return rc;
-  return accurate ? tc16p::launch_any<true>(s, a, sp, mh, ml) : tc16p::launch_any<false>(s, a, sp, mh, ml);
+  if (accurate) return tc16p::launch_any<true>(s, a, sp, mh, ml);
+  if (!a.ux) {
+    set_error("the fast mode of the fp16 tcgen05 engine needs its workspace");
+    return BX_E_WORKSPACE;
+  }
+  // largest |c'|^2 + |u'|^2 for which the expanded squared distance is used (0: never); see the producers
+  static const float smax = [] { const char* e = getenv("BX_EXPAND_SMAX"); return e ? (float)atof(e) : 64.f; }();
+  a.expand_smax = smax;
+  tc16p::ux_mid_kernel<<<a.f.d4, 256, 0, s>>>(a.f, a.ux);
+  BX_LAUNCH_CHECK();
+  tc16p::ux_rows_kernel<<<(a.f.np + 255) / 256, 256, 0, s>>>(a.f, a.ux);
+  BX_LAUNCH_CHECK();
+  return tc16p::launch_any<false>(s, a, sp, mh, ml);
 }
 
 }  // namespace bx

@@ -440,9 +440,10 @@ def main():
                     "algorithmic_flops_per_launch": fl, "peak_source": peak_src, "ffma_peak_this_run": ffma_peak,
                     "kernel_ms_covers": "front half of sample(): scoring kernel + hand-over pass (fp32 SIMT engine on the "
                                         "cancellation-regime candidates) + top-k merge"}
-        # per sample(): scoring 1 + hand-over pass 1 + top-k merge 1 (+ 1 more merge at N > 1) + start gather 1 + refinement
-        # 5 per round (K*, V chunks, reduce, W chunks, update) + proposal 1; memsets / copies not counted
-        launches_per_step = 3 + (1 if world > 1 else 0) + 1 + 5 * (opt.REFINE_ROUNDS + 1) + 1
+        # per sample(): the fast mode's centred observation copy 2 + scoring 1 + hand-over pass 1 + top-k merge 1 (+ 1 more
+        # merge at N > 1) + start gather 1 + refinement (first K* 1 + 5 per round: V blocks, reduce, W blocks, reduce,
+        # update) + proposal 1; memsets / copies not counted
+        launches_per_step = 2 + 3 + (1 if world > 1 else 0) + 1 + 1 + 5 * (opt.REFINE_ROUNDS + 1) + 1
         line = {
             "metric": "acq candidate-evals/sec", "value": M * args.steps / t_res, "unit": "candidates/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_res / args.steps, "higher_is_better": True,

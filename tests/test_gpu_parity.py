@@ -1116,3 +1116,28 @@ def test_batched_proposals_q():
     assert vals[0] >= vals[1] * (1 - 1e-4) - 1e-9 and vals[1] >= vals[2] * (1 - 1e-4) - 1e-9, vals
     with pytest.raises(ValueError):
         opt.sample(key, st, size=100, q=0)
+
+
+def test_expanded_distance_form(tmp_path):
+    """The fast mode forms the squared distance as |c'|^2 + |u'|^2 - 2 c'.u' (centred coordinates) while the norms are
+    small and as sum (u' - c')^2 otherwise (score_tc16p.cu).  Both forms, forced through BX_EXPAND_SMAX in fresh processes,
+    hold the bar on the candidates the production path lets the fast mode finalise; and the switch is live (the two runs
+    differ in bits)."""
+    import json, os, subprocess, sys
+    worker = os.path.join(os.path.dirname(os.path.abspath(__file__)), "expand_worker.py")
+    res = {}
+    for name, smax in (("direct", "0"), ("expanded", "1e9")):
+        out = str(tmp_path / f"{name}.json")
+        r = subprocess.run([sys.executable, worker, out], env=dict(os.environ, BX_EXPAND_SMAX=smax), capture_output=True, text=True,
+                           timeout=600)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+        res[name] = json.load(open(out))
+    differs = False
+    for key, v in res["expanded"].items():
+        if key.endswith("max_rel_var_err"):
+            assert v < RTOL and res["direct"][key] < RTOL, f"{key}: expanded {v:.3e}, direct {res['direct'][key]:.3e}"
+        if key.endswith("fast:mu_checksum"):
+            differs |= v != res["direct"][key]
+        if key.endswith("fast_tier_fraction"):
+            assert v > 0.01, f"{key}: the fixture leaves the fast tier nothing to finalise"
+    assert differs, "BX_EXPAND_SMAX did not change a bit: the expanded form never ran"
