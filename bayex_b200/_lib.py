@@ -52,6 +52,8 @@ SIGNATURES = {
     "bx_fit_adamw": (_i32, [_vp, _vp, _i32, _i32, _vp, _f32, _i32, _vp, _vp, _sz, _i32, _vp]),
     "bx_fit_adamw_batch": (_i32, [_vp, _vp, _i32, _i32, _vp, _i32, _f32, _i32, _vp, _vp, _sz, _vp]),
     "bx_factor_build": (_i32, [_vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "bx_factor_append_workspace_bytes": (_sz, [_i32]),
+    "bx_factor_append": (_i32, [C.POINTER(FactorT), _vp, _vp, _vp, _sz, _vp]),
     "bx_score_workspace_bytes": (_sz, [_u64]),
     "bx_score_points": (_i32, [C.POINTER(FactorT), _vp, _u64, _i32, _f32, _f32, _vp, _vp, _vp, _vp, _u64, _vp, _sz, _vp]),
     "bx_score_generated": (_i32, [C.POINTER(FactorT), _key, C.POINTER(DimT), _u64, _u64, _i32, _f32, _f32, _vp, _vp,

@@ -562,6 +562,91 @@ __global__ void add_inplace_kernel(float* __restrict__ x, const float* __restric
   if (i < n) x[i] += dx[i];
 }
 
+// alpha = T^T (T yc), quad = |T yc|^2, NLML; with `refine` (posterior build / append: the alpha the scoring kernels read, the
+// fit loop's gradient does not need it) one step of iterative refinement on alpha.  tmp: 3 np floats.
+static int32_t launch_alpha_tail(cudaStream_t a, const float* T, const float* U, float* alpha, float* hyp, int n, int np, int d4,
+                                 const float* yc, float* v, float* tmp, const float* logdet_part, int nb, const int* status,
+                                 bool refine) {
+  int32_t rc = trmv_lower(a, T, np, np, yc, v);
+  if (rc) return rc;
+  rc = trmv_lower_t(a, T, np, np, v, alpha);
+  if (rc) return rc;
+  nlml_kernel<<<1, 256, 0, a>>>(v, np, logdet_part, nb, n, hyp, status);
+  BX_LAUNCH_CHECK();
+  static const bool refine_alpha = [] { const char* e = getenv("BX_ALPHA_REFINE"); return !e || atoi(e) != 0; }();
+  if (refine && refine_alpha) {
+    float *res = tmp, *tv = tmp + np, *dx = tmp + 2 * (size_t)np;  // (the fit workspace's TMP is free once T is complete)
+    const size_t rsm = (2 * 32 * (d4 + 1) + 32) * sizeof(float);
+    gram_residual_kernel<<<np / 32, 256, rsm, a>>>(U, n, d4, hyp, yc, alpha, res);
+    BX_LAUNCH_CHECK();
+    rc = trmv_lower(a, T, np, np, res, tv);
+    if (rc) return rc;
+    rc = trmv_lower_t(a, T, np, np, tv, dx);
+    if (rc) return rc;
+    add_inplace_kernel<<<(np + 255) / 256, 256, 0, a>>>(alpha, dx, np);
+    BX_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+// ---- appending one observation to a built factor at unchanged hypers (optimizer.py:261-269) ---------------
+// The Gram matrix grows by one bordered row, K' = [K k; k^T kappa], so its factor does too:
+//   L' = [L 0; l^T lambda],  l = L^-1 k = T k,  lambda^2 = kappa - |l|^2,   T' = L'^-1 = [T 0; -(l^T T) / lambda   1 / lambda]
+// - two triangular matrix-vector products (O(n^2)) instead of Gram + Cholesky + inverse (O(n^3)).
+//
+// U[n] = x_new * scale, kvec[j] = amp 2^(-|U_j - U_n|^2) for j < n (the arithmetic of gram_kernel, entry by entry), 0 on the padding.
+__global__ void __launch_bounds__(256) append_cross_kernel(const float* __restrict__ x_new, int n, int d, int np, int d4,
+                                                           const float* __restrict__ scale, const float* __restrict__ hyp,
+                                                           float* U, float* __restrict__ kvec) {
+  __shared__ float un[BX_MAX_D + 4];
+  for (int k = threadIdx.x; k < d4; k += 256) un[k] = (k < d) ? x_new[k] * scale[k] : 0.f;
+  __syncthreads();
+  if (blockIdx.x == 0)
+    for (int k = threadIdx.x; k < d4; k += 256) U[(size_t)n * d4 + k] = un[k];  // row n is read by nobody in this launch
+  const int j = blockIdx.x * 256 + threadIdx.x;
+  if (j >= np) return;
+  float v = 0.f;
+  if (j < n) {
+    float s = 0.f;
+    for (int k = 0; k < d4; ++k) {
+      const float df = un[k] - U[(size_t)j * d4 + k];
+      s = fmaf(df, df, s);
+    }
+    v = hyp[HYP_AMP] * exp2f(-s);
+  }
+  kvec[j] = v;
+}
+// lambda, row n of T, log det.  One block; |l|^2 is accumulated in fp64 in a fixed order (lambda^2 = kappa - |l|^2 cancels
+// to the posterior variance at the new point plus the noise, exactly as the last pivot of a Cholesky does).
+__global__ void __launch_bounds__(1024) append_row_kernel(float* T, int n, int np, const float* __restrict__ l,
+                                                          const float* __restrict__ wv, const float* hyp, float* logdet_out,
+                                                          int* status) {
+  __shared__ double red[32];
+  __shared__ float lam_s;
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < n; i += 1024) acc = fma((double)l[i], (double)l[i], acc);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double ss = 0.0;
+    for (int w = 0; w < 32; ++w) ss += red[w];
+    const float kappa = hyp[HYP_AMP] + (hyp[HYP_NOISE] + kJitter);  // the diagonal entry gram_kernel writes
+    const double lam2 = (double)kappa - ss;
+    const bool bad = !(lam2 > 0.0) || !isfinite(lam2);
+    const float lam = (float)sqrt(lam2);  // NaN on a bad pivot: propagates like the reference's cholesky (gp.py:48)
+    lam_s = lam;
+    logdet_out[0] = hyp[HYP_LOGDET] + logf(lam);
+    status[0] = (bad || hyp[HYP_STATUS] != 0.f) ? 1 : 0;
+  }
+  __syncthreads();
+  const float inv = 1.f / lam_s;
+  float* row = T + (size_t)n * np;
+  for (int j = threadIdx.x; j < np; j += 1024) row[j] = (j < n) ? -wv[j] * inv : (j == n ? inv : 0.f);
+}
+
+
 int32_t launch_factor(cudaStream_t s, const float* d_X, const float* d_y, int n, int d, const float* d_raw, FitWs& w,
                       float* T_out, float* U_out, float* alpha_out, float* scale_out, float* hyp_out) {
   float* T = T_out ? T_out : w.A;
@@ -592,25 +677,8 @@ int32_t launch_factor(cudaStream_t s, const float* d_X, const float* d_y, int n,
     BX_CUDA(cudaEventRecord(w.la->ev_bulk, s));
     BX_CUDA(cudaStreamWaitEvent(a, w.la->ev_bulk, 0));
   }
-  rc = trmv_lower(a, T, np, np, w.yc, w.v);
+  rc = launch_alpha_tail(a, T, U, alpha, hyp, n, np, d4, w.yc, w.v, w.TMP, w.logdet_part, w.nb, w.status, alpha_out != nullptr);
   if (rc) return rc;
-  rc = trmv_lower_t(a, T, np, np, w.v, alpha);
-  if (rc) return rc;
-  nlml_kernel<<<1, 256, 0, a>>>(w.v, np, w.logdet_part, w.nb, n, hyp, w.status);
-  BX_LAUNCH_CHECK();
-  static const bool refine_alpha = [] { const char* e = getenv("BX_ALPHA_REFINE"); return !e || atoi(e) != 0; }();
-  if (alpha_out && refine_alpha) {  // the posterior the scoring kernels read (the fit loop's gradient does not need it)
-    float *res = w.TMP, *tv = w.TMP + np, *dx = w.TMP + 2 * (size_t)np;  // TMP is free once T is complete
-    const size_t rsm = (2 * 32 * (d4 + 1) + 32) * sizeof(float);
-    gram_residual_kernel<<<np / 32, 256, rsm, a>>>(U, n, d4, hyp, w.yc, alpha, res);
-    BX_LAUNCH_CHECK();
-    rc = trmv_lower(a, T, np, np, res, tv);
-    if (rc) return rc;
-    rc = trmv_lower_t(a, T, np, np, tv, dx);
-    if (rc) return rc;
-    add_inplace_kernel<<<(np + 255) / 256, 256, 0, a>>>(alpha, dx, np);
-    BX_LAUNCH_CHECK();
-  }
   if (w.la) BX_CUDA(cudaEventRecord(w.la->ev_chain, a));
   return 0;
 }
@@ -876,6 +944,74 @@ extern "C" int32_t bx_factor_build(const float* d_X, const float* d_y, int32_t n
   BX_LAUNCH_CHECK();
   split_T_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(d_T, w.np, reinterpret_cast<__half*>(d_T16hi),
                                                                reinterpret_cast<__half*>(d_T16lo), amax, d_hyp);
+  BX_LAUNCH_CHECK();
+  return 0;
+}
+
+namespace {
+struct AppendWs {
+  float *kvec, *l, *wv, *yc, *v, *tmp, *logdet;  // tmp: 3 np floats
+  int* status;                          // [0] status, [1] max|T| bits
+  size_t bytes;
+};
+AppendWs carve_append_ws(void* base, int np) {
+  AppendWs w{};
+  size_t off = 0;
+  auto take = [&](size_t nfloat) {
+    float* p = base ? reinterpret_cast<float*>(reinterpret_cast<char*>(base) + off) : nullptr;
+    off += (nfloat * sizeof(float) + 255) / 256 * 256;
+    return p;
+  };
+  w.kvec = take(np); w.l = take(np); w.wv = take(np); w.yc = take(np); w.v = take(np); w.tmp = take(3 * (size_t)np);
+  w.logdet = take(1);
+  w.status = reinterpret_cast<int*>(take(2));
+  w.bytes = off;
+  return w;
+}
+}  // namespace
+
+extern "C" size_t bx_factor_append_workspace_bytes(int32_t np) {
+  if (np <= 0 || np % BX_TILE) return 0;
+  return carve_append_ws(nullptr, np).bytes;
+}
+
+extern "C" int32_t bx_factor_append(const bx_factor_t* f, const float* d_x_new, const float* d_y, void* d_ws, size_t ws_bytes,
+                                    void* stream) {
+  BX_CHECK_ARG(f && d_x_new && d_y && d_ws, BX_E_ARG, "null pointer argument");
+  BX_CHECK_ARG(f->d_U && f->d_T && f->d_alpha && f->d_scale && f->d_hyp, BX_E_ARG, "incomplete factor");
+  BX_CHECK_ARG((f->d_T16hi == nullptr) == (f->d_T16lo == nullptr), BX_E_ARG, "T16hi and T16lo must be given together");
+  BX_CHECK_ARG(f->n > 0 && f->d > 0 && f->d <= BX_MAX_D && f->np % BX_TILE == 0 && f->d4 == round_up(f->d, 4), BX_E_ARG,
+               "malformed factor (n=%d np=%d d=%d d4=%d)", f->n, f->np, f->d, f->d4);
+  BX_CHECK_ARG(f->n < f->np, BX_E_RANGE, "no free row: n=%d fills the padded size np=%d (rebuild the factor with bx_factor_build)",
+               f->n, f->np);
+  BX_CHECK_ARG(ws_bytes >= bx_factor_append_workspace_bytes(f->np), BX_E_WORKSPACE, "workspace too small: %zu < %zu", ws_bytes,
+               bx_factor_append_workspace_bytes(f->np));
+  cudaStream_t s = (cudaStream_t)stream;
+  const int n = f->n, np = f->np, d = f->d, d4 = f->d4;
+  AppendWs w = carve_append_ws(d_ws, np);
+  float *T = const_cast<float*>(f->d_T), *U = const_cast<float*>(f->d_U), *alpha = const_cast<float*>(f->d_alpha),
+        *hyp = const_cast<float*>(f->d_hyp);
+  append_cross_kernel<<<(np + 255) / 256, 256, 0, s>>>(d_x_new, n, d, np, d4, f->d_scale, hyp, U, w.kvec);
+  BX_LAUNCH_CHECK();
+  int32_t rc = trmv_lower(s, T, np, np, w.kvec, w.l);  // l = T k   (rows >= n of T are zero)
+  if (rc) return rc;
+  rc = trmv_lower_t(s, T, np, np, w.l, w.wv);          // T^T l
+  if (rc) return rc;
+  append_row_kernel<<<1, 1024, 0, s>>>(T, n, np, w.l, w.wv, hyp, w.logdet, w.status);
+  BX_LAUNCH_CHECK();
+  // the mean of y moved: centre again, alpha and the NLML from the grown factor
+  center_y_kernel<<<1, 1024, 0, s>>>(d_y, n + 1, np, w.yc, hyp);
+  BX_LAUNCH_CHECK();
+  rc = launch_alpha_tail(s, T, U, alpha, hyp, n + 1, np, d4, w.yc, w.v, w.tmp, w.logdet, 1, w.status, true);
+  if (rc) return rc;
+  // the new row may move max|T|, i.e. the power-of-two scale of the fp16 copies: split again (O(n^2) bytes, no arithmetic)
+  const size_t tot = (size_t)np * np;
+  unsigned int* amax = reinterpret_cast<unsigned int*>(w.status) + 1;
+  BX_CUDA(cudaMemsetAsync(amax, 0, sizeof(unsigned int), s));
+  zero_pad_absmax_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(T, n + 1, np, amax);
+  BX_LAUNCH_CHECK();
+  split_T_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(T, np, reinterpret_cast<__half*>(const_cast<void*>(f->d_T16hi)),
+                                                               reinterpret_cast<__half*>(const_cast<void*>(f->d_T16lo)), amax, hyp);
   BX_LAUNCH_CHECK();
   return 0;
 }

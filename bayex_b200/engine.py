@@ -169,15 +169,43 @@ class Posterior:
                                       C.c_void_p(self.stream.cuda_stream)),
                   "bx_factor_build")
         self._set_factor()
+        self._warn_if_not_pd()
+        return self
+
+    def _warn_if_not_pd(self):
         # gp.py:48: the reference's cholesky returns NaN silently on a non-PD Gram matrix; so do the kernels (hyp[7] records
         # it).  Surface it as a warning - never an exception, the NaNs propagate exactly as they do upstream.
         rc = lib.bx_check_status(_ptr(self._bufs["hyp"]), C.c_void_p(self.stream.cuda_stream))
         if rc == _lib.E_NOTPD:
             import warnings
             warnings.warn("bayex_b200: " + lib.bx_last_error().decode("utf-8", "replace") + "; posterior values are NaN",
-                          RuntimeWarning, stacklevel=2)
+                          RuntimeWarning, stacklevel=3)
         elif rc != 0:
             check(rc, "bx_check_status")
+
+    def can_append(self) -> bool:
+        """A built factor with a free padding row (np = roundup(n, 128)): ``append`` applies."""
+        return self.factor is not None and self.n < self.np_
+
+    def append(self, x_new, y_new):
+        """One more observation at UNCHANGED hypers (optimizer.py:261-269): the factor grows by one
+        bordered row in O(n^2) - two triangular matrix-vector products - instead of the O(n^3) rebuild of gp.py:46-49."""
+        if not self.can_append():
+            raise ValueError("append() needs a built factor with a free padding row; rebuild the posterior instead")
+        x_new = np.ascontiguousarray(x_new, dtype=np.float32).reshape(-1)
+        if x_new.size != self.d:
+            raise ValueError(f"the new point has {x_new.size} coordinates for {self.d} input dimensions")
+        nbytes = lib.bx_factor_append_workspace_bytes(self.np_)
+        ws = _workspace(self.dev, nbytes)
+        with on_stream(self.stream, self.dev):
+            xn = torch.from_numpy(x_new).to(self.dev)
+            self.X = torch.cat([self.X, xn[None]], dim=0)
+            self.y = torch.cat([self.y, torch.tensor([float(np.float32(y_new))], dtype=torch.float32, device=self.dev)])
+            check(lib.bx_factor_append(C.byref(self.factor), _ptr(xn), _ptr(self.y), _ptr(ws), nbytes,
+                                       C.c_void_p(self.stream.cuda_stream)), "bx_factor_append")
+        self.n += 1
+        self._set_factor()
+        self._warn_if_not_pd()
         return self
 
     def _alloc_bufs(self):

@@ -147,6 +147,16 @@ class Optimizer:
             parts.append(np.asarray(v, dtype=np.float32).tobytes())
         return tuple(parts)
 
+    def _cached_posterior(self, state: OptimizerState):
+        """The factor cached for exactly this state (observations and hypers), or None - never builds one."""
+        ident = self._identity(state)
+        hit = self._cache.get("ident")
+        if hit is not None and hit[0] == ident:
+            return hit[1]
+        xs, ys_signed, mask = self._arrays(state.params, state.ys, state.mask)
+        post = self._cache.get(self._digest(xs, ys_signed, mask, engine.raw_vector(state.gp_params, xs.shape[1])))
+        return post if (post is not None and post.factor is not None) else None
+
     def posterior(self, state: OptimizerState) -> engine.Posterior:
         """The GPU-resident factor for ``state`` (cached; rebuilt if the state came from elsewhere)."""
         ident = self._identity(state)
@@ -367,8 +377,17 @@ class Optimizer:
         return OptimizerState(params=params, ys=ys, best_score=opt_state.best_score, best_params=opt_state.best_params,
                               mask=mask, gp_params=opt_state.gp_params)
 
-    def fit(self, opt_state: OptimizerState, y, new_params) -> OptimizerState:
-        """optimizer.py:242-280: insert the observation at the first free slot and refit (warm start)."""
+    def fit(self, opt_state: OptimizerState, y, new_params, *, trainsteps: int = 100) -> OptimizerState:
+        """optimizer.py:242-280: insert the observation at the first free slot and refit (warm start).
+
+        ``trainsteps`` (keyword-only; the reference always runs the 100 AdamW steps of gp.py:96): with ``trainsteps=0`` the
+        hyper-parameters are kept and the cached factor of ``opt_state`` takes the new observation as one bordered row -
+        an O(n^2) update (``bx_factor_append``) instead of the O(n^3) rebuild; every rank of a
+        multi-GPU job applies it to its own copy, so nothing is broadcast.  With any hyper-parameter step the Gram matrix
+        changes as a whole and the factor is rebuilt, as upstream."""
+        if trainsteps < 0:
+            raise ValueError("trainsteps must be non-negative")
+        prior_post = self._cached_posterior(opt_state) if trainsteps == 0 else None
         opt_state = self.expand(opt_state)
         slot = int(np.argmin(opt_state.mask))  # :261 first False
         last = np.arange(len(opt_state.mask)) == slot
@@ -381,7 +400,10 @@ class Optimizer:
             params[k] = pv.astype(np.float32) if pv.dtype == np.float64 else pv
         xs, ys_signed, maskb = self._arrays(params, ys, mask)
         raw0 = engine.raw_vector(opt_state.gp_params, xs.shape[1])
-        post = self._make_posterior(xs, ys_signed, maskb, raw0, fit_steps=100)  # :269
+        if prior_post is not None and prior_post.can_append():
+            post = prior_post.append(xs[slot], ys_signed[slot])  # hypers kept: the factor grows by one row
+        else:
+            post = self._make_posterior(xs, ys_signed, maskb, raw0, fit_steps=trainsteps)  # :269
         raw = self._remember(xs, ys_signed, maskb, post)
         best_score = float(np.max(ys_signed[maskb]))  # :271
         best_idx = int(np.argmax(np.where(maskb, ys_signed, -np.inf)))  # :272

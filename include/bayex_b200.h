@@ -140,6 +140,17 @@ int32_t bx_factor_build(const float* d_X, const float* d_y, int32_t n, int32_t d
                         float* d_T, void* d_T16hi, void* d_T16lo, float* d_alpha,
                         float* d_scale, float* d_hyp, void* d_ws, size_t ws_bytes, void* stream);
 
+/* Append one observation to a built factor at UNCHANGED hyper-parameters - SURVEY 8(f) rank 1, the incremental refit of
+ * optimizer.py:261-269 (`_fit` inserts one point; gp.py:46-49 then rebuilds and refactorises the whole Gram matrix).  The
+ * matrix only grows by one bordered row, so its inverse factor does too: l = T k, lambda^2 = kappa - |l|^2,
+ * T' = [T 0; -(l^T T)/lambda  1/lambda] - O(n^2) instead of O(n^3).  `f` is a factor bx_factor_build filled, with a free
+ * padding row (f->n < f->np, else BX_E_RANGE: rebuild); d_x_new [d] raw coordinates of the new point; d_y [f->n + 1] all
+ * observed values, the new one last (the mean of gp.py:43 moves, so alpha = K^-1 (y - mean) is recomputed in full, with the
+ * same refinement step as the build).  Rewrites row f->n of U and T, alpha, hyp (mean, NLML, log det, status, T16 scale) and
+ * the fp16 copies in place; afterwards the factor is valid with n = f->n + 1 (the caller bumps its copy of the struct). */
+size_t bx_factor_append_workspace_bytes(int32_t np);
+int32_t bx_factor_append(const bx_factor_t* f, const float* d_x_new, const float* d_y, void* d_ws, size_t ws_bytes, void* stream);
+
 #define BX_POINTS_TC_MIN 65536 /* bx_score_points: point sets at least this large use the tcgen05 path if the factor has its fp16 copies */
 
 /* Hand-over workspace of the two-tier production path (bytes): the fp16 tcgen05 engine lists the candidates whose variance is

@@ -69,3 +69,19 @@ def test_batched_fit_rejects_bad_arguments_without_a_gpu():
     slot = _lib.lib.bx_fit_workspace_bytes(100, 3)
     assert f(fake, fake, 100, 3, fake, 4, 1e-3, 10, None, fake, 4 * slot - 1, None) == -3
     assert b"workspace" in _lib.lib.bx_last_error()
+
+
+def test_factor_append_rejects_bad_arguments_without_a_gpu():
+    """bx_factor_append validates before touching the device: null pointers, a factor without a free padding row (the caller
+    must rebuild), a workspace that is too small."""
+    import ctypes
+    from bayex_b200 import _lib
+    f, ws = _lib.lib.bx_factor_append, _lib.lib.bx_factor_append_workspace_bytes
+    assert ws(0) == 0 and ws(100) == 0 and ws(128) >= 8 * 128 * 4
+    fake = 256  # never dereferenced: every call below fails validation first
+    fac = lambda n, np_: _lib.FactorT(n, np_, 3, 4, fake, fake, 0, 0, fake, fake, fake)
+    assert f(ctypes.byref(fac(100, 128)), None, fake, fake, 1 << 20, None) == _lib.E_ARG
+    assert f(ctypes.byref(fac(128, 128)), fake, fake, fake, 1 << 20, None) == _lib.E_RANGE
+    assert b"no free row" in _lib.lib.bx_last_error()
+    assert f(ctypes.byref(fac(100, 128)), fake, fake, fake, ws(128) - 1, None) == _lib.E_WORKSPACE
+    assert f(ctypes.byref(_lib.FactorT(100, 128, 3, 8, fake, fake, 0, 0, fake, fake, fake)), fake, fake, fake, 1 << 20, None) == _lib.E_ARG

@@ -1141,3 +1141,120 @@ def test_expanded_distance_form(tmp_path):
         if key.endswith("fast_tier_fraction"):
             assert v > 0.01, f"{key}: the fixture leaves the fast tier nothing to finalise"
     assert differs, "BX_EXPAND_SMAX did not change a bit: the expanded form never ran"
+
+
+# ---- incremental refit: one bordered row instead of a rebuild ------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,d,nadd", [(20, 2, 3), (100, 3, 8), (500, 6, 12), (1000, 6, 5), (2040, 10, 8), (120, 4, 8)])
+def test_factor_append_matches_oracle_and_rebuild(n, d, nadd):
+    """``Posterior.append`` (bx_factor_append: l = T k, lambda^2 = kappa - |l|^2, one new row of T, alpha recomputed) after
+    ``nadd`` observations one by one against the oracle's posterior of all n + nadd observations - the same pointwise bar as
+    a factor built from scratch - for the fp32 arrays (SIMT engine on explicit points) and for the fp16 copies (production
+    path on generated candidates); NLML, mean of y and status follow.  Every second appended point sits 2e-3 away from an
+    earlier observation (the pivot lambda^2 cancels to noise + variance there).  Shapes are those of
+    test_score_points_vs_oracle's families: appended and rebuilt factors are equally accurate on every shape tried
+    (scripts/dev/diag_append.py, profiles/r2y_diag_append.txt)."""
+    N = n + nadd
+    X, Y, raw, P = make_problem(N, d, seed=11 * n + d)
+    rng = np.random.default_rng(n)
+    X[n::2] = X[:len(X[n::2])] + rng.normal(0, 2e-3, X[n::2].shape).astype(np.float32)
+    Y[n::2] = (np.sin(3 * X[n::2].sum(1)) + 0.1 * rng.standard_normal(len(X[n::2]))).astype(np.float32)
+    post = engine.Posterior(X[:n], Y[:n], raw, want_tc=True).build()
+    for a in range(n, N):
+        if not post.can_append():
+            break
+        post.append(X[a], Y[a])
+    assert post.n == N and post.factor.n == N
+    mask = np.ones(N)
+    f64, f32 = ogp.Factor(P, X, Y, mask, np.float64), ogp.Factor(P, X, Y, mask, np.float32)
+    hyp = post.hyp()
+    assert hyp[7] == 0.0
+    assert np.isclose(hyp[2], Y.mean(dtype=np.float64), rtol=1e-6, atol=1e-7)
+    nl64 = float(f64.nlml())
+    assert abs(hyp[4] - nl64) <= max(RTOL * abs(nl64), 4 * abs(float(f32.nlml()) - nl64)), (hyp[4], nl64)
+    # explicit points, fp32 arrays
+    M = 3000
+    cand = rng.uniform(-0.1, 1.1, (M, d)).astype(np.float32)
+    cand[:nadd] = X[n:] + 1e-3
+    cand[nadd:2 * nadd] = X[n:]
+    for acq in ("EI", "LCB"):
+        ystar = bayex.acq.ystar_for(acq, Y, mask)
+        out = post.score_points(cand, acq=acq, param=bayex.acq.DEFAULT_PARAM[acq], ystar=ystar)
+        mu64, sd64, var64 = f64.predict(cand.astype(np.float64), return_var=True)
+        mu32, sd32, var32 = f32.predict(cand, return_var=True)
+        assert_close(out["mu"].cpu().numpy(), mu64, mu32, what="mean after append", floor=mean_sum_floor(f64, cand))
+        got_var = out["sigma"].cpu().numpy().astype(np.float64) ** 2
+        assert_close(got_var, np.maximum(var64, 1e-10), np.maximum(var32, 1e-10), what="var after append")
+        check_acq(acq, out["acq"].cpu().numpy(), out["mu"].cpu().numpy(), out["sigma"].cpu().numpy(), mu64, sd64, mu32, sd32, Y, mask)
+    # generated candidates, production path (reads T16hi / T16lo and the re-derived power-of-two scale)
+    dom = {f"x{i}": bayex.domain.Real(-0.1, 1.1) for i in range(d)}
+    dims = engine.dims_array(dom)
+    key, Mg = prng.key(N), 20000
+    ystar = bayex.acq.ystar_for("EI", Y, mask)
+    v_q, b_q = post.score_generated(key, dims, 0, Mg, "EI", 0.01, ystar, engine=_lib.ENGINE_AUTO)
+    gen = engine.threefry_fill(key, dims, d, 0, Mg).cpu().numpy()
+    mu64, sd64 = f64.predict(gen.astype(np.float64))
+    mu32, sd32 = f32.predict(gen)
+    a64, tol = acq_tolerance("EI", mu64, sd64, mu32, sd32, Y, mask)
+    err = np.abs(v_q.cpu().numpy().astype(np.float64) - a64)
+    assert np.all(err <= tol), f"production path after append: {np.sum(err > tol)}/{Mg} outside tolerance, worst {err.max():.3e}"
+    # and the rebuilt factor of the same observations says the same thing within the two factors' own tolerances
+    full = engine.Posterior(X, Y, raw, want_tc=True).build()
+    v_f, b_f = full.score_generated(key, dims, 0, Mg, "EI", 0.01, ystar, engine=_lib.ENGINE_AUTO)
+    assert np.all(np.abs(v_f.cpu().numpy().astype(np.float64) - v_q.cpu().numpy()) <= 2 * tol)
+    if not post.can_append():
+        with pytest.raises(ValueError):
+            post.append(X[0], Y[0])
+        rc = _lib.lib.bx_factor_append(_lib.C.byref(post.factor), None, None, None, 0, None)
+        assert rc == _lib.E_ARG
+
+
+@pytest.mark.gpu
+def test_fit_with_kept_hypers_appends_to_the_cached_factor():
+    """``Optimizer.fit(..., trainsteps=0)``: hypers unchanged, the cached factor takes the observation as one row (no rebuild:
+    the Posterior object survives), the state is what the reference's _fit leaves apart from gp_params (optimizer.py:261-276),
+    and the next sample() scores with a posterior that matches the oracle's for the grown state; a cold optimiser given the
+    same state rebuilds from scratch and proposes the same point."""
+    dom, odomn = both_spaces("mixed10")
+    opt = bayex.Optimizer(dom, acq="EI", maximize=True)
+    rng = np.random.default_rng(5)
+    n0 = 118
+    P0 = {k: (rng.integers(-10, 11, n0) if getattr(v, "is_integer", False) else rng.uniform(-5, 5, n0).astype(np.float32))
+          for k, v in dom.items()}
+    f = lambda p: -sum((np.asarray(p[k], np.float64) - 1.0) ** 2 for k in dom) / 50.0
+    st = opt.init(f(P0).astype(np.float32), P0)
+    prev = opt.posterior(st)
+    key = bayex.random.key(11)
+    for step in range(12):  # 118 -> 130 observations: crosses np = 128 (no free row there: that one fit rebuilds)
+        count = int(st.mask.sum())
+        new = opt.sample(bayex.random.fold_in(key, step), st, size=4096)
+        st2 = opt.fit(st, float(f({k: v[0] for k, v in new.items()})), new, trainsteps=0)
+        for a, b in zip(st.gp_params, st2.gp_params):
+            assert np.array_equal(np.asarray(a), np.asarray(b))
+        assert int(st2.mask.sum()) == count + 1
+        cur = opt.posterior(st2)
+        assert cur.n == count + 1
+        assert (cur is prev) == (count % 128 != 0), "the cached factor is extended in place while it has a free row"
+        prev, st = cur, st2
+    assert st.best_score == float(np.max(st.ys[st.mask]))
+    # the grown posterior against the oracle
+    new, info = opt.sample(bayex.random.key(99), st, size=8192, details=True)
+    space = odom.ParamSpace(odomn)
+    cand = space.to_array(space.sample_params(prng.key(99), (8192,)))
+    xs = space.to_array({k: st.params[k] for k in dom})
+    ys = np.asarray(st.ys, np.float32)
+    gp = ogp.GPParams(*st.gp_params)
+    f64, f32 = ogp.Factor(gp, xs, ys, st.mask, np.float64), ogp.Factor(gp, xs, ys, st.mask, np.float32)
+    mu64, sd64 = f64.predict(cand.astype(np.float64))
+    mu32, sd32 = f32.predict(cand)
+    a64, tol = acq_tolerance("EI", mu64, sd64, mu32, sd32, ys, st.mask)
+    err = np.abs(info["acq_vals"].astype(np.float64) - a64)
+    assert np.all(err <= tol), f"{np.sum(err > tol)} outside tolerance, worst {err.max():.3e}"
+    cold = bayex.Optimizer(dom, acq="EI", maximize=True)
+    new_c, info_c = cold.sample(bayex.random.key(99), st, size=8192, details=True)
+    assert np.all(np.abs(info_c["acq_vals"].astype(np.float64) - info["acq_vals"]) <= 2 * tol)
+    # the default stays the reference's: 100 AdamW steps move the hypers
+    st3 = opt.fit(st, 0.0, new)
+    assert not np.array_equal(np.asarray(st3.gp_params.lengthscale), np.asarray(st.gp_params.lengthscale))
+    with pytest.raises(ValueError):
+        opt.fit(st, 0.0, new, trainsteps=-1)
