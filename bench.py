@@ -438,8 +438,8 @@ def main():
                     "traffic": TRAFFIC_BYTES.get((args.workload, M)), "kernel_ms": kern_ms_avg,
                     "kernel_ms_per_rank": kern_ms_ranks,
                     "algorithmic_flops_per_launch": fl, "peak_source": peak_src, "ffma_peak_this_run": ffma_peak,
-                    "kernel_ms_covers": "front half of sample(): scoring kernel + hand-over pass (fp32 SIMT engine on the "
-                                        "cancellation-regime candidates) + top-k merge"}
+                    "kernel_ms_covers": "front half of sample(): scoring kernel (fast mode) + hand-over pass (accurate mode of the "
+                                        "same kernel on the cancellation-regime candidates) + top-k merge"}
         # per sample(): the fast mode's centred observation copy 2 + scoring 1 + hand-over pass 1 + top-k merge 1 (+ 1 more
         # merge at N > 1) + start gather 1 + refinement (first K* 1 + 5 per round: V blocks, reduce, W blocks, reduce,
         # update) + proposal 1; memsets / copies not counted
