@@ -37,7 +37,7 @@ WORKLOADS = {
 
 # dram__bytes_read.sum + dram__bytes_write.sum of the scoring kernel from the committed `ncu --set full` capture
 # (profiles/), keyed by (workload, candidates); None where no capture exists for that size.
-TRAFFIC_BYTES = {("c3", 1 << 24): 39638272}  # profiles/r2l_score_tc16p_ncu_full_c3.csv (37.57 MB read + 2.07 MB written: no per-candidate vector any more)
+TRAFFIC_BYTES = {("c3", 1 << 24): 39168000}  # profiles/r2z_score_tc16p_ncu_full_c3.csv (37.89 MB read + 1.28 MB written: no per-candidate vector any more)
 
 
 def ackley(u):
