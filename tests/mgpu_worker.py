@@ -4,7 +4,8 @@
     python tests/mgpu_worker.py OUT_PREFIX                             (single process, no process group)
 
 Every rank writes OUT_PREFIX.rank<r>.json: proposals (all four acquisitions, ragged candidate counts, fewer candidates than
-ranks), the merged top-k indices, the refined points and the winner of a restart sweep."""
+ranks), the merged top-k indices, the refined points, a fit() with and without hyper-parameter steps and the winner of a
+restart sweep."""
 import json
 import os
 import sys
@@ -53,6 +54,10 @@ def main():
     st2 = opt.fit(st2, 0.5, {f"x{i}": np.array([X[100, i]], np.float32) for i in range(d)})
     res["after_fit"] = {k: float(v[0]) for k, v in opt.sample(bayex.random.key(3), st2, size=50_000).items()}
     res["after_fit_raw"] = [float(np.ravel(v)[j]) for v in st2.gp_params for j in range(np.size(v))]
+    # hypers kept: every rank extends its own copy of the factor by one bordered row (no broadcast), same bits everywhere
+    st3 = opt.fit(st2, 0.25, {f"x{i}": np.array([X[101, i]], np.float32) for i in range(d)}, trainsteps=0)
+    assert opt.posterior(st3).n == 66
+    res["after_append"] = {k: float(v[0]) for k, v in opt.sample(bayex.random.key(4), st3, size=50_000).items()}
     # BASELINE config 5 in miniature: restart sweep sharded over the ranks
     raws = np.concatenate([rng.uniform(-8, -2, (6, 1)), rng.uniform(-1, 1, (6, 1 + d))], axis=1).astype(np.float32)
     best, idx, table = bayex.gp.posterior_fit_restarts(Y[:300], X[:300], np.ones(300, bool), raws, trainsteps=20)
