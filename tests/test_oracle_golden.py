@@ -268,3 +268,26 @@ def test_lbfgs_restatement_on_a_quadratic_and_in_the_reference_call_pattern():
     _, qk = opt.sample(key, st, size=2000, refine="lbfgs_quirk", n_starts=8, details=True)
     assert np.all(np.isfinite(qk["optimized"])) and np.all(np.abs(qk["optimized"]) <= 1e6)
     assert qk["all_vals"][qk["chosen"]] >= ident["acq_vals"].max() - 1e-9
+
+
+def test_bordered_row_update_of_the_inverse_factor():
+    """The identity behind bx_factor_append, checked in float64 on the oracle's own factor: appending an
+    observation to gp.py:46-49's Gram matrix grows T = L^-1 by the row [-(l^T T) / lambda, 1 / lambda] with l = T k and
+    lambda^2 = kappa - |l|^2, and leaves the rows above it untouched."""
+    from scipy.linalg import solve_triangular
+    rng = np.random.default_rng(3)
+    n, d = 60, 3
+    X = rng.uniform(0, 1, (n + 1, d))
+    Y = np.sin(3 * X.sum(1))
+    P = ogp.GPParams(-4.0, 0.3, np.array([0.1, -0.2, 0.4]))
+    small = ogp.Factor(P, X[:n], Y[:n], np.ones(n), np.float64)
+    full = ogp.Factor(P, X, Y, np.ones(n + 1), np.float64)
+    T = solve_triangular(small.L, np.eye(n), lower=True)
+    k = full.K[n, :n]
+    l = T @ k
+    lam = np.sqrt(full.K[n, n] - l @ l)
+    row = np.concatenate([-(l @ T) / lam, [1.0 / lam]])
+    T_full = solve_triangular(full.L, np.eye(n + 1), lower=True)
+    assert np.allclose(T_full[:n, :n], T, rtol=0, atol=1e-12 * np.abs(T).max())
+    assert np.allclose(T_full[n], row, rtol=1e-9, atol=1e-11 * np.abs(T_full).max())
+    assert np.isclose(np.log(lam), np.sum(np.log(np.diag(full.L))) - np.sum(np.log(np.diag(small.L))), rtol=1e-10)
