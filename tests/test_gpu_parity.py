@@ -1258,3 +1258,31 @@ def test_fit_with_kept_hypers_appends_to_the_cached_factor():
     assert not np.array_equal(np.asarray(st3.gp_params.lengthscale), np.asarray(st.gp_params.lengthscale))
     with pytest.raises(ValueError):
         opt.fit(st, 0.0, new, trainsteps=-1)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,d", [(40, 1), (128, 2), (312, 3)])
+def test_dense_low_dimensional_posteriors_sit_at_the_float32_limit(n, d):
+    """Where the bar itself is at the float32 floor: with this many observations on the unit interval /
+    square / cube EVERY candidate's variance is a few per cent of the amplitude, so 1e-4 * mean(var) is ~20 ulp of amp, and
+    amp - sum (T k*)^2 evaluated in float32 through the explicit inverse misses it by a small factor for ~1 % of the points (a
+    NumPy model of the path: half from the FFMA chain of T k*, half from the float32 sum of squares; the oracle's float32
+    triangular solve is ~4x more accurate there).  Pinned so that it cannot get worse unnoticed: at most 3 % of the points
+    outside the bar, none beyond 3x; the mean holds the bar as everywhere else."""
+    X, Y, raw, P = make_problem(n, d, seed=11 * n + d)
+    rng = np.random.default_rng(n)
+    M = 3000
+    cand = rng.uniform(-0.1, 1.1, (M, d)).astype(np.float32)
+    post = engine.Posterior(X, Y, raw, want_tc=False).build()
+    out = post.score_points(cand, acq="UCB", param=0.01, ystar=0.0)
+    mask = np.ones(n)
+    f64, f32 = ogp.Factor(P, X, Y, mask, np.float64), ogp.Factor(P, X, Y, mask, np.float32)
+    mu64, sd64, var64 = f64.predict(cand.astype(np.float64), return_var=True)
+    mu32, sd32, var32 = f32.predict(cand, return_var=True)
+    assert_close(out["mu"].cpu().numpy(), mu64, mu32, what="mean", floor=mean_sum_floor(f64, cand))
+    r64, r32 = np.maximum(var64, 1e-10), np.maximum(var32, 1e-10).astype(np.float64)
+    tol = np.maximum(RTOL * np.maximum(r64, r64.mean()), 4 * np.abs(r32 - r64))
+    err = np.abs(out["sigma"].cpu().numpy().astype(np.float64) ** 2 - r64)
+    frac_out, worst = float(np.mean(err > tol)), float(np.max(err / tol))
+    print(f"n={n} d={d}: {100 * frac_out:.2f} % of the points outside the bar, worst {worst:.2f}x; max var / amp {r64.max() / float(f64.amp):.3f}")
+    assert frac_out <= 0.03 and worst <= 3.0, (frac_out, worst)
