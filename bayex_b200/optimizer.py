@@ -47,10 +47,14 @@ def _optimize_suggestion(params, fun, max_iter: int = 10):
     ``fun`` is what the reference passes (optimizer.py:190-194): a ``functools.partial`` of one of the ``bayex.acq``
     functions with ``xs, ys, mask, gp_params`` (and optionally ``xi`` / ``kappa``) bound.  The optax L-BFGS of the
     reference (unpinned, mis-signed value_fn: Q12) is replaced by the device refinement ``bx_refine`` - a monotone
-    analytic-gradient ascent, 3 evaluations per reference iteration; the returned point never scores below ``params``."""
+    analytic-gradient ascent, 3 evaluations per reference iteration; the returned point never scores below ``params``.
+    Any other scalar callable of a (d,) point gets the same ascent rule driven from the host with central differences
+    (``_ascend_callable``)."""
     import functools
+    if not callable(fun):
+        raise TypeError("fun must be callable")
     if not isinstance(fun, functools.partial) or getattr(fun.func, "__name__", "") not in _ACQ_BY_FUNC:
-        raise TypeError("fun must be functools.partial(bayex.acq.<acquisition>, xs=..., ys=..., mask=..., gp_params=...)")
+        return _ascend_callable(np.asarray(params, dtype=np.float32).reshape(-1), fun, 3 * int(max_iter))
     name = _ACQ_BY_FUNC[fun.func.__name__]
     kw = dict(fun.keywords)
     for slot, arg in zip(("xs", "ys", "mask", "gp_params"), fun.args):
@@ -66,6 +70,45 @@ def _optimize_suggestion(params, fun, max_iter: int = 10):
     out, _ = post.refine(start, 3 * int(max_iter), name, param, boacq.ystar_for(name, ys, mask))
     with engine.on_stream(post.stream, post.dev):
         return out.cpu().numpy()[0]
+
+
+def _ascend_callable(x0, fun, rounds):
+    """``_optimize_suggestion`` for a callable that is NOT one of the bayex acquisitions (the reference accepts any
+    JAX-differentiable scalar function of a (d,) point: optimizer.py:59-66).  There is no closed form to hand to the device
+    refinement, so the same monotone ascent (trial = best + step g / |g|, accepted iff the value strictly improves, step
+    doubles / halves from 0.1, iterates clipped to +-1e6: optimizer.py:68) runs on the host with central differences of
+    ``fun`` - 2 d + 1 calls per round.  Host control logic around the caller's own function, not a fallback of a kernel."""
+    x0 = np.asarray(x0, dtype=np.float32)
+    d = x0.size
+
+    def value(x):
+        v = np.asarray(fun(x.astype(np.float32)), dtype=np.float64)
+        if v.size != 1:
+            raise TypeError("fun must map a (d,) point to a scalar")
+        return float(v.reshape(()))
+
+    def grad(x):
+        g = np.zeros(d, np.float64)
+        for k in range(d):
+            h = 1e-3 * max(1.0, abs(float(x[k])))
+            e = np.zeros(d, np.float32)
+            e[k] = h
+            g[k] = (value(x + e) - value(x - e)) / (float((x + e)[k]) - float((x - e)[k]))
+        return g
+
+    xb, fb = x0.copy(), value(x0)
+    gb, step = grad(xb), 0.1
+    for _ in range(int(rounds)):
+        nrm = float(np.sqrt(np.sum(gb * gb)))
+        if not (np.isfinite(nrm) and nrm > 0.0):
+            break
+        xt = np.clip(xb + np.float32(step) * (gb / nrm).astype(np.float32), -1e6, 1e6).astype(np.float32)
+        ft = value(xt)
+        if ft > fb:
+            xb, fb, gb, step = xt, ft, grad(xt), step * 2.0
+        else:
+            step *= 0.5
+    return xb
 
 
 class Optimizer:

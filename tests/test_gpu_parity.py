@@ -968,7 +968,7 @@ def test_optimize_suggestion_reference_call_pattern():
         v0, v1 = fun(x0[None])[0], fun(x1[None])[0]
         assert v1 >= v0 - 1e-6 * max(1.0, abs(v0)), (v0, v1)
     with pytest.raises(TypeError):
-        _optimize_suggestion(np.zeros(d, np.float32), lambda x: x)
+        _optimize_suggestion(np.zeros(d, np.float32), lambda x: x)  # not a scalar function
 
 
 # ---- edge cases of the path --------------------------------------------------------------------------------------

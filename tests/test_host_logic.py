@@ -187,3 +187,25 @@ def test_weighted_shards_cover_the_draw_exactly():
     assert small == [bopt.shard_range(1000, k, world) for k in range(world)]
     lop = [bopt.shard_range(1 << 20, k, 2, [1e-9, 1.0]) for k in range(2)]  # a rank may end up with (almost) nothing
     assert lop[0][1] + lop[1][1] == 1 << 20 and lop[0][1] <= bopt.SHARD_GRANULE
+
+
+def test_optimize_suggestion_with_a_generic_callable():
+    """optimizer.py:39-73 accepts any scalar function of a (d,) point; a callable that is not a bayex acquisition is ascended
+    on the host with central differences under the device refinement's rule: never worse than the start, float32 (d,) out,
+    iterates clipped to +-1e6, no GPU involved."""
+    from bayex_b200.optimizer import _optimize_suggestion
+    c = np.array([0.3, -1.2, 2.0])
+    fun = lambda x: -float(np.sum((np.asarray(x, np.float64) - c) ** 2))
+    x0 = np.zeros(3, np.float32)
+    x1 = _optimize_suggestion(x0, fun, max_iter=10)
+    assert x1.shape == (3,) and x1.dtype == np.float32
+    assert fun(x1) >= fun(x0) and np.linalg.norm(x1 - c) < 0.05 * np.linalg.norm(x0 - c)
+    flat = _optimize_suggestion(x0, lambda x: 1.0, max_iter=10)          # zero gradient: stays put
+    assert np.array_equal(flat, x0)
+    far = _optimize_suggestion(np.full(2, 9.9e5, np.float32), lambda x: float(np.sum(x)), max_iter=10)
+    assert np.all(far <= 1e6) and np.all(far >= 9.9e5)                   # optimizer.py:68
+    import pytest
+    with pytest.raises(TypeError):
+        _optimize_suggestion(x0, lambda x: np.asarray(x), max_iter=2)    # not a scalar function
+    with pytest.raises(TypeError):
+        _optimize_suggestion(x0, 3.0)
