@@ -196,21 +196,19 @@ __device__ __forceinline__ float block_sum_128(float v, float* red) {
   return t;
 }
 
-// One block per start: value + gradient of the acquisition at the trial point, accept/reject, next trial point.
+// One block per start: value + gradient of the acquisition at the trial point, accept/reject, next trial point.  The body is
+// shared by refine_update_kernel (one launch per round) and refine_small_kernel (all rounds in one launch: the caller puts a
+// block barrier between two calls); sm = 2 np floats of shared memory.
 template <int RU_T>
-__global__ void __launch_bounds__(RU_T) refine_update_kernel(bx_factor_t f, const float* __restrict__ Kst, const float* __restrict__ V,
-                                                            const float* __restrict__ W, int acq_id, float acq_param,
-                                                            float ystar, int first, float* xt, float* xb, float* gb,
-                                                            float* fb, float* step, float* Kst_next) {
-  extern __shared__ float sm[];
+__device__ __forceinline__ void refine_update_body(const bx_factor_t& f, const float* Kst, const float* V, const float* W, int acq_id,
+                                                   float acq_param, float ystar, int first, float* xt, float* xb, float* gb,
+                                                   float* fb, float* step, float* Kst_next, float* sm, int s) {
   float* ak = sm;              // [np] alpha_j k_j
   float* wk = sm + f.np;       // [np] w_j k_j
   constexpr int RU_W = RU_T / 32;
   __shared__ float red[RU_W];
   __shared__ float dmu[BX_MAX_D], dvar[BX_MAX_D], ct[BX_MAX_D];
-  const int s = blockIdx.x, tid = threadIdx.x, d = f.d;
-  pdl_launch_dependents();  // the next round's block kernel stages its T blocks under this kernel
-  pdl_wait();
+  const int tid = threadIdx.x, d = f.d;
   if (tid < BX_MAX_D) ct[tid] = (tid < d) ? xt[(size_t)s * d + tid] * f.d_scale[tid] : 0.f;
   float mu_p = 0.f, ss_p = 0.f;
   for (int j = tid; j < f.np; j += RU_T) {
@@ -349,6 +347,63 @@ __global__ void __launch_bounds__(RU_T) refine_update_kernel(bx_factor_t f, cons
   }
 }
 
+template <int RU_T>
+__global__ void __launch_bounds__(RU_T) refine_update_kernel(bx_factor_t f, const float* __restrict__ Kst, const float* __restrict__ V,
+                                                            const float* __restrict__ W, int acq_id, float acq_param,
+                                                            float ystar, int first, float* xt, float* xb, float* gb,
+                                                            float* fb, float* step, float* Kst_next) {
+  extern __shared__ float sm[];
+  pdl_launch_dependents();  // the next round's block kernel stages its T blocks under this kernel
+  pdl_wait();
+  refine_update_body<RU_T>(f, Kst, V, W, acq_id, acq_param, ystar, first, xt, xb, gb, fb, step, Kst_next, sm, (int)blockIdx.x);
+}
+
+// n <= 128 (np == 128: the README / test-suite regime): the WHOLE refinement of a start in one launch.  T is 64 KB - it is
+// staged once in shared memory (row stride 129: conflict-free along rows and along columns) and a start's 31 rounds run
+// back to back in its own CTA of 128 threads (thread i forms row i of V = T k*, then column i of W = T^T V, then the block
+// runs the update body), with block barriers where the general path has kernel boundaries: ~95 launches of a few
+// microseconds become one.  A start's arithmetic involves nobody else, so sharding the starts still cannot change a bit.
+constexpr int RSM_LD = RBS + 1;
+__global__ void __launch_bounds__(RBS) refine_small_kernel(bx_factor_t f, float* Kst, float* Kst2, float* V, float* W, int acq_id,
+                                                           float acq_param, float ystar, int rounds, float* xt, float* xb,
+                                                           float* gb, float* fb, float* step) {
+  extern __shared__ float sm[];  // [2 np] scratch of the update body | T [128][129]
+  float* Ts = sm + 2 * RBS;
+  const int s = blockIdx.x, i = threadIdx.x;
+  for (int e = i; e < RBS * RBS; e += RBS) Ts[(e >> 7) * RSM_LD + (e & 127)] = f.d_T[e];  // zero above the diagonal
+  float *kcur = Kst, *knext = Kst2;
+  float* Vs = V + (size_t)s * RBS;
+  float* Ws = W + (size_t)s * RBS;
+  for (int r = 0; r <= rounds; ++r) {
+    __syncthreads();  // T staged / the previous round's K* written
+    const float* k = kcur + (size_t)s * RBS;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int j = 0;
+    for (; j + 3 <= i; j += 4) {  // V[i] = sum_{j <= i} T[i][j] k[j]   (gp.py:68)
+      a0 = fmaf(Ts[i * RSM_LD + j], k[j], a0);
+      a1 = fmaf(Ts[i * RSM_LD + j + 1], k[j + 1], a1);
+      a2 = fmaf(Ts[i * RSM_LD + j + 2], k[j + 2], a2);
+      a3 = fmaf(Ts[i * RSM_LD + j + 3], k[j + 3], a3);
+    }
+    for (; j <= i; ++j) a0 = fmaf(Ts[i * RSM_LD + j], k[j], a0);
+    Vs[i] = (a0 + a1) + (a2 + a3);
+    __syncthreads();
+    a0 = a1 = a2 = a3 = 0.f;
+    int q = i;
+    for (; q + 3 < RBS; q += 4) {  // W[i] = sum_{q >= i} T[q][i] V[q]   (K^-1 k*)
+      a0 = fmaf(Ts[q * RSM_LD + i], Vs[q], a0);
+      a1 = fmaf(Ts[(q + 1) * RSM_LD + i], Vs[q + 1], a1);
+      a2 = fmaf(Ts[(q + 2) * RSM_LD + i], Vs[q + 2], a2);
+      a3 = fmaf(Ts[(q + 3) * RSM_LD + i], Vs[q + 3], a3);
+    }
+    for (; q < RBS; ++q) a0 = fmaf(Ts[q * RSM_LD + i], Vs[q], a0);
+    Ws[i] = (a0 + a1) + (a2 + a3);
+    __syncthreads();
+    refine_update_body<RBS>(f, kcur, V, W, acq_id, acq_param, ystar, r == 0 ? 1 : 0, xt, xb, gb, fb, step, knext, sm, s);
+    float* t = kcur; kcur = knext; knext = t;
+  }
+}
+
 int32_t check_factor(const bx_factor_t* f);
 
 }  // namespace bx
@@ -404,6 +459,15 @@ extern "C" int32_t bx_refine(const bx_factor_t* f, float* d_x, int32_t S, int32_
   BX_CUDA(cudaMemsetAsync(w.Kst2, 0, sizeof(float) * (size_t)w.S16 * f->np, s));  // unused start slots stay zero
   refine_kstar_kernel<<<(f->np * w.S16 + 255) / 256, 256, 0, s>>>(*f, w.xt, S, w.S16, w.Kst);
   BX_LAUNCH_CHECK();
+  const bool no_small = getenv("BX_NO_REFINE_SMALL") != nullptr;  // read per call: the A/B of the two paths in one process
+  if (nb == 1 && !no_small) {  // n <= 128: one launch for all rounds
+    const size_t ssm = sizeof(float) * (2 * RBS + RBS * RSM_LD);
+    BX_CUDA(cudaFuncSetAttribute(refine_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssm));
+    refine_small_kernel<<<S, RBS, ssm, s>>>(*f, w.Kst, w.Kst2, w.V, w.W, acq_id, acq_param, ystar, rounds, w.xt, w.xb, w.gb, w.fb,
+                                            w.step);
+    BX_LAUNCH_CHECK();
+    rounds = -1;  // skip the per-round loop below
+  }
   float *kcur = w.Kst, *knext = w.Kst2;
   for (int r = 0; r <= rounds; ++r) {
     if (nb == 1) {  // a single block: its partial product is the product
