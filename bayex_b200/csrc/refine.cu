@@ -358,48 +358,52 @@ __global__ void __launch_bounds__(RU_T) refine_update_kernel(bx_factor_t f, cons
   refine_update_body<RU_T>(f, Kst, V, W, acq_id, acq_param, ystar, first, xt, xb, gb, fb, step, Kst_next, sm, (int)blockIdx.x);
 }
 
-// n <= 128 (np == 128: the README / test-suite regime): the WHOLE refinement of a start in one launch.  T is 64 KB - it is
-// staged once in shared memory (row stride 129: conflict-free along rows and along columns) and a start's 31 rounds run
-// back to back in its own CTA of 128 threads (thread i forms row i of V = T k*, then column i of W = T^T V, then the block
-// runs the update body), with block barriers where the general path has kernel boundaries: ~95 launches of a few
-// microseconds become one.  A start's arithmetic involves nobody else, so sharding the starts still cannot change a bit.
-constexpr int RSM_LD = RBS + 1;
-__global__ void __launch_bounds__(RBS) refine_small_kernel(bx_factor_t f, float* Kst, float* Kst2, float* V, float* W, int acq_id,
-                                                           float acq_param, float ystar, int rounds, float* xt, float* xb,
-                                                           float* gb, float* fb, float* step) {
-  extern __shared__ float sm[];  // [2 np] scratch of the update body | T [128][129]
-  float* Ts = sm + 2 * RBS;
+// n <= 256 (np = 128 or 256: the README / test-suite regime and most real optimisation budgets): the WHOLE refinement of a
+// start in one launch.  The lower triangle of T is at most 129 KB - it is staged once in shared memory, packed row by row
+// (row i at i (i + 1) / 2: contiguous along a row, consecutive along a column), and a start's 31 rounds run back to back
+// in its own CTA of np threads (thread i forms row i of V = T k*, then column i of W = T^T V, then the block runs the
+// update body), with block barriers where the general path has kernel boundaries: ~95-160 launches of a few microseconds
+// become one.  A start's arithmetic involves nobody else, so sharding the starts still cannot change a bit.
+constexpr int RSM_MAX_NP = 256;
+template <int NP>
+__global__ void __launch_bounds__(NP) refine_small_kernel(bx_factor_t f, float* Kst, float* Kst2, float* V, float* W, int acq_id,
+                                                          float acq_param, float ystar, int rounds, float* xt, float* xb,
+                                                          float* gb, float* fb, float* step) {
+  extern __shared__ float sm[];  // [2 NP] scratch of the update body | packed lower triangle of T
+  float* Ts = sm + 2 * NP;
   const int s = blockIdx.x, i = threadIdx.x;
-  for (int e = i; e < RBS * RBS; e += RBS) Ts[(e >> 7) * RSM_LD + (e & 127)] = f.d_T[e];  // zero above the diagonal
+  for (int r = 0; r < NP; ++r)  // row r: entries 0 .. r (coalesced; everything above the diagonal is zero and never read)
+    if (i <= r) Ts[r * (r + 1) / 2 + i] = f.d_T[(size_t)r * NP + i];
   float *kcur = Kst, *knext = Kst2;
-  float* Vs = V + (size_t)s * RBS;
-  float* Ws = W + (size_t)s * RBS;
+  float* Vs = V + (size_t)s * NP;
+  float* Ws = W + (size_t)s * NP;
+  const float* Ti = Ts + i * (i + 1) / 2;
   for (int r = 0; r <= rounds; ++r) {
     __syncthreads();  // T staged / the previous round's K* written
-    const float* k = kcur + (size_t)s * RBS;
+    const float* k = kcur + (size_t)s * NP;
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
     int j = 0;
     for (; j + 3 <= i; j += 4) {  // V[i] = sum_{j <= i} T[i][j] k[j]   (gp.py:68)
-      a0 = fmaf(Ts[i * RSM_LD + j], k[j], a0);
-      a1 = fmaf(Ts[i * RSM_LD + j + 1], k[j + 1], a1);
-      a2 = fmaf(Ts[i * RSM_LD + j + 2], k[j + 2], a2);
-      a3 = fmaf(Ts[i * RSM_LD + j + 3], k[j + 3], a3);
+      a0 = fmaf(Ti[j], k[j], a0);
+      a1 = fmaf(Ti[j + 1], k[j + 1], a1);
+      a2 = fmaf(Ti[j + 2], k[j + 2], a2);
+      a3 = fmaf(Ti[j + 3], k[j + 3], a3);
     }
-    for (; j <= i; ++j) a0 = fmaf(Ts[i * RSM_LD + j], k[j], a0);
+    for (; j <= i; ++j) a0 = fmaf(Ti[j], k[j], a0);
     Vs[i] = (a0 + a1) + (a2 + a3);
     __syncthreads();
     a0 = a1 = a2 = a3 = 0.f;
     int q = i;
-    for (; q + 3 < RBS; q += 4) {  // W[i] = sum_{q >= i} T[q][i] V[q]   (K^-1 k*)
-      a0 = fmaf(Ts[q * RSM_LD + i], Vs[q], a0);
-      a1 = fmaf(Ts[(q + 1) * RSM_LD + i], Vs[q + 1], a1);
-      a2 = fmaf(Ts[(q + 2) * RSM_LD + i], Vs[q + 2], a2);
-      a3 = fmaf(Ts[(q + 3) * RSM_LD + i], Vs[q + 3], a3);
+    for (; q + 3 < NP; q += 4) {  // W[i] = sum_{q >= i} T[q][i] V[q]   (K^-1 k*)
+      a0 = fmaf(Ts[q * (q + 1) / 2 + i], Vs[q], a0);
+      a1 = fmaf(Ts[(q + 1) * (q + 2) / 2 + i], Vs[q + 1], a1);
+      a2 = fmaf(Ts[(q + 2) * (q + 3) / 2 + i], Vs[q + 2], a2);
+      a3 = fmaf(Ts[(q + 3) * (q + 4) / 2 + i], Vs[q + 3], a3);
     }
-    for (; q < RBS; ++q) a0 = fmaf(Ts[q * RSM_LD + i], Vs[q], a0);
+    for (; q < NP; ++q) a0 = fmaf(Ts[q * (q + 1) / 2 + i], Vs[q], a0);
     Ws[i] = (a0 + a1) + (a2 + a3);
     __syncthreads();
-    refine_update_body<RBS>(f, kcur, V, W, acq_id, acq_param, ystar, r == 0 ? 1 : 0, xt, xb, gb, fb, step, knext, sm, s);
+    refine_update_body<NP>(f, kcur, V, W, acq_id, acq_param, ystar, r == 0 ? 1 : 0, xt, xb, gb, fb, step, knext, sm, s);
     float* t = kcur; kcur = knext; knext = t;
   }
 }
@@ -460,11 +464,17 @@ extern "C" int32_t bx_refine(const bx_factor_t* f, float* d_x, int32_t S, int32_
   refine_kstar_kernel<<<(f->np * w.S16 + 255) / 256, 256, 0, s>>>(*f, w.xt, S, w.S16, w.Kst);
   BX_LAUNCH_CHECK();
   const bool no_small = getenv("BX_NO_REFINE_SMALL") != nullptr;  // read per call: the A/B of the two paths in one process
-  if (nb == 1 && !no_small) {  // n <= 128: one launch for all rounds
-    const size_t ssm = sizeof(float) * (2 * RBS + RBS * RSM_LD);
-    BX_CUDA(cudaFuncSetAttribute(refine_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssm));
-    refine_small_kernel<<<S, RBS, ssm, s>>>(*f, w.Kst, w.Kst2, w.V, w.W, acq_id, acq_param, ystar, rounds, w.xt, w.xb, w.gb, w.fb,
-                                            w.step);
+  if (f->np <= RSM_MAX_NP && !no_small) {  // n <= 256: one launch for all rounds
+    const size_t ssm = sizeof(float) * (2 * (size_t)f->np + (size_t)f->np * (f->np + 1) / 2);
+    if (f->np == 128) {
+      BX_CUDA(cudaFuncSetAttribute(refine_small_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssm));
+      refine_small_kernel<128><<<S, 128, ssm, s>>>(*f, w.Kst, w.Kst2, w.V, w.W, acq_id, acq_param, ystar, rounds, w.xt, w.xb, w.gb,
+                                                   w.fb, w.step);
+    } else {
+      BX_CUDA(cudaFuncSetAttribute(refine_small_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssm));
+      refine_small_kernel<256><<<S, 256, ssm, s>>>(*f, w.Kst, w.Kst2, w.V, w.W, acq_id, acq_param, ystar, rounds, w.xt, w.xb, w.gb,
+                                                   w.fb, w.step);
+    }
     BX_LAUNCH_CHECK();
     rounds = -1;  // skip the per-round loop below
   }

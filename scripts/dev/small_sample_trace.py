@@ -1,10 +1,10 @@
-"""Per-phase device timeline (BX_TRACE_SAMPLE) and wall time of sample() in the README regime (n <= 128); dev tool."""
+"""Per-phase device timeline (BX_TRACE_SAMPLE) and wall time of sample() in the README regime (n <= 256); dev tool."""
 import os, sys, time
 os.environ["BX_TRACE_SAMPLE"] = "1"
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 import bayex_b200 as bayex
-for n0, d, M, acq in [(23, 1, 10_000, "PI"), (100, 3, 10_000, "EI"), (120, 6, 100_000, "EI")]:
+for n0, d, M, acq in [(23, 1, 10_000, "PI"), (100, 3, 10_000, "EI"), (120, 6, 100_000, "EI"), (200, 4, 10_000, "EI"), (250, 6, 100_000, "UCB")]:
     rng = np.random.default_rng(0)
     dom = {f"x{i}": bayex.domain.Real(0.0, 1.0) for i in range(d)}
     P0 = {k: rng.uniform(0, 1, n0).astype(np.float32) for k in dom}

@@ -399,13 +399,13 @@ def test_adamw_kernel_step_by_step(n, scale_y, multi_kernel, expect_clipped, mon
     assert np.array_equal(again.raw_host(), final)
 
 
-@pytest.mark.parametrize("n,d", [(300, 4), (100, 3)])
+@pytest.mark.parametrize("n,d", [(300, 4), (100, 3), (200, 5)])
 @pytest.mark.parametrize("acq", ["EI", "PI", "UCB", "LCB"])
 def test_refinement_contract(acq, n, d, monkeypatch):
     """Replacement of optimizer.py:39-73: monotone ascent - every refined value >= its start value, and the values
     bx_refine reports are the ones bx_score_points gives at the returned points.  n = 300: one launch per product and round
-    (refine_blk / refine_partsum / refine_update); n = 100: all rounds of a start in one launch (refine_small_kernel), held to
-    the same contract and compared with the per-round path on the same starts."""
+    (refine_blk / refine_partsum / refine_update); n = 100 and 200 (np = 128, 256): all rounds of a start in one launch
+    (refine_small_kernel), held to the same contract and compared with the per-round path on the same starts."""
     X, Y, raw, P = make_problem(n, d, seed=99)
     post = engine.Posterior(X, Y, raw, want_tc=False).build()
     rng = np.random.default_rng(1)
@@ -440,7 +440,7 @@ def test_refinement_contract(acq, n, d, monkeypatch):
     moved = np.linalg.norm(step, axis=1) > 0
     cos = np.sum(step * grad * (ogp.softplus(raw[2:]) ** 2), axis=1)
     assert np.all(cos[moved] > 0)
-    if n <= 128:  # the per-round path on the same starts: same rule, other summation order - comparable gains, same contract
+    if n <= 256:  # the per-round path on the same starts: same rule, other summation order - comparable gains, same contract
         monkeypatch.setenv("BX_NO_REFINE_SMALL", "1")
         xg, vg = post.refine(torch.from_numpy(starts).cuda(), 30, acq, param, ystar)
         monkeypatch.delenv("BX_NO_REFINE_SMALL")
