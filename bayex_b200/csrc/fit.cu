@@ -463,6 +463,267 @@ fit_small_kernel(const float* __restrict__ X, const float* __restrict__ y, int n
   for (int p = tid; p < P; p += FS_THREADS) raw_g[p] = raw[p];
 }
 
+// ---- n <= 128: the whole fit loop in one CTA with the matrix in REGISTERS ------------------------------------------------------
+// fit_small_kernel above keeps K in shared memory and walks a textbook Cholesky with three block barriers per column, a
+// triangular inverse on one thread per column and T^T T by dot products: it crosses over with the multi-kernel path at n = 56
+// (0.087 ms per step).  This kernel holds the lower 32 x 32 tiles of the padded matrix in the registers of 1024 threads
+// (thread (ty, tx) owns element (32 a + ty, 32 b + tx) of every tile a >= b; diagonal tiles are kept whole) and turns K
+// into -K^-1 IN PLACE with the symmetric sweep operator - per pivot k: A_ij -= A_ik A_kj / p, A_ik <- A_ik / p,
+// A_kk <- -1 / p with p = A_kk - one uniform rank-1 update per pivot, ONE block barrier per pivot (the pivot column
+// travels through a double-buffered shared-memory vector), no separate factorisation / inverse / product phases.  The
+// pivots are the squares of the Cholesky diagonal (gp.py:48: log det = 1/2 sum log p_k; a non-positive pivot becomes NaN
+// exactly where cholesky() would produce one); alpha = K^-1 yc, the NLML (gp.py:52-57), the gradient contraction
+//  and clip + AdamW (gp.py:99-106) follow in the same launch for all `steps`.  n^3 / 2 FMAs per step instead
+// of n^3 / 3 + n^3 / 6 + n^3 / 6, but every one of them on 1024 threads; fp32 error of K^-1 at the level of the Cholesky
+// route (both ~ cond(K) eps).  Reductions run in a fixed order: the result does not depend on the launch.
+constexpr int SW_THREADS = 1024;
+constexpr int SW_MAX_NT = 4;  // n <= 128: tiles a thread owns NT (NT + 1) / 2 <= 10, twice that live in the gradient phase
+__host__ __device__ constexpr int sw_e(int a, int b) { return a * (a + 1) / 2 + b; }
+
+__device__ __forceinline__ float sw_block_sum(float v, float* red) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = 0.f;
+#pragma unroll
+  for (int w = 0; w < SW_THREADS / 32; ++w) t += red[w];
+  return t;
+}
+
+template <int NT>
+__global__ void __launch_bounds__(SW_THREADS, 1)
+fit_sweep_kernel(const float* __restrict__ X, const float* __restrict__ y, int n, int d, float* raw_g, float lr, int steps,
+                 float* trace, float* gbuf_out, int grad_only) {
+  constexpr int NP = 32 * NT, NE = NT * (NT + 1) / 2;
+  extern __shared__ float sm[];
+  const int d4 = round_up(d, 4), P = d + 2, tid = threadIdx.x, ty = tid >> 5, tx = tid & 31;
+  float* Ut = sm;                 // [d4][NP] scaled observations, dimension-major
+  float* yc = Ut + d4 * NP;       // [NP]
+  float* al = yc + NP;            // [NP]
+  float* cb = al + NP;            // [2][NP] pivot column, double-buffered
+  float* part = cb + 2 * NP;      // [32][NP] cross-warp partial sums
+  float* raw = part + 32 * NP;    // [P]
+  float* grad = raw + P;          // [P]
+  float* dsum = grad + P;         // [d4] per-dimension gradient sums
+  float* scale = dsum + d4;       // [d4]
+  float* mom = scale + d4;        // [2P] Adam moments
+  __shared__ float red[SW_THREADS / 32];
+  __shared__ float red4[4][SW_THREADS / 32];
+  __shared__ float sc[8];         // amp, noise+jitter
+  for (int p = tid; p < P; p += SW_THREADS) { raw[p] = raw_g[p]; mom[p] = 0.f; mom[P + p] = 0.f; }
+  const float ysum = sw_block_sum(tid < n ? y[tid] : 0.f, red);  // n <= 128 < SW_THREADS
+  const float ymean = ysum / (float)n;
+  if (tid < NP) yc[tid] = (tid < n) ? y[tid] - ymean : 0.f;
+  __syncthreads();
+
+  for (int step = 0; step <= steps; ++step) {
+    const bool last = (step == steps);  // the extra pass only evaluates (bx_nlml_grad) - no update
+    if (last && !grad_only) break;
+    // hypers (gp.py:41) and scaled observations (gp.py:45)
+    if (tid == 0) { sc[0] = softplus_f(raw[1]); sc[1] = softplus_f(raw[0]) + kJitter; }
+    for (int k = tid; k < d4; k += SW_THREADS) scale[k] = (k < d) ? kSqrtLog2e / softplus_f(raw[2 + k]) : 0.f;
+    __syncthreads();
+    for (int e = tid; e < d4 * NP; e += SW_THREADS) {
+      const int k = e / NP, i = e - k * NP;
+      Ut[e] = (i < n && k < d) ? X[(size_t)i * d + k] * scale[k] : 0.f;
+    }
+    __syncthreads();
+    const float amp = sc[0];
+    // Gram (gp.py:46) into registers; identity on the padding
+    float A[NE];
+#pragma unroll
+    for (int e = 0; e < NE; ++e) A[e] = 0.f;
+    for (int k = 0; k < d4; ++k) {
+      float ui[NT], uj[NT];
+#pragma unroll
+      for (int a = 0; a < NT; ++a) { ui[a] = Ut[k * NP + 32 * a + ty]; uj[a] = Ut[k * NP + 32 * a + tx]; }
+#pragma unroll
+      for (int a = 0; a < NT; ++a)
+#pragma unroll
+        for (int b = 0; b <= a; ++b) { const float df = ui[a] - uj[b]; A[sw_e(a, b)] = fmaf(df, df, A[sw_e(a, b)]); }
+    }
+#pragma unroll
+    for (int a = 0; a < NT; ++a)
+#pragma unroll
+      for (int b = 0; b <= a; ++b) {
+        const int i = 32 * a + ty, j = 32 * b + tx;
+        A[sw_e(a, b)] = (i < n && j < n) ? amp * exp2f(-A[sw_e(a, b)]) + (i == j ? sc[1] : 0.f) : (i == j ? 1.f : 0.f);
+      }
+    // sweep every valid pivot: A -> -K^-1
+#pragma unroll
+    for (int kb = 0; kb < NT; ++kb) {
+      const int kmax = min(32, n - 32 * kb);
+      for (int kx = 0; kx < kmax; ++kx) {
+        const int k = 32 * kb + kx;
+        float* buf = cb + (k & 1) * NP;
+        if (tx == kx) {  // column k: the diagonal tile's rows and the tiles below it
+#pragma unroll
+          for (int a = kb; a < NT; ++a) buf[32 * a + ty] = A[sw_e(a, kb)];
+        }
+        if (ty == kx) {  // row k (= column k above the diagonal tile)
+#pragma unroll
+          for (int b = 0; b < kb; ++b) buf[32 * b + tx] = A[sw_e(kb, b)];
+        }
+        __syncthreads();
+        float p = buf[k];
+        if (!(p > 0.f)) p = CUDART_NAN_F;  // gp.py:48: cholesky() of a non-PD matrix gives NaN, and so does everything after
+        const float ip = __frcp_rn(p);     // correctly rounded, without the division's slow path: it heads every pivot's chain
+        if (tid == 0) part[k] = p;         // the logarithms are taken after the loop, one pivot per thread
+        float ci[NT], cjp[NT];
+#pragma unroll
+        for (int a = 0; a < NT; ++a) { ci[a] = buf[32 * a + ty]; cjp[a] = buf[32 * a + tx] * ip; }
+#pragma unroll
+        for (int a = 0; a < NT; ++a)
+#pragma unroll
+          for (int b = 0; b <= a; ++b) A[sw_e(a, b)] = fmaf(-ci[a], cjp[b], A[sw_e(a, b)]);
+#pragma unroll
+        for (int a = kb + 1; a < NT; ++a)
+          if (tx == kx) A[sw_e(a, kb)] = ci[a] * ip;
+#pragma unroll
+        for (int b = 0; b < kb; ++b)
+          if (ty == kx) A[sw_e(kb, b)] = cjp[b];
+        if (ty == kx && tx == kx) A[sw_e(kb, kb)] = -ip;
+        else if (ty == kx) A[sw_e(kb, kb)] = cjp[kb];
+        else if (tx == kx) A[sw_e(kb, kb)] = ci[kb] * ip;
+      }
+    }
+    __syncthreads();
+    const float logdet = 0.5f * sw_block_sum(tid < n ? logf(part[tid]) : 0.f, red);  // (ends with every thread past its reads of part)
+    // alpha = K^-1 yc (gp.py:49) with K^-1 = -A: row sums inside the warp, transposed contributions of the off-diagonal
+    // tiles through per-warp partials added in warp order
+#pragma unroll
+    for (int a = 0; a < NT; ++a) {
+      float r = 0.f;
+#pragma unroll
+      for (int b = 0; b <= a; ++b) r = fmaf(-A[sw_e(a, b)], yc[32 * b + tx], r);
+      r = warp_sum(r);
+      if (tx == 0) al[32 * a + ty] = r;
+    }
+#pragma unroll
+    for (int b = 0; b < NT; ++b) {
+      float t = 0.f;
+#pragma unroll
+      for (int a = b + 1; a < NT; ++a) t = fmaf(-A[sw_e(a, b)], yc[32 * a + ty], t);
+      part[ty * NP + 32 * b + tx] = t;
+    }
+    __syncthreads();
+    if (tid < NP) {
+      float t = al[tid];
+#pragma unroll 8
+      for (int w = 0; w < 32; ++w) t += part[w * NP + tid];
+      al[tid] = t;
+    }
+    __syncthreads();
+    const float quad = sw_block_sum(tid < NP ? yc[tid] * al[tid] : 0.f, red);
+    const float la = logf(amp);
+    const float nlml = 0.5f * quad + logdet + ((float)n * 0.5f) * kLog2Pi + (-0.5f * kLog2Pi - la - la * la);  // gp.py:52-57
+    // weights W_ij C_ij (x2 off the diagonal, lower triangle only) into A; trace and amplitude sums
+    float S[NE];
+#pragma unroll
+    for (int e = 0; e < NE; ++e) S[e] = 0.f;
+    for (int k = 0; k < d4; ++k) {
+      float ui[NT], uj[NT];
+#pragma unroll
+      for (int a = 0; a < NT; ++a) { ui[a] = Ut[k * NP + 32 * a + ty]; uj[a] = Ut[k * NP + 32 * a + tx]; }
+#pragma unroll
+      for (int a = 0; a < NT; ++a)
+#pragma unroll
+        for (int b = 0; b <= a; ++b) { const float df = ui[a] - uj[b]; S[sw_e(a, b)] = fmaf(df, df, S[sw_e(a, b)]); }
+    }
+    float trp = 0.f, sap = 0.f;
+#pragma unroll
+    for (int a = 0; a < NT; ++a)
+#pragma unroll
+      for (int b = 0; b <= a; ++b) {
+        const int i = 32 * a + ty, j = 32 * b + tx;
+        const float w = -A[sw_e(a, b)] - al[i] * al[j];
+        float f = 2.f;
+        if (a == b) f = (tx < ty) ? 2.f : (tx == ty ? 1.f : 0.f);  // a diagonal tile holds both triangles: count the lower one
+        if (!(i < n && j < n)) f = 0.f;
+        const float wc = (f != 0.f) ? w * exp2f(-S[sw_e(a, b)]) * f : 0.f;
+        A[sw_e(a, b)] = wc;
+        if (a == b && tx == ty && i < n) trp += w;
+        sap += wc;
+      }
+    const float tr = sw_block_sum(trp, red);
+    const float samp = sw_block_sum(sap, red);
+    // per-dimension sums, four dimensions per reduction pass
+    for (int k0 = 0; k0 < d; k0 += 4) {
+      float s4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int k = k0 + q;  // < d4
+        float ui[NT], uj[NT];
+#pragma unroll
+        for (int a = 0; a < NT; ++a) { ui[a] = Ut[k * NP + 32 * a + ty]; uj[a] = Ut[k * NP + 32 * a + tx]; }
+#pragma unroll
+        for (int a = 0; a < NT; ++a)
+#pragma unroll
+          for (int b = 0; b <= a; ++b) { const float df = ui[a] - uj[b]; s4[q] = fmaf(A[sw_e(a, b)], df * df, s4[q]); }
+        s4[q] = warp_sum(s4[q]);
+      }
+      __syncthreads();
+      if (tx == 0) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) red4[q][ty] = s4[q];
+      }
+      __syncthreads();
+      if (tid < 4) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < SW_THREADS / 32; ++w) t += red4[tid][w];
+        dsum[k0 + tid] = t;
+      }
+    }
+    __syncthreads();
+    if (tid == 0) {
+      float prior = 0.f;
+      for (int p = 0; p < P; ++p) {
+        float g;  // d NLML / d raw_p
+        if (p == 0) g = 0.5f * tr * sigmoid_f(raw[0]);
+        else if (p == 1) g = (0.5f * samp - 1.f / amp - 2.f * la / amp) * sigmoid_f(raw[1]);
+        else {
+          const float ls = softplus_f(raw[p]);
+          g = 0.5f * amp * dsum[p - 2] * (2.f / (kLog2e * ls)) * sigmoid_f(raw[p]);
+        }
+        const float pr = (p == 0) ? kPriorNoise : (p == 1 ? kPriorAmp : kPriorLs);
+        grad[p] = -g + (raw[p] - pr);  // gp.py:78-87
+        if (gbuf_out && last) { gbuf_out[2 + p] = grad[p]; gbuf_out[2 + P + p] = g; }
+        prior += (raw[p] - pr) * (raw[p] - pr);
+      }
+      if (gbuf_out && last) { gbuf_out[0] = nlml; gbuf_out[1] = -(nlml - 0.5f * prior); }
+      if (!last) {  // clip_by_global_norm(10) + adamw (gp.py:99,105-106)
+        if (trace) for (int p = 0; p < P; ++p) trace[(size_t)step * P + p] = raw[p];
+        float gn = 0.f;
+        for (int p = 0; p < P; ++p) gn = fmaf(grad[p], grad[p], gn);
+        gn = sqrtf(gn);
+        const float t = (float)(step + 1), c1 = 1.f - powf(0.9f, t), c2 = 1.f - powf(0.999f, t);
+        for (int p = 0; p < P; ++p) {
+          float g = grad[p];
+          if (!(gn < 10.f)) g = g / gn * 10.f;
+          mom[p] = 0.9f * mom[p] + 0.1f * g;
+          mom[P + p] = 0.999f * mom[P + p] + 0.001f * g * g;
+          const float u = (mom[p] / c1) / (sqrtf(mom[P + p] / c2) + 1e-8f) + 1e-4f * raw[p];
+          raw[p] = raw[p] - lr * u;
+        }
+      }
+    }
+    __syncthreads();
+    if (last) break;
+  }
+  for (int p = tid; p < P; p += SW_THREADS) raw_g[p] = raw[p];
+}
+
+static size_t fit_sweep_smem(int n, int d) {
+  const int np = round_up(n, 32), d4 = round_up(d, 4), P = d + 2;
+  return sizeof(float) * ((size_t)d4 * np + 4 * (size_t)np + 32 * (size_t)np + 4 * P + 2 * d4);
+}
+static bool fit_sweep_ok(int n) {
+  static const bool off = getenv("BX_NO_FIT_SWEEP") != nullptr;
+  return !off && n <= 32 * SW_MAX_NT;
+}
+
 static size_t fit_small_smem(int n, int d) {
   const int d4 = round_up(d, 4), P = d + 2;
   return sizeof(float) * ((size_t)2 * n * (n + 1) + (size_t)n * d4 + 3 * n + 2 * P + d4 + 2 * P);
@@ -470,10 +731,28 @@ static size_t fit_small_smem(int n, int d) {
 // measured on B200: fused 0.027 ms/step at n=24, 0.065 at 48, 0.087 at 56, 0.110 at 64, 0.165 at 80; the multi-kernel
 // path (one 128-row tile, CUDA graph) takes 0.085 ms/step for every n <= 128 -> cross-over at n = 56
 constexpr int FS_DISPATCH_N = 56;
-static bool fit_small_ok(int n, int d) { return n <= FS_DISPATCH_N && fit_small_smem(n, d) <= 200 * 1024; }
+static bool fit_small_ok(int n, int d) {
+  if (fit_sweep_ok(n)) return true;  // register-resident sweep kernel: n <= 128
+  return n <= FS_DISPATCH_N && fit_small_smem(n, d) <= 200 * 1024;
+}
 
 static int32_t launch_fit_small(cudaStream_t s, const float* d_X, const float* d_y, int n, int d, float* d_raw, float lr,
                                 int steps, float* d_trace, float* d_gbuf, int grad_only) {
+  if (fit_sweep_ok(n)) {
+    const size_t ssm = fit_sweep_smem(n, d);
+    const int nt = (n + 31) / 32;
+#define BX_SWEEP_CASE(NT)                                                                                                  \
+  case NT:                                                                                                                 \
+    BX_CUDA(cudaFuncSetAttribute(fit_sweep_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssm));            \
+    fit_sweep_kernel<NT><<<1, SW_THREADS, ssm, s>>>(d_X, d_y, n, d, d_raw, lr, steps, d_trace, d_gbuf, grad_only);         \
+    break;
+    switch (nt) {
+      BX_SWEEP_CASE(1) BX_SWEEP_CASE(2) BX_SWEEP_CASE(3) BX_SWEEP_CASE(4)
+    }
+#undef BX_SWEEP_CASE
+    BX_LAUNCH_CHECK();
+    return 0;
+  }
   const size_t smem = fit_small_smem(n, d);
   BX_CUDA(cudaFuncSetAttribute(fit_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   fit_small_kernel<<<1, FS_THREADS, smem, s>>>(d_X, d_y, n, d, d_raw, lr, steps, d_trace, d_gbuf, grad_only);

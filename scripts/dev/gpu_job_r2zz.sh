@@ -1,10 +1,8 @@
 #!/bin/bash
-# r2zz: single-launch refinement for n <= 256 - contract tests, every test that runs sample() at small n, sample() timeline
-# with the single-launch kernel and (BX_NO_REFINE_SMALL=1) with the per-round path
+# r2zz-b: register-resident sweep fit kernel (n <= 128) - every test of the fit path at small n, per-step timing old / new
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_parity.py -q -k "refinement_contract or readme or reference_test or single_observation or optimize_suggestion or sample_matches_oracle or batched_proposals or state_file or state_rebuilds or ragged_shards or config2_sample or kept_hypers or fused_topk_mass" > gpurun_out/r2zz_tests.txt 2>&1
-echo "pytest rc=$?"; grep -E "^(FAILED|ERROR)|passed|failed|Error" gpurun_out/r2zz_tests.txt | tail -12
-python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
-timeout 300 python scripts/dev/small_sample_trace.py > gpurun_out/r2zz_small_sample_trace.txt 2>&1; grep -E "^==|wall" gpurun_out/r2zz_small_sample_trace.txt
-echo "--- per-round path"
-BX_NO_REFINE_SMALL=1 timeout 300 python scripts/dev/small_sample_trace.py > gpurun_out/r2zz_small_sample_trace_per_round.txt 2>&1; grep -E "^==|wall" gpurun_out/r2zz_small_sample_trace_per_round.txt
+timeout 900 python -m pytest tests/test_gpu_parity.py -q -x -k "posterior_fit_vs_oracle or adamw_kernel or nlml_and_gradient or golden or readme or reference_test or restarts_side or single_observation or failed_cholesky or state_rebuilds or kept_hypers or append" > gpurun_out/r2zz_fit_tests.txt 2>&1
+echo "pytest rc=$?"; grep -E "^(FAILED|ERROR)|passed|failed|Error|assert" gpurun_out/r2zz_fit_tests.txt | tail -15
+timeout 300 python scripts/dev/small_fit_time.py > gpurun_out/r2zz_small_fit_time.txt 2>&1; cat gpurun_out/r2zz_small_fit_time.txt | tail -10
+echo "--- previous paths"
+BX_NO_FIT_SWEEP=1 timeout 300 python scripts/dev/small_fit_time.py > gpurun_out/r2zz_small_fit_time_prev.txt 2>&1; cat gpurun_out/r2zz_small_fit_time_prev.txt | tail -10
