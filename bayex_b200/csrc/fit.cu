@@ -466,18 +466,21 @@ fit_small_kernel(const float* __restrict__ X, const float* __restrict__ y, int n
 // ---- n <= 128: the whole fit loop in one CTA with the matrix in REGISTERS ------------------------------------------------------
 // fit_small_kernel above keeps K in shared memory and walks a textbook Cholesky with three block barriers per column, a
 // triangular inverse on one thread per column and T^T T by dot products: it crosses over with the multi-kernel path at n = 56
-// (0.087 ms per step).  This kernel holds the lower 32 x 32 tiles of the padded matrix in the registers of 1024 threads
-// (thread (ty, tx) owns element (32 a + ty, 32 b + tx) of every tile a >= b; diagonal tiles are kept whole) and turns K
+// (0.087 ms per step).  This kernel holds the lower 32 x 32 tiles of the padded matrix in the registers of 256 threads
+// (thread (w, tx) owns rows 32 a + w + 8 r, r < 4, of column 32 b + tx of every tile a >= b; diagonal tiles are kept whole) and turns K
 // into -K^-1 IN PLACE with the symmetric sweep operator - per pivot k: A_ij -= A_ik A_kj / p, A_ik <- A_ik / p,
 // A_kk <- -1 / p with p = A_kk - one uniform rank-1 update per pivot, ONE block barrier per pivot (the pivot column
 // travels through a double-buffered shared-memory vector), no separate factorisation / inverse / product phases.  The
 // pivots are the squares of the Cholesky diagonal (gp.py:48: log det = 1/2 sum log p_k; a non-positive pivot becomes NaN
 // exactly where cholesky() would produce one); alpha = K^-1 yc, the NLML (gp.py:52-57), the gradient contraction
 //  and clip + AdamW (gp.py:99-106) follow in the same launch for all `steps`.  n^3 / 2 FMAs per step instead
-// of n^3 / 3 + n^3 / 6 + n^3 / 6, but every one of them on 1024 threads; fp32 error of K^-1 at the level of the Cholesky
+// of n^3 / 3 + n^3 / 6 + n^3 / 6, but every one of them on all threads; fp32 error of K^-1 at the level of the Cholesky
 // route (both ~ cond(K) eps).  Reductions run in a fixed order: the result does not depend on the launch.
-constexpr int SW_THREADS = 1024;
-constexpr int SW_MAX_NT = 4;  // n <= 128: tiles a thread owns NT (NT + 1) / 2 <= 10, twice that live in the gradient phase
+constexpr int SW_RPT = 4;                  // rows of every tile a thread owns
+constexpr int SW_NW = 32 / SW_RPT;         // warps: thread (w, tx) owns rows 32 a + w + SW_NW r, column 32 b + tx
+constexpr int SW_THREADS = 32 * SW_NW;     // 256: with one row per thread (1024 threads) the pivot loop was issue-bound on its
+                                           // per-warp overhead (column loads, reciprocal, fix-ups, publish): 0.44 us per pivot
+constexpr int SW_MAX_NT = 4;  // n <= 128
 __host__ __device__ constexpr int sw_e(int a, int b) { return a * (a + 1) / 2 + b; }
 
 __device__ __forceinline__ float sw_block_sum(float v, float* red) {
@@ -487,7 +490,7 @@ __device__ __forceinline__ float sw_block_sum(float v, float* red) {
   __syncthreads();
   float t = 0.f;
 #pragma unroll
-  for (int w = 0; w < SW_THREADS / 32; ++w) t += red[w];
+  for (int w = 0; w < SW_NW; ++w) t += red[w];
   return t;
 }
 
@@ -495,26 +498,27 @@ template <int NT>
 __global__ void __launch_bounds__(SW_THREADS, 1)
 fit_sweep_kernel(const float* __restrict__ X, const float* __restrict__ y, int n, int d, float* raw_g, float lr, int steps,
                  float* trace, float* gbuf_out, int grad_only) {
-  constexpr int NP = 32 * NT, NE = NT * (NT + 1) / 2;
+  constexpr int NP = 32 * NT, NE = NT * (NT + 1) / 2, R = SW_RPT, NW = SW_NW;
   extern __shared__ float sm[];
-  const int d4 = round_up(d, 4), P = d + 2, tid = threadIdx.x, ty = tid >> 5, tx = tid & 31;
+  const int d4 = round_up(d, 4), P = d + 2, tid = threadIdx.x, w = tid >> 5, tx = tid & 31;
   float* Ut = sm;                 // [d4][NP] scaled observations, dimension-major
   float* yc = Ut + d4 * NP;       // [NP]
   float* al = yc + NP;            // [NP]
   float* cb = al + NP;            // [2][NP] pivot column, double-buffered
-  float* part = cb + 2 * NP;      // [32][NP] cross-warp partial sums
-  float* raw = part + 32 * NP;    // [P]
+  float* part = cb + 2 * NP;      // [NW][NP] cross-warp partial sums (also: the pivots)
+  float* raw = part + NW * NP;    // [P]
   float* grad = raw + P;          // [P]
   float* dsum = grad + P;         // [d4] per-dimension gradient sums
   float* scale = dsum + d4;       // [d4]
   float* mom = scale + d4;        // [2P] Adam moments
-  __shared__ float red[SW_THREADS / 32];
-  __shared__ float red4[4][SW_THREADS / 32];
+  __shared__ float red[NW];
+  __shared__ float red4[4][NW];
   __shared__ float sc[8];         // amp, noise+jitter
   for (int p = tid; p < P; p += SW_THREADS) { raw[p] = raw_g[p]; mom[p] = 0.f; mom[P + p] = 0.f; }
-  const float ysum = sw_block_sum(tid < n ? y[tid] : 0.f, red);  // n <= 128 < SW_THREADS
-  const float ymean = ysum / (float)n;
-  if (tid < NP) yc[tid] = (tid < n) ? y[tid] - ymean : 0.f;
+  float ysp = 0.f;
+  for (int i = tid; i < n; i += SW_THREADS) ysp += y[i];
+  const float ymean = sw_block_sum(ysp, red) / (float)n;
+  for (int i = tid; i < NP; i += SW_THREADS) yc[i] = (i < n) ? y[i] - ymean : 0.f;
   __syncthreads();
 
   for (int step = 0; step <= steps; ++step) {
@@ -531,121 +535,174 @@ fit_sweep_kernel(const float* __restrict__ X, const float* __restrict__ y, int n
     __syncthreads();
     const float amp = sc[0];
     // Gram (gp.py:46) into registers; identity on the padding
-    float A[NE];
+    float A[NE][R];
 #pragma unroll
-    for (int e = 0; e < NE; ++e) A[e] = 0.f;
+    for (int e = 0; e < NE; ++e)
+#pragma unroll
+      for (int r = 0; r < R; ++r) A[e][r] = 0.f;
     for (int k = 0; k < d4; ++k) {
-      float ui[NT], uj[NT];
+      float ui[NT][R], uj[NT];
 #pragma unroll
-      for (int a = 0; a < NT; ++a) { ui[a] = Ut[k * NP + 32 * a + ty]; uj[a] = Ut[k * NP + 32 * a + tx]; }
+      for (int a = 0; a < NT; ++a) {
+        uj[a] = Ut[k * NP + 32 * a + tx];
+#pragma unroll
+        for (int r = 0; r < R; ++r) ui[a][r] = Ut[k * NP + 32 * a + w + NW * r];
+      }
 #pragma unroll
       for (int a = 0; a < NT; ++a)
 #pragma unroll
-        for (int b = 0; b <= a; ++b) { const float df = ui[a] - uj[b]; A[sw_e(a, b)] = fmaf(df, df, A[sw_e(a, b)]); }
+        for (int b = 0; b <= a; ++b)
+#pragma unroll
+          for (int r = 0; r < R; ++r) { const float df = ui[a][r] - uj[b]; A[sw_e(a, b)][r] = fmaf(df, df, A[sw_e(a, b)][r]); }
     }
 #pragma unroll
     for (int a = 0; a < NT; ++a)
 #pragma unroll
-      for (int b = 0; b <= a; ++b) {
-        const int i = 32 * a + ty, j = 32 * b + tx;
-        A[sw_e(a, b)] = (i < n && j < n) ? amp * exp2f(-A[sw_e(a, b)]) + (i == j ? sc[1] : 0.f) : (i == j ? 1.f : 0.f);
-      }
+      for (int b = 0; b <= a; ++b)
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const int i = 32 * a + w + NW * r, j = 32 * b + tx;
+          A[sw_e(a, b)][r] = (i < n && j < n) ? amp * exp2f(-A[sw_e(a, b)][r]) + (i == j ? sc[1] : 0.f) : (i == j ? 1.f : 0.f);
+        }
     // sweep every valid pivot: A -> -K^-1
 #pragma unroll
     for (int kb = 0; kb < NT; ++kb) {
       const int kmax = min(32, n - 32 * kb);
       for (int kx = 0; kx < kmax; ++kx) {
         const int k = 32 * kb + kx;
+        const int wk = kx % NW, rk = kx / NW;  // row k belongs to warp wk, register slot rk
         float* buf = cb + (k & 1) * NP;
         if (tx == kx) {  // column k: the diagonal tile's rows and the tiles below it
 #pragma unroll
-          for (int a = kb; a < NT; ++a) buf[32 * a + ty] = A[sw_e(a, kb)];
-        }
-        if (ty == kx) {  // row k (= column k above the diagonal tile)
+          for (int a = kb; a < NT; ++a)
 #pragma unroll
-          for (int b = 0; b < kb; ++b) buf[32 * b + tx] = A[sw_e(kb, b)];
+            for (int r = 0; r < R; ++r) buf[32 * a + w + NW * r] = A[sw_e(a, kb)][r];
+        }
+        if (w == wk) {  // row k (= column k above the diagonal tile): warp-uniform
+#pragma unroll
+          for (int b = 0; b < kb; ++b) {
+            float v = A[sw_e(kb, b)][0];
+#pragma unroll
+            for (int r = 1; r < R; ++r) v = (rk == r) ? A[sw_e(kb, b)][r] : v;
+            buf[32 * b + tx] = v;
+          }
         }
         __syncthreads();
         float p = buf[k];
         if (!(p > 0.f)) p = CUDART_NAN_F;  // gp.py:48: cholesky() of a non-PD matrix gives NaN, and so does everything after
         const float ip = __frcp_rn(p);     // correctly rounded, without the division's slow path: it heads every pivot's chain
         if (tid == 0) part[k] = p;         // the logarithms are taken after the loop, one pivot per thread
-        float ci[NT], cjp[NT];
+        float ci[NT][R], cjp[NT];
 #pragma unroll
-        for (int a = 0; a < NT; ++a) { ci[a] = buf[32 * a + ty]; cjp[a] = buf[32 * a + tx] * ip; }
+        for (int a = 0; a < NT; ++a) {
+          cjp[a] = buf[32 * a + tx] * ip;
+#pragma unroll
+          for (int r = 0; r < R; ++r) ci[a][r] = buf[32 * a + w + NW * r];
+        }
 #pragma unroll
         for (int a = 0; a < NT; ++a)
 #pragma unroll
-          for (int b = 0; b <= a; ++b) A[sw_e(a, b)] = fmaf(-ci[a], cjp[b], A[sw_e(a, b)]);
+          for (int b = 0; b <= a; ++b)
 #pragma unroll
-        for (int a = kb + 1; a < NT; ++a)
-          if (tx == kx) A[sw_e(a, kb)] = ci[a] * ip;
+            for (int r = 0; r < R; ++r) A[sw_e(a, b)][r] = fmaf(-ci[a][r], cjp[b], A[sw_e(a, b)][r]);
+        if (tx == kx) {  // column k below the diagonal tile
 #pragma unroll
-        for (int b = 0; b < kb; ++b)
-          if (ty == kx) A[sw_e(kb, b)] = cjp[b];
-        if (ty == kx && tx == kx) A[sw_e(kb, kb)] = -ip;
-        else if (ty == kx) A[sw_e(kb, kb)] = cjp[kb];
-        else if (tx == kx) A[sw_e(kb, kb)] = ci[kb] * ip;
+          for (int a = kb + 1; a < NT; ++a)
+#pragma unroll
+            for (int r = 0; r < R; ++r) A[sw_e(a, kb)][r] = ci[a][r] * ip;
+        }
+        if (w == wk) {   // row k left of the diagonal tile
+#pragma unroll
+          for (int b = 0; b < kb; ++b)
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+              if (rk == r) A[sw_e(kb, b)][r] = cjp[b];
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {  // the diagonal tile
+          const bool ik = (w == wk) && (rk == r), jk = (tx == kx);
+          if (ik && jk) A[sw_e(kb, kb)][r] = -ip;
+          else if (ik) A[sw_e(kb, kb)][r] = cjp[kb];
+          else if (jk) A[sw_e(kb, kb)][r] = ci[kb][r] * ip;
+        }
       }
     }
     __syncthreads();
-    const float logdet = 0.5f * sw_block_sum(tid < n ? logf(part[tid]) : 0.f, red);  // (ends with every thread past its reads of part)
+    float ldp = 0.f;
+    for (int i = tid; i < n; i += SW_THREADS) ldp += logf(part[i]);
+    const float logdet = 0.5f * sw_block_sum(ldp, red);  // (ends with every thread past its reads of part)
     // alpha = K^-1 yc (gp.py:49) with K^-1 = -A: row sums inside the warp, transposed contributions of the off-diagonal
     // tiles through per-warp partials added in warp order
 #pragma unroll
-    for (int a = 0; a < NT; ++a) {
-      float r = 0.f;
+    for (int a = 0; a < NT; ++a)
 #pragma unroll
-      for (int b = 0; b <= a; ++b) r = fmaf(-A[sw_e(a, b)], yc[32 * b + tx], r);
-      r = warp_sum(r);
-      if (tx == 0) al[32 * a + ty] = r;
-    }
+      for (int r = 0; r < R; ++r) {
+        float t = 0.f;
+#pragma unroll
+        for (int b = 0; b <= a; ++b) t = fmaf(-A[sw_e(a, b)][r], yc[32 * b + tx], t);
+        t = warp_sum(t);
+        if (tx == 0) al[32 * a + w + NW * r] = t;
+      }
 #pragma unroll
     for (int b = 0; b < NT; ++b) {
       float t = 0.f;
 #pragma unroll
-      for (int a = b + 1; a < NT; ++a) t = fmaf(-A[sw_e(a, b)], yc[32 * a + ty], t);
-      part[ty * NP + 32 * b + tx] = t;
+      for (int a = b + 1; a < NT; ++a)
+#pragma unroll
+        for (int r = 0; r < R; ++r) t = fmaf(-A[sw_e(a, b)][r], yc[32 * a + w + NW * r], t);
+      part[w * NP + 32 * b + tx] = t;
     }
     __syncthreads();
-    if (tid < NP) {
-      float t = al[tid];
-#pragma unroll 8
-      for (int w = 0; w < 32; ++w) t += part[w * NP + tid];
-      al[tid] = t;
+    for (int j = tid; j < NP; j += SW_THREADS) {
+      float t = al[j];
+#pragma unroll
+      for (int q = 0; q < NW; ++q) t += part[q * NP + j];
+      al[j] = t;
     }
     __syncthreads();
-    const float quad = sw_block_sum(tid < NP ? yc[tid] * al[tid] : 0.f, red);
+    float qp = 0.f;
+    for (int i = tid; i < NP; i += SW_THREADS) qp = fmaf(yc[i], al[i], qp);
+    const float quad = sw_block_sum(qp, red);
     const float la = logf(amp);
     const float nlml = 0.5f * quad + logdet + ((float)n * 0.5f) * kLog2Pi + (-0.5f * kLog2Pi - la - la * la);  // gp.py:52-57
     // weights W_ij C_ij (x2 off the diagonal, lower triangle only) into A; trace and amplitude sums
-    float S[NE];
+    float S[NE][R];
 #pragma unroll
-    for (int e = 0; e < NE; ++e) S[e] = 0.f;
+    for (int e = 0; e < NE; ++e)
+#pragma unroll
+      for (int r = 0; r < R; ++r) S[e][r] = 0.f;
     for (int k = 0; k < d4; ++k) {
-      float ui[NT], uj[NT];
+      float ui[NT][R], uj[NT];
 #pragma unroll
-      for (int a = 0; a < NT; ++a) { ui[a] = Ut[k * NP + 32 * a + ty]; uj[a] = Ut[k * NP + 32 * a + tx]; }
+      for (int a = 0; a < NT; ++a) {
+        uj[a] = Ut[k * NP + 32 * a + tx];
+#pragma unroll
+        for (int r = 0; r < R; ++r) ui[a][r] = Ut[k * NP + 32 * a + w + NW * r];
+      }
 #pragma unroll
       for (int a = 0; a < NT; ++a)
 #pragma unroll
-        for (int b = 0; b <= a; ++b) { const float df = ui[a] - uj[b]; S[sw_e(a, b)] = fmaf(df, df, S[sw_e(a, b)]); }
+        for (int b = 0; b <= a; ++b)
+#pragma unroll
+          for (int r = 0; r < R; ++r) { const float df = ui[a][r] - uj[b]; S[sw_e(a, b)][r] = fmaf(df, df, S[sw_e(a, b)][r]); }
     }
     float trp = 0.f, sap = 0.f;
 #pragma unroll
     for (int a = 0; a < NT; ++a)
 #pragma unroll
-      for (int b = 0; b <= a; ++b) {
-        const int i = 32 * a + ty, j = 32 * b + tx;
-        const float w = -A[sw_e(a, b)] - al[i] * al[j];
-        float f = 2.f;
-        if (a == b) f = (tx < ty) ? 2.f : (tx == ty ? 1.f : 0.f);  // a diagonal tile holds both triangles: count the lower one
-        if (!(i < n && j < n)) f = 0.f;
-        const float wc = (f != 0.f) ? w * exp2f(-S[sw_e(a, b)]) * f : 0.f;
-        A[sw_e(a, b)] = wc;
-        if (a == b && tx == ty && i < n) trp += w;
-        sap += wc;
-      }
+      for (int b = 0; b <= a; ++b)
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const int li = w + NW * r, i = 32 * a + li, j = 32 * b + tx;
+          const float wgt = -A[sw_e(a, b)][r] - al[i] * al[j];
+          float f = 2.f;
+          if (a == b) f = (tx < li) ? 2.f : (tx == li ? 1.f : 0.f);  // a diagonal tile holds both triangles: count the lower one
+          if (!(i < n && j < n)) f = 0.f;
+          const float wc = (f != 0.f) ? wgt * exp2f(-S[sw_e(a, b)][r]) * f : 0.f;
+          A[sw_e(a, b)][r] = wc;
+          if (a == b && tx == li && i < n) trp += wgt;
+          sap += wc;
+        }
     const float tr = sw_block_sum(trp, red);
     const float samp = sw_block_sum(sap, red);
     // per-dimension sums, four dimensions per reduction pass
@@ -654,25 +711,31 @@ fit_sweep_kernel(const float* __restrict__ X, const float* __restrict__ y, int n
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const int k = k0 + q;  // < d4
-        float ui[NT], uj[NT];
+        float ui[NT][R], uj[NT];
 #pragma unroll
-        for (int a = 0; a < NT; ++a) { ui[a] = Ut[k * NP + 32 * a + ty]; uj[a] = Ut[k * NP + 32 * a + tx]; }
+        for (int a = 0; a < NT; ++a) {
+          uj[a] = Ut[k * NP + 32 * a + tx];
+#pragma unroll
+          for (int r = 0; r < R; ++r) ui[a][r] = Ut[k * NP + 32 * a + w + NW * r];
+        }
 #pragma unroll
         for (int a = 0; a < NT; ++a)
 #pragma unroll
-          for (int b = 0; b <= a; ++b) { const float df = ui[a] - uj[b]; s4[q] = fmaf(A[sw_e(a, b)], df * df, s4[q]); }
+          for (int b = 0; b <= a; ++b)
+#pragma unroll
+            for (int r = 0; r < R; ++r) { const float df = ui[a][r] - uj[b]; s4[q] = fmaf(A[sw_e(a, b)][r], df * df, s4[q]); }
         s4[q] = warp_sum(s4[q]);
       }
       __syncthreads();
       if (tx == 0) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) red4[q][ty] = s4[q];
+        for (int q = 0; q < 4; ++q) red4[q][w] = s4[q];
       }
       __syncthreads();
       if (tid < 4) {
         float t = 0.f;
 #pragma unroll
-        for (int w = 0; w < SW_THREADS / 32; ++w) t += red4[tid][w];
+        for (int q = 0; q < NW; ++q) t += red4[tid][q];
         dsum[k0 + tid] = t;
       }
     }
@@ -717,7 +780,7 @@ fit_sweep_kernel(const float* __restrict__ X, const float* __restrict__ y, int n
 
 static size_t fit_sweep_smem(int n, int d) {
   const int np = round_up(n, 32), d4 = round_up(d, 4), P = d + 2;
-  return sizeof(float) * ((size_t)d4 * np + 4 * (size_t)np + 32 * (size_t)np + 4 * P + 2 * d4);
+  return sizeof(float) * ((size_t)d4 * np + 4 * (size_t)np + SW_NW * (size_t)np + 4 * P + 2 * d4);
 }
 static bool fit_sweep_ok(int n) {
   static const bool off = getenv("BX_NO_FIT_SWEEP") != nullptr;
