@@ -179,7 +179,8 @@ def test_multidim_golden(golden):
     assert_close(got, golden["md_nlmlgrad_fd_f64"], rtol=2e-3, what="grad_fun")
 
 
-@pytest.mark.parametrize("n,d", [(100, 3), (512, 6), (1000, 8), (2048, 10)])
+# n <= 128: the register-resident sweep kernel, one case per tile count (NT = 1 .. 4) and both edges of its range
+@pytest.mark.parametrize("n,d", [(1, 2), (33, 1), (70, 2), (96, 3), (128, 5), (129, 5), (100, 3), (512, 6), (1000, 8), (2048, 10)])
 def test_nlml_and_gradient_vs_oracle(n, d):
     X, Y, raw, P = make_problem(n, d, seed=n + d)
     post = engine.Posterior(X, Y, raw, want_tc=False)
